@@ -1,0 +1,801 @@
+// libchi: C ABI (include/chi.h) over the sm_100a kernels in kernels.cuh.
+// Host-side logic only: argument checks, device workspace, launch geometry,
+// host<->device copies.  There is no CPU compute path in this file.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/chi.h"
+#include "kernels.cuh"
+
+using namespace chi;
+
+namespace {
+
+std::string g_create_error;
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  double* d() const { return (double*)p; }
+};
+
+struct DevDataset {
+  int S = 0, nb = 0;
+  bool has_offset = false;
+  Buf vax, yeff, wgt, basis, offset;
+  void release() { vax.release(); yeff.release(); wgt.release(); basis.release(); offset.release(); }
+};
+
+}  // namespace
+
+struct chi_handle {
+  chi_config cfg;
+  MapCfg map;
+  int device = 0;
+  int n_sm = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_pending = false;
+  float kernel_ms = 0.f;
+  bool has_e = false, has_a = false, spectra_set = false;
+  int n_sl = 0;
+  DevDataset e, a;
+  Buf lconst;
+  // workspace for host entry points
+  Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca, w_gbe, w_gba, w_mue, w_mua, w_misc[8];
+  // internal workspace
+  Buf cc, mom_e, mom_a;
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(chi_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(h, _e == cudaErrorMemoryAllocation ? CHI_ENOMEM : CHI_ECUDA,            \
+                  std::string(#call) + ": " + cudaGetErrorString(_e));                    \
+  } while (0)
+
+bool kind_has_emission(int m) {
+  return m == CHI_MODEL_EMISSION || m == CHI_MODEL_EMISSION_ABSORPTION ||
+         m == CHI_MODEL_EMISSION_PHYSICAL || m == CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL;
+}
+bool kind_has_absorption(int m) {
+  return m == CHI_MODEL_ABSORPTION || m == CHI_MODEL_EMISSION_ABSORPTION ||
+         m == CHI_MODEL_ABSORPTION_PHYSICAL || m == CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL;
+}
+
+int em_record(const chi_handle* h) { return 1 + h->e.nb + h->cfg.n_clouds * (h->cfg.lorentzian ? 8 : 5); }
+int ab_record(const chi_handle* h) { return 1 + h->a.nb + h->cfg.n_clouds * (h->cfg.lorentzian ? 6 : 3); }
+
+// channel chunking: enough warps to fill the machine when B is small
+void pick_chunks(const chi_handle* h, int64_t B, int S, int* n_chunks, int* chunk_len) {
+  const int64_t target = (int64_t)h->n_sm * 16;  // warp items wanted per launch
+  int64_t want = (target + B - 1) / B;
+  int max_chunks = std::max(1, S / 128);  // at least 4 channel iterations per lane
+  int nc = (int)std::min<int64_t>(std::max<int64_t>(want, 1), max_chunks);
+  int len = (S + nc - 1) / nc;
+  len = (len + 31) / 32 * 32;
+  *chunk_len = len;
+  *n_chunks = (S + len - 1) / len;
+}
+
+template <template <int, bool> class Launcher, class... A>
+int dispatch_np(int N, bool pv, A... args) {
+  switch (N * 2 + (pv ? 1 : 0)) {
+#define CASE(n)                                        \
+  case (n)*2: return Launcher<n, false>::run(args...); \
+  case (n)*2 + 1: return Launcher<n, true>::run(args...);
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  return -1;
+}
+
+template <int N, bool PV>
+struct LaunchEm {
+  static int run(const ChanArgs& a, cudaStream_t st) {
+    int64_t items = a.B * a.n_chunks;
+    unsigned grid = (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
+    k_moments_em<N, PV><<<grid, CHI_BLOCK, 0, st>>>(a);
+    return 0;
+  }
+};
+template <int N, bool PV>
+struct LaunchAb {
+  static int run(const ChanArgs& a, cudaStream_t st) {
+    int64_t items = a.B * a.n_chunks;
+    unsigned grid = (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
+    k_moments_abs<N, PV><<<grid, CHI_BLOCK, 0, st>>>(a);
+    return 0;
+  }
+};
+
+#define MODEL_SWITCH(model, STMT)                                                                 \
+  switch (model) {                                                                                \
+    case CHI_MODEL_PHYSICS: { constexpr int M = CHI_MODEL_PHYSICS; STMT; } break;                 \
+    case CHI_MODEL_ABSORPTION: { constexpr int M = CHI_MODEL_ABSORPTION; STMT; } break;           \
+    case CHI_MODEL_EMISSION: { constexpr int M = CHI_MODEL_EMISSION; STMT; } break;               \
+    case CHI_MODEL_EMISSION_ABSORPTION: { constexpr int M = CHI_MODEL_EMISSION_ABSORPTION; STMT; } break; \
+    case CHI_MODEL_ABSORPTION_PHYSICAL: { constexpr int M = CHI_MODEL_ABSORPTION_PHYSICAL; STMT; } break; \
+    case CHI_MODEL_EMISSION_PHYSICAL: { constexpr int M = CHI_MODEL_EMISSION_PHYSICAL; STMT; } break;     \
+    case CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL: { constexpr int M = CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL; STMT; } break; \
+  }
+
+int launch_cloud_map(chi_handle* h, int64_t B, const double* theta) {
+  const int N = h->cfg.n_clouds;
+  CK(h->cc.ensure((size_t)B * N * CHI_CC_STRIDE * sizeof(double)));
+  unsigned grid = (unsigned)((B * N + 127) / 128);
+  MODEL_SWITCH(h->cfg.model, (k_cloud_map<M><<<grid, 128, 0, h->stream>>>(h->map, B, N, theta, h->cc.d())));
+  h->launches++;
+  CK(cudaGetLastError());
+  return CHI_OK;
+}
+
+// moments (+ optional logp) + epilogue; gbar_* != null selects the VJP mode
+int run_backward(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                 const int32_t* sl, const double* gbar_e, const double* gbar_a, bool vjp, double* logp,
+                 double* grad, double* gce, double* gca) {
+  const int N = h->cfg.n_clouds;
+  const bool pv = h->cfg.lorentzian != 0;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int rc = launch_cloud_map(h, B, theta);
+  if (rc) return rc;
+
+  EpiArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.B = B; ea.N = N; ea.pv = pv;
+  ea.theta = theta; ea.sl = sl; ea.logp = logp; ea.grad = grad; ea.gcoeff_e = gce; ea.gcoeff_a = gca;
+  ea.lconst = vjp ? nullptr : h->lconst.d();
+
+  // in VJP mode a dataset without cotangent contributes nothing
+  const bool do_e = h->has_e && (!vjp || gbar_e);
+  const bool do_a = h->has_a && (!vjp || gbar_a);
+  if (do_e) {
+    ChanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp;
+    pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
+    a.mom_stride = em_record(h);
+    CK(h->mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
+    a.vax = h->e.vax.d(); a.yeff = h->e.yeff.d(); a.wgt = h->e.wgt.d(); a.basis = h->e.basis.d();
+    a.coeff = ce; a.sl = sl; a.gbar = vjp ? gbar_e : nullptr; a.cc = h->cc.d(); a.mom = h->mom_e.d();
+    if (dispatch_np<LaunchEm>(N, pv, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    h->launches++;
+    CK(cudaGetLastError());
+    ea.has_e = 1; ea.nb_e = a.n_base; ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride;
+    ea.mom_e = h->mom_e.d();
+  }
+  if (do_a) {
+    ChanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.S = h->a.S; a.n_base = h->a.nb; a.bg = 0.0;
+    pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
+    a.mom_stride = ab_record(h);
+    CK(h->mom_a.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
+    a.vax = h->a.vax.d(); a.yeff = h->a.yeff.d(); a.wgt = h->a.wgt.d(); a.basis = h->a.basis.d();
+    a.coeff = ca; a.sl = sl; a.gbar = vjp ? gbar_a : nullptr; a.cc = h->cc.d(); a.mom = h->mom_a.d();
+    if (dispatch_np<LaunchAb>(N, pv, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    h->launches++;
+    CK(cudaGetLastError());
+    ea.has_a = 1; ea.nb_a = a.n_base; ea.chunks_a = a.n_chunks; ea.stride_a = a.mom_stride;
+    ea.mom_a = h->mom_a.d();
+  }
+  // baseline-coefficient gradients of a dataset that did not run are zero
+  if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), h->stream));
+  if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), h->stream));
+
+  unsigned grid = (unsigned)((B * N + 127) / 128);
+  MODEL_SWITCH(h->cfg.model, (k_epilogue<M><<<grid, 128, 0, h->stream>>>(h->map, ea)));
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->ev_pending = true;
+  return CHI_OK;
+}
+
+int run_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                double* mu_e, double* mu_a) {
+  const int N = h->cfg.n_clouds;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int rc = launch_cloud_map(h, B, theta);
+  if (rc) return rc;
+  SpecArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.pv = h->cfg.lorentzian != 0; a.cc = h->cc.d();
+  if (mu_e && h->has_e) {
+    a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp; a.vax = h->e.vax.d();
+    a.basis = h->e.basis.d(); a.offset = h->e.has_offset ? h->e.offset.d() : nullptr;
+    a.coeff = ce; a.mu = mu_e; a.emission = 1;
+    k_spectra<true><<<(unsigned)B, 256, 0, h->stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  if (mu_a && h->has_a) {
+    a.S = h->a.S; a.n_base = h->a.nb; a.bg = 0.0; a.vax = h->a.vax.d();
+    a.basis = h->a.basis.d(); a.offset = h->a.has_offset ? h->a.offset.d() : nullptr;
+    a.coeff = ca; a.mu = mu_a; a.emission = 0;
+    k_spectra<false><<<(unsigned)B, 256, 0, h->stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->ev_pending = true;
+  return CHI_OK;
+}
+
+int check_model_call(chi_handle* h, int64_t B, const double* theta) {
+  if (!h) return CHI_EINVAL;
+  if (B < 0 || (B > 0 && !theta)) return fail(h, CHI_EINVAL, "theta is NULL or B < 0");
+  if (!h->spectra_set) return fail(h, CHI_ESTATE, "chi_set_spectra has not been called");
+  return CHI_OK;
+}
+
+int upload_dataset(chi_handle* h, DevDataset& d, const chi_dataset* src, int n_sl, double* lconst_host,
+                   const char* name) {
+  const int S = src->n_channels;
+  if (S < 2) return fail(h, CHI_EINVAL, std::string(name) + ": need at least 2 channels (physics.py:294)");
+  if (!src->spectral || !src->brightness || !src->noise)
+    return fail(h, CHI_EINVAL, std::string(name) + ": spectral/brightness/noise must be non-NULL");
+  if (src->n_baseline < 0 || src->n_baseline > CHI_MAX_BASELINE)
+    return fail(h, CHI_EINVAL, std::string(name) + ": n_baseline out of range");
+  if (src->n_baseline > 0 && !src->basis) return fail(h, CHI_EINVAL, std::string(name) + ": basis is NULL");
+  d.S = S;
+  d.nb = src->n_baseline;
+  d.has_offset = src->offset != nullptr;
+  std::vector<double> yeff((size_t)n_sl * S), wgt((size_t)n_sl * S);
+  const double half_log_2pi = 0.5 * log(2.0 * M_PI);
+  for (int i = 0; i < n_sl; ++i) {
+    double lc = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const double sig = src->noise[(size_t)i * S + s];
+      if (!(sig > 0.0)) return fail(h, CHI_EINVAL, std::string(name) + ": noise must be > 0");
+      yeff[(size_t)i * S + s] = src->brightness[(size_t)i * S + s] - (src->offset ? src->offset[s] : 0.0);
+      wgt[(size_t)i * S + s] = 1.0 / (sig * sig);
+      lc += -log(sig) - half_log_2pi;  // pm.Normal logp normalisation
+    }
+    lconst_host[i] += lc;
+  }
+  CK(d.vax.ensure(S * sizeof(double)));
+  CK(d.yeff.ensure(yeff.size() * sizeof(double)));
+  CK(d.wgt.ensure(wgt.size() * sizeof(double)));
+  CK(d.basis.ensure(std::max<size_t>(1, (size_t)d.nb * S) * sizeof(double)));
+  CK(d.offset.ensure(S * sizeof(double)));
+  CK(cudaMemcpy(d.vax.p, src->spectral, S * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.yeff.p, yeff.data(), yeff.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.wgt.p, wgt.data(), wgt.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (d.nb > 0) CK(cudaMemcpy(d.basis.p, src->basis, (size_t)d.nb * S * sizeof(double), cudaMemcpyHostToDevice));
+  if (src->offset) CK(cudaMemcpy(d.offset.p, src->offset, S * sizeof(double), cudaMemcpyHostToDevice));
+  return CHI_OK;
+}
+
+double channel_fwhm2(const double* v) {
+  // physics.py:294-295
+  const double channel_size = fabs(v[1] - v[0]);
+  const double channel_fwhm = 4.0 * log(2.0) * channel_size / M_PI;
+  return channel_fwhm * channel_fwhm;
+}
+
+// sub-batch size of the host entry points
+int64_t host_sub_batch(const chi_handle* h, size_t bytes_per_draw) {
+  const size_t budget = (size_t)1 << 30;
+  int64_t n = (int64_t)(budget / std::max<size_t>(bytes_per_draw, 1));
+  return std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)1 << 18));
+}
+
+int finish_timing(chi_handle* h) {
+  if (h->ev_pending) {
+    CK(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->kernel_ms += ms;
+    h->ev_pending = false;
+  }
+  return CHI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int chi_version(void) { return CHI_VERSION; }
+
+int chi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+  }
+  return ok;
+}
+
+const char* chi_last_error(const chi_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int chi_create(chi_handle** out, int device, const chi_config* cfg) {
+  chi_handle* h = nullptr;
+  if (!out || !cfg) return fail(h, CHI_EINVAL, "chi_create: NULL argument");
+  *out = nullptr;
+  if (cfg->model < CHI_MODEL_PHYSICS || cfg->model > CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL)
+    return fail(h, CHI_EINVAL, "chi_create: unknown model kind");
+  if (cfg->n_clouds < 1 || cfg->n_clouds > CHI_MAX_CLOUDS)
+    return fail(h, CHI_EINVAL, "chi_create: n_clouds must be in 1..CHI_MAX_CLOUDS");
+  if (cfg->dtype != 0) return fail(h, CHI_EINVAL, "chi_create: only dtype 0 (fp64) is implemented");
+  if (cfg->model >= CHI_MODEL_ABSORPTION_PHYSICAL && !(cfg->depth_nth_fwhm_power != 0.0))
+    return fail(h, CHI_EINVAL, "chi_create: depth_nth_fwhm_power must be non-zero");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(h, CHI_ENODEV, std::string("chi_create: no CUDA device (") + cudaGetErrorString(e) +
+                                   "); libchi has no CPU fallback");
+  if (device < 0 || device >= n) return fail(h, CHI_EINVAL, "chi_create: device index out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(h, CHI_ECUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(h, CHI_ENODEV, std::string("chi_create: device '") + prop.name +
+                                   "' is not sm_100; libchi is built for sm_100a only and has no fallback");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(h, CHI_ECUDA, cudaGetErrorString(e));
+  h = new chi_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->n_sm = prop.multiProcessorCount;
+  const int m = cfg->model;
+  h->has_e = (m == CHI_MODEL_PHYSICS) ? cfg->has_emission != 0 : kind_has_emission(m);
+  h->has_a = (m == CHI_MODEL_PHYSICS) ? cfg->has_absorption != 0 : kind_has_absorption(m);
+  MapCfg& mc = h->map;
+  memset(&mc, 0, sizeof(mc));
+  mc.model = m;
+  mc.lorentzian = cfg->lorentzian != 0;
+  mc.free_weight = cfg->free_weight != 0;
+  mc.has_e = h->has_e;
+  mc.has_a = h->has_a;
+  mc.bg_temp = cfg->bg_temp;
+  mc.inv_power = (cfg->depth_nth_fwhm_power != 0.0) ? 1.0 / cfg->depth_nth_fwhm_power : 0.0;  // physics.py:188
+  mc.prior_fwhm2 = cfg->prior_fwhm2;
+  mc.pv0 = cfg->prior_velocity[0]; mc.pv1 = cfg->prior_velocity[1];
+  mc.pn0 = cfg->prior_log10_nHI[0]; mc.pn1 = cfg->prior_log10_nHI[1];
+  mc.pa0 = cfg->prior_log10_n_alpha[0]; mc.pa1 = cfg->prior_log10_n_alpha[1];
+  mc.prior_fwhm_L = cfg->prior_fwhm_L;
+  mc.prior_amp = cfg->prior_amplitude;
+  mc.const_G = sqrt(2.0 * M_PI) / (2.0 * sqrt(2.0 * log(2.0)));  // emission_model.py:127
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, CHI_ECUDA, "chi_create: stream/event creation failed");
+  }
+  *out = h;
+  return CHI_OK;
+}
+
+void chi_destroy(chi_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->e.release(); h->a.release(); h->lconst.release();
+  Buf* bufs[] = {&h->w_theta, &h->w_ce, &h->w_ca, &h->w_sl, &h->w_logp, &h->w_grad, &h->w_gce, &h->w_gca,
+                 &h->w_gbe, &h->w_gba, &h->w_mue, &h->w_mua, &h->cc, &h->mom_e, &h->mom_a};
+  for (Buf* b : bufs) b->release();
+  for (Buf& b : h->w_misc) b.release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void* chi_stream(chi_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int chi_synchronize(chi_handle* h) {
+  if (!h) return CHI_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return CHI_OK;
+}
+
+int chi_host_alloc(void** out, size_t bytes) {
+  if (!out) return CHI_EINVAL;
+  cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("chi_host_alloc: ") + cudaGetErrorString(e);
+    return CHI_ENOMEM;
+  }
+  return CHI_OK;
+}
+
+int chi_host_free(void* p) {
+  if (!p) return CHI_OK;
+  return cudaFreeHost(p) == cudaSuccess ? CHI_OK : CHI_ECUDA;
+}
+
+int chi_set_spectra(chi_handle* h, int n_sightlines, const chi_dataset* emission,
+                    const chi_dataset* absorption) {
+  if (!h) return CHI_EINVAL;
+  if (n_sightlines < 1) return fail(h, CHI_EINVAL, "chi_set_spectra: n_sightlines must be >= 1");
+  CK(cudaSetDevice(h->device));
+  const bool got_e = emission && emission->n_channels > 0;
+  const bool got_a = absorption && absorption->n_channels > 0;
+  if (h->has_e && !got_e) return fail(h, CHI_EINVAL, "chi_set_spectra: model needs an emission dataset");
+  if (h->has_a && !got_a) return fail(h, CHI_EINVAL, "chi_set_spectra: model needs an absorption dataset");
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<double> lconst(n_sightlines, 0.0);
+  if (h->has_e) {
+    int rc = upload_dataset(h, h->e, emission, n_sightlines, lconst.data(), "emission");
+    if (rc) return rc;
+    h->map.wch2_e = channel_fwhm2(emission->spectral);
+  }
+  if (h->has_a) {
+    int rc = upload_dataset(h, h->a, absorption, n_sightlines, lconst.data(), "absorption");
+    if (rc) return rc;
+    h->map.wch2_a = channel_fwhm2(absorption->spectral);
+  }
+  CK(h->lconst.ensure(n_sightlines * sizeof(double)));
+  CK(cudaMemcpy(h->lconst.p, lconst.data(), n_sightlines * sizeof(double), cudaMemcpyHostToDevice));
+  h->n_sl = n_sightlines;
+  h->spectra_set = true;
+  return CHI_OK;
+}
+
+// ---- physics-level ------------------------------------------------------------
+int chi_spin_temp(chi_handle* h, int64_t n, const double* tk, const double* dens, const double* na,
+                  double* out) {
+  if (!h) return CHI_EINVAL;
+  if (n < 0 || (n > 0 && (!tk || !dens || !na || !out))) return fail(h, CHI_EINVAL, "chi_spin_temp: NULL argument");
+  if (n == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  const size_t nb = (size_t)n * sizeof(double);
+  for (int i = 0; i < 4; ++i) CK(h->w_misc[i].ensure(nb));
+  CK(cudaMemcpyAsync(h->w_misc[0].p, tk, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[1].p, dens, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[2].p, na, nb, cudaMemcpyHostToDevice, h->stream));
+  k_spin_temp<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->w_misc[0].d(), h->w_misc[1].d(),
+                                                                 h->w_misc[2].d(), h->w_misc[3].d());
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->w_misc[3].p, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CHI_OK;
+}
+
+int chi_spin_temp_vjp(chi_handle* h, int64_t n, const double* tk, const double* dens, const double* na,
+                      const double* gbar, double* g_tk, double* g_dens, double* g_na) {
+  if (!h) return CHI_EINVAL;
+  if (n < 0 || (n > 0 && (!tk || !dens || !na || !gbar || !g_tk || !g_dens || !g_na)))
+    return fail(h, CHI_EINVAL, "chi_spin_temp_vjp: NULL argument");
+  if (n == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  const size_t nb = (size_t)n * sizeof(double);
+  for (int i = 0; i < 7; ++i) CK(h->w_misc[i].ensure(nb));
+  CK(cudaMemcpyAsync(h->w_misc[0].p, tk, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[1].p, dens, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[2].p, na, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[3].p, gbar, nb, cudaMemcpyHostToDevice, h->stream));
+  k_spin_temp_vjp<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+      n, h->w_misc[0].d(), h->w_misc[1].d(), h->w_misc[2].d(), h->w_misc[3].d(), h->w_misc[4].d(),
+      h->w_misc[5].d(), h->w_misc[6].d());
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(g_tk, h->w_misc[4].p, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(g_dens, h->w_misc[5].p, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(g_na, h->w_misc[6].p, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CHI_OK;
+}
+
+int chi_pseudo_voigt(chi_handle* h, int S, int N, const double* vax, const double* velocity,
+                     const double* fwhm2, const double* fwhm_L, double* out) {
+  if (!h) return CHI_EINVAL;
+  if (S < 2) return fail(h, CHI_EINVAL, "chi_pseudo_voigt: need at least 2 channels (physics.py:294)");
+  if (N < 1 || !vax || !velocity || !fwhm2 || !fwhm_L || !out)
+    return fail(h, CHI_EINVAL, "chi_pseudo_voigt: bad argument");
+  CK(cudaSetDevice(h->device));
+  CK(h->w_misc[0].ensure(S * sizeof(double)));
+  for (int i = 1; i < 4; ++i) CK(h->w_misc[i].ensure(N * sizeof(double)));
+  CK(h->w_misc[4].ensure((size_t)S * N * sizeof(double)));
+  CK(cudaMemcpyAsync(h->w_misc[0].p, vax, S * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[1].p, velocity, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[2].p, fwhm2, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[3].p, fwhm_L, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int64_t tot = (int64_t)S * N;
+  k_pseudo_voigt<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
+      S, N, h->w_misc[0].d(), h->w_misc[1].d(), h->w_misc[2].d(), h->w_misc[3].d(), h->w_misc[4].d());
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->w_misc[4].p, (size_t)S * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CHI_OK;
+}
+
+int chi_radiative_transfer(chi_handle* h, int S, int N, const double* tau, const double* tspin,
+                           const double* ff, double bg_temp, double* out) {
+  if (!h) return CHI_EINVAL;
+  if (S < 1 || N < 1 || !tau || !tspin || !ff || !out)
+    return fail(h, CHI_EINVAL, "chi_radiative_transfer: bad argument");
+  CK(cudaSetDevice(h->device));
+  CK(h->w_misc[0].ensure((size_t)S * N * sizeof(double)));
+  CK(h->w_misc[1].ensure(N * sizeof(double)));
+  CK(h->w_misc[2].ensure(N * sizeof(double)));
+  CK(h->w_misc[3].ensure(S * sizeof(double)));
+  CK(cudaMemcpyAsync(h->w_misc[0].p, tau, (size_t)S * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[1].p, tspin, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[2].p, ff, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  k_radiative_transfer<<<(S + 127) / 128, 128, 0, h->stream>>>(S, N, h->w_misc[0].d(), h->w_misc[1].d(),
+                                                              h->w_misc[2].d(), bg_temp, h->w_misc[3].d());
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->w_misc[3].p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CHI_OK;
+}
+
+// ---- model-level, device pointers ------------------------------------------------
+int chi_logp_grad_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                      const int32_t* sl, double* logp, double* grad, double* gce, double* gca) {
+  int rc = check_model_call(h, B, theta);
+  if (rc) return rc;
+  if (!logp) return fail(h, CHI_EINVAL, "chi_logp_grad: logp_out is NULL");
+  if (B == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  h->kernel_ms = 0.f;
+  return run_backward(h, B, theta, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca);
+}
+
+int chi_spectra_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                    double* mu_e, double* mu_a) {
+  int rc = check_model_call(h, B, theta);
+  if (rc) return rc;
+  if (B == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  h->kernel_ms = 0.f;
+  return run_spectra(h, B, theta, ce, ca, mu_e, mu_a);
+}
+
+int chi_spectra_vjp_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                        const double* gbar_e, const double* gbar_a, double* grad, double* gce, double* gca) {
+  int rc = check_model_call(h, B, theta);
+  if (rc) return rc;
+  if (!grad) return fail(h, CHI_EINVAL, "chi_spectra_vjp: grad_out is NULL");
+  if (B == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  h->kernel_ms = 0.f;
+  return run_backward(h, B, theta, ce, ca, nullptr, gbar_e, gbar_a, true, nullptr, grad, gce, gca);
+}
+
+// ---- model-level, host pointers ---------------------------------------------------
+int chi_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                  const int32_t* sl, double* logp, double* grad, double* gce, double* gca) {
+  int rc = check_model_call(h, B, theta);
+  if (rc) return rc;
+  if (!logp) return fail(h, CHI_EINVAL, "chi_logp_grad: logp_out is NULL");
+  CK(cudaSetDevice(h->device));
+  if (sl)
+    for (int64_t i = 0; i < B; ++i)
+      if (sl[i] < 0 || sl[i] >= h->n_sl) return fail(h, CHI_EINVAL, "chi_logp_grad: sightline index out of range");
+  const int N = h->cfg.n_clouds;
+  const size_t th_b = (size_t)CHI_NSLOT * N * sizeof(double);
+  const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
+  const int64_t sub = host_sub_batch(h, 4096);
+  h->kernel_ms = 0.f;
+  for (int64_t b0 = 0; b0 < B; b0 += sub) {
+    const int64_t nb = std::min(sub, B - b0);
+    CK(h->w_theta.ensure(nb * th_b));
+    CK(h->w_logp.ensure(nb * sizeof(double)));
+    CK(cudaMemcpyAsync(h->w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    double *d_ce = nullptr, *d_ca = nullptr, *d_grad = nullptr, *d_gce = nullptr, *d_gca = nullptr;
+    int32_t* d_sl = nullptr;
+    if (ce && nbe) {
+      CK(h->w_ce.ensure(nb * nbe * sizeof(double)));
+      CK(cudaMemcpyAsync(h->w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ce = h->w_ce.d();
+    }
+    if (ca && nba) {
+      CK(h->w_ca.ensure(nb * nba * sizeof(double)));
+      CK(cudaMemcpyAsync(h->w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ca = h->w_ca.d();
+    }
+    if (sl) {
+      CK(h->w_sl.ensure(nb * sizeof(int32_t)));
+      CK(cudaMemcpyAsync(h->w_sl.p, sl + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+      d_sl = (int32_t*)h->w_sl.p;
+    }
+    if (grad) { CK(h->w_grad.ensure(nb * th_b)); d_grad = h->w_grad.d(); }
+    if (gce && nbe) { CK(h->w_gce.ensure(nb * nbe * sizeof(double))); d_gce = h->w_gce.d(); }
+    if (gca && nba) { CK(h->w_gca.ensure(nb * nba * sizeof(double))); d_gca = h->w_gca.d(); }
+    rc = run_backward(h, nb, h->w_theta.d(), d_ce, d_ca, d_sl, nullptr, nullptr, false, h->w_logp.d(), d_grad,
+                      d_gce, d_gca);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(logp + b0, h->w_logp.p, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (d_grad) CK(cudaMemcpyAsync(grad + b0 * CHI_NSLOT * N, d_grad, nb * th_b, cudaMemcpyDeviceToHost, h->stream));
+    if (d_gce) CK(cudaMemcpyAsync(gce + b0 * nbe, d_gce, nb * nbe * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    rc = finish_timing(h);
+    if (rc) return rc;
+  }
+  return CHI_OK;
+}
+
+int chi_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                double* mu_e, double* mu_a) {
+  int rc = check_model_call(h, B, theta);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.n_clouds;
+  const size_t th_b = (size_t)CHI_NSLOT * N * sizeof(double);
+  const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
+  const int Se = h->has_e ? h->e.S : 0, Sa = h->has_a ? h->a.S : 0;
+  const int64_t sub = host_sub_batch(h, (size_t)(Se + Sa) * sizeof(double) + 4096);
+  h->kernel_ms = 0.f;
+  for (int64_t b0 = 0; b0 < B; b0 += sub) {
+    const int64_t nb = std::min(sub, B - b0);
+    CK(h->w_theta.ensure(nb * th_b));
+    CK(cudaMemcpyAsync(h->w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    double *d_ce = nullptr, *d_ca = nullptr, *d_me = nullptr, *d_ma = nullptr;
+    if (ce && nbe) {
+      CK(h->w_ce.ensure(nb * nbe * sizeof(double)));
+      CK(cudaMemcpyAsync(h->w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ce = h->w_ce.d();
+    }
+    if (ca && nba) {
+      CK(h->w_ca.ensure(nb * nba * sizeof(double)));
+      CK(cudaMemcpyAsync(h->w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ca = h->w_ca.d();
+    }
+    if (mu_e && Se) { CK(h->w_mue.ensure((size_t)nb * Se * sizeof(double))); d_me = h->w_mue.d(); }
+    if (mu_a && Sa) { CK(h->w_mua.ensure((size_t)nb * Sa * sizeof(double))); d_ma = h->w_mua.d(); }
+    rc = run_spectra(h, nb, h->w_theta.d(), d_ce, d_ca, d_me, d_ma);
+    if (rc) return rc;
+    if (d_me) CK(cudaMemcpyAsync(mu_e + b0 * Se, d_me, (size_t)nb * Se * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (d_ma) CK(cudaMemcpyAsync(mu_a + b0 * Sa, d_ma, (size_t)nb * Sa * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    rc = finish_timing(h);
+    if (rc) return rc;
+  }
+  return CHI_OK;
+}
+
+int chi_spectra_vjp(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                    const double* gbar_e, const double* gbar_a, double* grad, double* gce, double* gca) {
+  int rc = check_model_call(h, B, theta);
+  if (rc) return rc;
+  if (!grad) return fail(h, CHI_EINVAL, "chi_spectra_vjp: grad_out is NULL");
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.n_clouds;
+  const size_t th_b = (size_t)CHI_NSLOT * N * sizeof(double);
+  const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
+  const int Se = h->has_e ? h->e.S : 0, Sa = h->has_a ? h->a.S : 0;
+  const int64_t sub = host_sub_batch(h, (size_t)(Se + Sa) * sizeof(double) + 4096);
+  h->kernel_ms = 0.f;
+  for (int64_t b0 = 0; b0 < B; b0 += sub) {
+    const int64_t nb = std::min(sub, B - b0);
+    CK(h->w_theta.ensure(nb * th_b));
+    CK(h->w_grad.ensure(nb * th_b));
+    CK(cudaMemcpyAsync(h->w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    double *d_ce = nullptr, *d_ca = nullptr, *d_ge = nullptr, *d_ga = nullptr, *d_gce = nullptr, *d_gca = nullptr;
+    if (ce && nbe) {
+      CK(h->w_ce.ensure(nb * nbe * sizeof(double)));
+      CK(cudaMemcpyAsync(h->w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ce = h->w_ce.d();
+    }
+    if (ca && nba) {
+      CK(h->w_ca.ensure(nb * nba * sizeof(double)));
+      CK(cudaMemcpyAsync(h->w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ca = h->w_ca.d();
+    }
+    if (gbar_e && Se) {
+      CK(h->w_gbe.ensure((size_t)nb * Se * sizeof(double)));
+      CK(cudaMemcpyAsync(h->w_gbe.p, gbar_e + b0 * Se, (size_t)nb * Se * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ge = h->w_gbe.d();
+    }
+    if (gbar_a && Sa) {
+      CK(h->w_gba.ensure((size_t)nb * Sa * sizeof(double)));
+      CK(cudaMemcpyAsync(h->w_gba.p, gbar_a + b0 * Sa, (size_t)nb * Sa * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ga = h->w_gba.d();
+    }
+    if (gce && nbe) { CK(h->w_gce.ensure(nb * nbe * sizeof(double))); d_gce = h->w_gce.d(); }
+    if (gca && nba) { CK(h->w_gca.ensure(nb * nba * sizeof(double))); d_gca = h->w_gca.d(); }
+    rc = run_backward(h, nb, h->w_theta.d(), d_ce, d_ca, nullptr, d_ge, d_ga, true, nullptr, h->w_grad.d(), d_gce, d_gca);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(grad + b0 * CHI_NSLOT * N, h->w_grad.p, nb * th_b, cudaMemcpyDeviceToHost, h->stream));
+    if (d_gce) CK(cudaMemcpyAsync(gce + b0 * nbe, d_gce, nb * nbe * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    rc = finish_timing(h);
+    if (rc) return rc;
+  }
+  return CHI_OK;
+}
+
+int chi_deterministics(chi_handle* h, int64_t B, const double* theta, double* det_out) {
+  if (!h) return CHI_EINVAL;
+  if (B < 0 || (B > 0 && (!theta || !det_out))) return fail(h, CHI_EINVAL, "chi_deterministics: NULL argument");
+  if (B == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.n_clouds;
+  const size_t th_b = (size_t)CHI_NSLOT * N * sizeof(double), det_b = (size_t)CHI_NDET * N * sizeof(double);
+  const int64_t sub = host_sub_batch(h, 4096);
+  for (int64_t b0 = 0; b0 < B; b0 += sub) {
+    const int64_t nb = std::min(sub, B - b0);
+    CK(h->w_theta.ensure(nb * th_b));
+    CK(h->w_misc[0].ensure(nb * det_b));
+    CK(cudaMemcpyAsync(h->w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    unsigned grid = (unsigned)((nb * N + 127) / 128);
+    MODEL_SWITCH(h->cfg.model, (k_deterministics<M><<<grid, 128, 0, h->stream>>>(h->map, nb, N, h->w_theta.d(),
+                                                                                 h->w_misc[0].d())));
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(det_out + b0 * CHI_NDET * N, h->w_misc[0].p, nb * det_b, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return CHI_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------
+int chi_last_kernel_ms(chi_handle* h, float* ms_out) {
+  if (!h || !ms_out) return CHI_EINVAL;
+  CK(cudaSetDevice(h->device));
+  int rc = finish_timing(h);
+  if (rc) return rc;
+  *ms_out = h->kernel_ms;
+  return CHI_OK;
+}
+
+int64_t chi_launch_count(const chi_handle* h) { return h ? h->launches : 0; }
+
+int chi_microbench_fp64(chi_handle* h, double* tflops_out) {
+  if (!h || !tflops_out) return CHI_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(h->w_misc[7].ensure(256));
+  const int iters = 4096, blocks = h->n_sm * 8, threads = 256;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(a, h->stream));
+    k_dfma_peak<<<blocks, threads, 0, h->stream>>>(h->w_misc[7].d(), iters, 1.0000001, 1e-9);
+    h->launches++;
+    CK(cudaEventRecord(b, h->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  return CHI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+"""Host-side owner of one ``libchi`` handle: marshals NumPy (host) or torch-CUDA
+(device) buffers through the C ABI.  All arithmetic happens in the CUDA library;
+this module only checks shapes, packs parameter blocks and allocates outputs.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, layout
+
+
+def _f64(a, shape=None, name="array"):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return a
+
+
+class PinnedArray:
+    """A NumPy view of page-locked host memory from ``chi_host_alloc`` (fast copies)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        lib = _lib.load()
+        self._lib = lib
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        rc = lib.chi_host_alloc(C.byref(ptr), max(nbytes, 1))
+        if rc != 0:
+            raise _lib.ChiError(rc, "chi_host_alloc failed")
+        self._ptr = ptr
+        buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            self._lib.chi_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One handle on one B200.  ``kind`` is a key of ``layout.KINDS``."""
+
+    def __init__(
+        self,
+        kind,
+        n_clouds,
+        *,
+        device=0,
+        lorentzian=False,
+        free_weight=True,
+        has_emission=None,
+        has_absorption=None,
+        bg_temp=3.77,
+        depth_nth_fwhm_power=1.0 / 3.0,
+        prior_fwhm2=500.0,
+        prior_velocity=(0.0, 10.0),
+        prior_log10_nHI=(0.0, 1.5),
+        prior_log10_n_alpha=(-6.0, 2.0),
+        prior_fwhm_L=0.0,
+        prior_amplitude=1.0,
+    ):
+        if kind not in layout.KINDS:
+            raise ValueError(f"unknown model kind {kind!r}")
+        self._lib = _lib.load()
+        self._h = None
+        self.kind = kind
+        self.n_clouds = int(n_clouds)
+        self.lorentzian = bool(lorentzian)
+        self.free_weight = bool(free_weight)
+        if kind == "physics":
+            self.has_emission = True if has_emission is None else bool(has_emission)
+            self.has_absorption = True if has_absorption is None else bool(has_absorption)
+        else:
+            self.has_emission = layout.has_emission(kind)
+            self.has_absorption = layout.has_absorption(kind)
+        cfg = _lib.ChiConfig()
+        cfg.model = layout.KINDS[kind]
+        cfg.n_clouds = self.n_clouds
+        cfg.has_emission = int(self.has_emission)
+        cfg.has_absorption = int(self.has_absorption)
+        cfg.lorentzian = int(self.lorentzian)
+        cfg.free_weight = int(self.free_weight)
+        cfg.dtype = 0
+        cfg.bg_temp = float(bg_temp)
+        cfg.depth_nth_fwhm_power = float(depth_nth_fwhm_power)
+        cfg.prior_fwhm2 = float(prior_fwhm2)
+        cfg.prior_velocity = (C.c_double * 2)(*map(float, prior_velocity))
+        cfg.prior_log10_nHI = (C.c_double * 2)(*map(float, prior_log10_nHI))
+        cfg.prior_log10_n_alpha = (C.c_double * 2)(*map(float, prior_log10_n_alpha))
+        cfg.prior_fwhm_L = float(prior_fwhm_L or 0.0)
+        cfg.prior_amplitude = float(prior_amplitude)
+        h = C.c_void_p()
+        rc = self._lib.chi_create(C.byref(h), int(device), C.byref(cfg))
+        if rc != 0:
+            raise _lib.ChiError(rc, self._lib.chi_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.slots = layout.slot_names(kind, self.lorentzian, self.free_weight)
+        self.S_e = self.S_a = 0
+        self.nb_e = self.nb_a = 0
+        self.n_sightlines = 0
+        self._keep = []
+
+    # ---- lifetime -----------------------------------------------------------
+    def close(self):
+        if self._h is not None:
+            self._lib.chi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.ChiError(rc, self._lib.chi_last_error(self._h).decode())
+
+    # ---- spectra ------------------------------------------------------------
+    def _dataset(self, d, n_sl):
+        ds = _lib.ChiDataset()
+        if d is None:
+            return ds, 0, 0
+        spectral = _f64(d["spectral"])
+        S = spectral.shape[0]
+        brightness = _f64(d["brightness"]).reshape(-1, S)
+        if brightness.shape[0] != n_sl:
+            raise ValueError("brightness: expected [n_sightlines, S]")
+        # scalar, [S] or [n_sightlines, S] (SpecData accepts a scalar or per-channel noise)
+        noise = _f64(np.broadcast_to(np.asarray(d["noise"], dtype=np.float64), (n_sl, S)), (n_sl, S), "noise")
+        basis = d.get("basis")
+        nb = 0
+        if basis is not None:
+            basis = _f64(basis).reshape(-1, S)
+            nb = basis.shape[0]
+        offset = d.get("offset")
+        if offset is not None:
+            offset = _f64(np.broadcast_to(np.asarray(offset, dtype=np.float64), (S,)))
+        ds.n_channels = S
+        ds.n_baseline = nb
+        ds.spectral = _lib.as_dp(spectral)
+        ds.brightness = _lib.as_dp(brightness)
+        ds.noise = _lib.as_dp(noise)
+        ds.basis = _lib.as_dp(basis) if nb else None
+        ds.offset = _lib.as_dp(offset) if offset is not None else None
+        self._keep = getattr(self, "_keep", []) + [spectral, brightness, noise, basis, offset]
+        return ds, S, nb
+
+    def set_spectra(self, emission=None, absorption=None, n_sightlines=1):
+        """Upload observed spectra.  Each dataset is a dict with ``spectral [S]``,
+        ``brightness [S]`` or ``[n_sightlines, S]``, ``noise`` (scalar, ``[S]`` or
+        ``[n_sightlines, S]``), optional ``basis [D+1, S]`` and ``offset`` (scalar or
+        ``[S]``) describing the affine baseline."""
+        self._keep = []
+        de, self.S_e, self.nb_e = self._dataset(emission if self.has_emission else None, n_sightlines)
+        da, self.S_a, self.nb_a = self._dataset(absorption if self.has_absorption else None, n_sightlines)
+        self._check(self._lib.chi_set_spectra(self._h, int(n_sightlines), C.byref(de), C.byref(da)))
+        self.n_sightlines = int(n_sightlines)
+        self._keep = []
+
+    # ---- packing ------------------------------------------------------------
+    def pack(self, rvs, B=None):
+        """dict of RV arrays (``[B, N]``, ``[N]``, ``[B, 1]`` or ``[B]`` for a
+        per-draw scalar) -> ``theta [B, NSLOT, N]``."""
+        N = self.n_clouds
+        if B is None:
+            B = max((np.asarray(v).shape[0] if np.asarray(v).ndim == 2 else 1) for v in rvs.values())
+        theta = np.zeros((B, layout.NSLOT, N), dtype=np.float64)
+        scal = layout.scalar_rvs(self.kind)
+        if self.kind == "physics":
+            theta[:, layout.PHYSICS_SLOTS["filling_factor"], :] = 1.0
+            theta[:, layout.PHYSICS_SLOTS["absorption_weight"], :] = 1.0
+        for name, slot in self.slots.items():
+            if name not in rvs:
+                if self.kind == "physics":
+                    continue
+                raise KeyError(f"missing free RV {name!r} for model kind {self.kind!r}")
+            v = np.asarray(rvs[name], dtype=np.float64)
+            if v.ndim == 1:
+                # 1-D: one value per draw for the per-draw scalar RVs, else one per cloud
+                v = v[:, None] if name in scal else v[None, :]
+            theta[:, slot, :] = np.broadcast_to(v, (B, N))
+        return theta
+
+    def unpack_grad(self, grad):
+        """``grad [B, NSLOT, N]`` -> dict keyed by RV name; per-draw scalar RVs are
+        summed over clouds (``[B, 1]``)."""
+        out = {}
+        scal = layout.scalar_rvs(self.kind)
+        for name, slot in self.slots.items():
+            g = grad[:, slot, :]
+            out[name] = g.sum(axis=1, keepdims=True) if name in scal else g
+        return out
+
+    # ---- model-level, host buffers -------------------------------------------
+    def _coeffs(self, coeff, nb, B, name):
+        if coeff is None or nb == 0:
+            return None
+        return _f64(np.broadcast_to(np.asarray(coeff, dtype=np.float64), (B, nb)), (B, nb), name)
+
+    def logp_grad(self, theta, coeff_e=None, coeff_a=None, sightline=None, want_grad=True, out=None):
+        """Likelihood logp ``[B]`` and gradients for ``theta [B, NSLOT, N]``.
+        Returns ``(logp, grad, gcoeff_e, gcoeff_a)`` (``None`` where not applicable).
+        ``out`` may supply preallocated (e.g. pinned) ``logp``/``grad`` arrays."""
+        N = self.n_clouds
+        theta = _f64(theta)
+        if theta.ndim != 3 or theta.shape[1:] != (layout.NSLOT, N):
+            raise ValueError(f"theta: expected [B, {layout.NSLOT}, {N}], got {theta.shape}")
+        B = theta.shape[0]
+        ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
+        ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
+        sl = None
+        if sightline is not None:
+            sl = np.ascontiguousarray(sightline, dtype=np.int32)
+            if sl.shape != (B,):
+                raise ValueError("sightline: expected [B]")
+        out = out or {}
+        logp = out.get("logp")
+        if logp is None:
+            logp = np.empty(B, dtype=np.float64)
+        grad = gce = gca = None
+        if want_grad:
+            grad = out.get("grad")
+            if grad is None:
+                grad = np.empty((B, layout.NSLOT, N), dtype=np.float64)
+            if self.nb_e:
+                gce = np.empty((B, self.nb_e), dtype=np.float64)
+            if self.nb_a:
+                gca = np.empty((B, self.nb_a), dtype=np.float64)
+        self._check(
+            self._lib.chi_logp_grad(
+                self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca), _lib.as_ip(sl),
+                _lib.as_dp(logp), _lib.as_dp(grad), _lib.as_dp(gce), _lib.as_dp(gca),
+            )
+        )
+        return logp, grad, gce, gca
+
+    def spectra(self, theta, coeff_e=None, coeff_a=None):
+        """Predicted spectra ``(mu_e [B, S_e] | None, mu_a [B, S_a] | None)``."""
+        N = self.n_clouds
+        theta = _f64(theta)
+        B = theta.shape[0]
+        if theta.shape[1:] != (layout.NSLOT, N):
+            raise ValueError("theta: bad shape")
+        ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
+        ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
+        mu_e = np.empty((B, self.S_e), dtype=np.float64) if self.has_emission else None
+        mu_a = np.empty((B, self.S_a), dtype=np.float64) if self.has_absorption else None
+        self._check(
+            self._lib.chi_spectra(self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca),
+                                  _lib.as_dp(mu_e), _lib.as_dp(mu_a))
+        )
+        return mu_e, mu_a
+
+    def spectra_vjp(self, theta, gbar_e=None, gbar_a=None, coeff_e=None, coeff_a=None):
+        """VJP of :meth:`spectra`: returns ``(grad, gcoeff_e, gcoeff_a)``."""
+        N = self.n_clouds
+        theta = _f64(theta)
+        B = theta.shape[0]
+        ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
+        ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
+        ge = _f64(gbar_e, (B, self.S_e), "gbar_e") if (gbar_e is not None and self.has_emission) else None
+        ga = _f64(gbar_a, (B, self.S_a), "gbar_a") if (gbar_a is not None and self.has_absorption) else None
+        grad = np.empty((B, layout.NSLOT, N), dtype=np.float64)
+        gce = np.empty((B, self.nb_e), dtype=np.float64) if self.nb_e else None
+        gca = np.empty((B, self.nb_a), dtype=np.float64) if self.nb_a else None
+        self._check(
+            self._lib.chi_spectra_vjp(self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca),
+                                      _lib.as_dp(ge), _lib.as_dp(ga), _lib.as_dp(grad), _lib.as_dp(gce),
+                                      _lib.as_dp(gca))
+        )
+        return grad, gce, gca
+
+    def deterministics(self, theta):
+        """dict of the reference's per-cloud Deterministics, each ``[B, N]``."""
+        theta = _f64(theta)
+        B = theta.shape[0]
+        det = np.empty((B, _lib.CHI_NDET, self.n_clouds), dtype=np.float64)
+        self._check(self._lib.chi_deterministics(self._h, B, _lib.as_dp(theta), _lib.as_dp(det)))
+        return {name: det[:, i, :] for i, name in enumerate(layout.DET_NAMES)}
+
+    # ---- model-level, device buffers (torch CUDA tensors or raw pointers) ----------
+    @staticmethod
+    def _ptr(t):
+        if t is None:
+            return None
+        if isinstance(t, int):
+            return C.c_void_p(t)
+        return C.c_void_p(t.data_ptr())
+
+    def logp_grad_dev(self, B, theta, logp, grad=None, coeff_e=None, coeff_a=None, sightline=None,
+                      gcoeff_e=None, gcoeff_a=None):
+        """Enqueue on the handle's stream; arguments are device tensors/pointers."""
+        p = self._ptr
+        self._check(
+            self._lib.chi_logp_grad_dev(self._h, int(B), p(theta), p(coeff_e), p(coeff_a), p(sightline),
+                                        p(logp), p(grad), p(gcoeff_e), p(gcoeff_a))
+        )
+
+    def spectra_dev(self, B, theta, mu_e=None, mu_a=None, coeff_e=None, coeff_a=None):
+        p = self._ptr
+        self._check(self._lib.chi_spectra_dev(self._h, int(B), p(theta), p(coeff_e), p(coeff_a), p(mu_e), p(mu_a)))
+
+    def spectra_vjp_dev(self, B, theta, grad, gbar_e=None, gbar_a=None, coeff_e=None, coeff_a=None,
+                        gcoeff_e=None, gcoeff_a=None):
+        p = self._ptr
+        self._check(
+            self._lib.chi_spectra_vjp_dev(self._h, int(B), p(theta), p(coeff_e), p(coeff_a), p(gbar_e),
+                                          p(gbar_a), p(grad), p(gcoeff_e), p(gcoeff_a))
+        )
+
+    def synchronize(self):
+        self._check(self._lib.chi_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.chi_stream(self._h)
+
+    # ---- physics-level ---------------------------------------------------------
+    def spin_temp(self, kinetic_temp, density, n_alpha):
+        tk, de, na = np.broadcast_arrays(*(np.asarray(x, dtype=np.float64) for x in (kinetic_temp, density, n_alpha)))
+        shape = tk.shape
+        tk, de, na = (_f64(x).ravel() for x in (tk, de, na))
+        out = np.empty_like(tk)
+        self._check(self._lib.chi_spin_temp(self._h, tk.size, _lib.as_dp(tk), _lib.as_dp(de), _lib.as_dp(na), _lib.as_dp(out)))
+        return out.reshape(shape)
+
+    def spin_temp_vjp(self, kinetic_temp, density, n_alpha, gbar):
+        tk, de, na, gb = np.broadcast_arrays(
+            *(np.asarray(x, dtype=np.float64) for x in (kinetic_temp, density, n_alpha, gbar))
+        )
+        shape = tk.shape
+        tk, de, na, gb = (_f64(x).ravel() for x in (tk, de, na, gb))
+        g = [np.empty_like(tk) for _ in range(3)]
+        self._check(
+            self._lib.chi_spin_temp_vjp(self._h, tk.size, _lib.as_dp(tk), _lib.as_dp(de), _lib.as_dp(na),
+                                        _lib.as_dp(gb), *(_lib.as_dp(x) for x in g))
+        )
+        return tuple(x.reshape(shape) for x in g)
+
+    def pseudo_voigt(self, velo_axis, velocity, fwhm2, fwhm_L):
+        v = _f64(velo_axis)
+        c = _f64(np.atleast_1d(velocity))
+        N = c.shape[0]
+        w = _f64(np.broadcast_to(np.asarray(fwhm2, dtype=np.float64), (N,)))
+        fl = _f64(np.broadcast_to(np.asarray(fwhm_L, dtype=np.float64), (N,)))
+        out = np.empty((v.shape[0], N), dtype=np.float64)
+        self._check(
+            self._lib.chi_pseudo_voigt(self._h, v.shape[0], N, _lib.as_dp(v), _lib.as_dp(c), _lib.as_dp(w),
+                                       _lib.as_dp(fl), _lib.as_dp(out))
+        )
+        return out
+
+    def radiative_transfer(self, tau, tspin, filling_factor, bg_temp):
+        tau = _f64(tau)
+        S, N = tau.shape
+        ts = _f64(np.broadcast_to(np.asarray(tspin, dtype=np.float64), (N,)))
+        ff = _f64(np.broadcast_to(np.asarray(filling_factor, dtype=np.float64), (N,)))
+        out = np.empty(S, dtype=np.float64)
+        self._check(
+            self._lib.chi_radiative_transfer(self._h, S, N, _lib.as_dp(tau), _lib.as_dp(ts), _lib.as_dp(ff),
+                                             float(bg_temp), _lib.as_dp(out))
+        )
+        return out
+
+    # ---- measurement -------------------------------------------------------------
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.chi_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self._lib.chi_launch_count(self._h))
+
+    def microbench_fp64(self):
+        v = C.c_double()
+        self._check(self._lib.chi_microbench_fp64(self._h, C.byref(v)))
+        return float(v.value)

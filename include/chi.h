@@ -1,0 +1,262 @@
+/*
+ * chi.h -- C ABI of libchi: the B200 (sm_100a) forward-model likelihood path of
+ * caribou_hi (spin temperature -> line-profile optical depth -> ordered-cloud
+ * radiative transfer -> Gaussian log-likelihood -> reverse-mode gradient).
+ *
+ * The reference (tvwenger/caribou_hi) has no FFI: its seam is the Python function
+ * API of caribou_hi/physics.py plus the add_likelihood() bodies of the six model
+ * classes, executed by PyTensor.  Every entry point below names the reference
+ * code it replaces (file:line into the reference tree).  The reference-side
+ * binding (ctypes stub + PyTensor Op) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every call returns 0 on success or a negative CHI_E* code; it never throws,
+ *    aborts or falls back to a CPU implementation.  chi_last_error() gives text.
+ *  - all arrays are C-contiguous float64 (fp64 is the reference's floatX);
+ *    "host" entry points take host pointers (pageable or pinned), "_dev" entry
+ *    points take device pointers valid on the handle's device and enqueue on the
+ *    handle's stream without synchronising.
+ *  - the caller owns every buffer passed in; the library owns its device
+ *    workspace, stream and events inside the handle.  One handle per
+ *    (process, device); calls on one handle must be serialised by the caller.
+ *  - parameter blocks are structure-of-arrays: theta[B][CHI_NSLOT][N]
+ *    (draw-major, then slot, clouds fastest).
+ */
+#ifndef CHI_H
+#define CHI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHI_VERSION 100
+
+/* error codes */
+#define CHI_OK 0
+#define CHI_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define CHI_ECUDA (-2)    /* CUDA runtime error (text in chi_last_error) */
+#define CHI_ENODEV (-3)   /* no sm_100 device: there is NO CPU fallback */
+#define CHI_ESTATE (-4)   /* call order violated (e.g. spectra not set) */
+#define CHI_ENOMEM (-5)
+
+/* Model kinds.  CHI_MODEL_PHYSICS takes the seven likelihood inputs directly
+ * (the boundary a PyTensor Op uses); the other six take the free random variables
+ * of the corresponding reference class and apply its add_priors()/
+ * add_deterministics() maps on the device:
+ *   ABSORPTION                    absorption_model.py:44-72 + hi_model.py:93-136
+ *   EMISSION                      emission_model.py:60-132
+ *   EMISSION_ABSORPTION           emission_absorption_model.py:45-64
+ *   ABSORPTION_PHYSICAL           absorption_physical_model.py:43-77 + hi_physical_model.py:109-197
+ *   EMISSION_PHYSICAL             emission_physical_model.py:59-129
+ *   EMISSION_ABSORPTION_PHYSICAL  emission_absorption_physical_model.py:41-60 */
+enum {
+  CHI_MODEL_PHYSICS = 0,
+  CHI_MODEL_ABSORPTION = 1,
+  CHI_MODEL_EMISSION = 2,
+  CHI_MODEL_EMISSION_ABSORPTION = 3,
+  CHI_MODEL_ABSORPTION_PHYSICAL = 4,
+  CHI_MODEL_EMISSION_PHYSICAL = 5,
+  CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL = 6
+};
+
+/* Slots of theta[B][CHI_NSLOT][N]. */
+#define CHI_NSLOT 10
+/* CHI_MODEL_PHYSICS: the likelihood inputs (slots 7..9 ignored) */
+enum {
+  CHI_PH_VELOCITY = 0,
+  CHI_PH_FWHM2 = 1,
+  CHI_PH_FWHM_L = 2,
+  CHI_PH_TAU_TOTAL = 3,
+  CHI_PH_TSPIN = 4,
+  CHI_PH_FILLING_FACTOR = 5,
+  CHI_PH_ABSORPTION_WEIGHT = 6
+};
+/* model kinds 1..6: the free RVs, named as the reference names them */
+enum {
+  CHI_FR_FWHM2_NORM = 0,          /* hi_model.py:95, hi_physical_model.py:111 */
+  CHI_FR_VELOCITY_NORM = 1,       /* hi_model.py:109, hi_physical_model.py:115 */
+  CHI_FR_LOG10_NHI_NORM = 2,      /* hi_model.py:99 (observational models only) */
+  CHI_FR_LOG10_N_ALPHA_NORM = 3,  /* hi_model.py:122, hi_physical_model.py:128 */
+  CHI_FR_NTH_FWHM_1PC = 4,        /* hi_physical_model.py:138 (physical models only) */
+  CHI_FR_FWHM_L_NORM = 5,         /* hi_model.py:133 per cloud; hi_physical_model.py:148 one
+                                     value per draw, replicated over clouds by the caller, whose
+                                     gradient is the sum over clouds */
+  CHI_FR_AMPLITUDE_NORM = 6,      /* tau_total_norm (absorption_model.py:46) | TB_fwhm_norm
+                                     (emission_model.py:62) | NHI_fwhm2_thermal_norm
+                                     (absorption_physical_model.py:45) | ff_NHI_norm
+                                     (emission_physical_model.py:61) */
+  CHI_FR_THERMAL = 7,             /* tkin_factor (absorption_model.py:55) | tkin_factor_norm
+                                     (emission_model.py:76) | fwhm2_thermal_fraction
+                                     (absorption_physical_model.py:51) |
+                                     fwhm2_thermal_fraction_norm (emission_physical_model.py:75) */
+  CHI_FR_FILLING_FACTOR_NORM = 8, /* emission_model.py:107, emission_physical_model.py:110 */
+  CHI_FR_LOG10_WT = 9             /* log10_wt_ff_tkin (emission_absorption_model.py:53) |
+                                     log10_wt_ff_fwhm2_thermal
+                                     (emission_absorption_physical_model.py:46) */
+};
+
+/* Per-cloud derived quantities written by chi_deterministics (the reference's
+ * pm.Deterministic nodes), det[B][CHI_NDET][N]. NaN where a model lacks one. */
+#define CHI_NDET 16
+enum {
+  CHI_DET_VELOCITY = 0,
+  CHI_DET_FWHM2 = 1,
+  CHI_DET_FWHM_L = 2,
+  CHI_DET_TAU_TOTAL = 3,
+  CHI_DET_TSPIN = 4,
+  CHI_DET_FILLING_FACTOR = 5,
+  CHI_DET_ABSORPTION_WEIGHT = 6,
+  CHI_DET_TKIN = 7,
+  CHI_DET_LOG10_NHI = 8,       /* column density */
+  CHI_DET_LOG10_nHI = 9,       /* volume density */
+  CHI_DET_LOG10_DEPTH = 10,
+  CHI_DET_FWHM2_THERMAL = 11,
+  CHI_DET_FWHM2_NONTHERMAL = 12,
+  CHI_DET_LOG10_PTH = 13,
+  CHI_DET_LOG10_PNTH = 14,
+  CHI_DET_LOG10_PTOT = 15
+};
+
+typedef struct chi_config {
+  int32_t model;            /* CHI_MODEL_* */
+  int32_t n_clouds;         /* N, 1..CHI_MAX_CLOUDS */
+  int32_t has_emission;     /* CHI_MODEL_PHYSICS only; implied by the kind otherwise */
+  int32_t has_absorption;   /* CHI_MODEL_PHYSICS only */
+  int32_t lorentzian;       /* 0: prior_fwhm_L=None (pure Gaussian, fwhm_L==0, hi_model.py:136);
+                               1: pseudo-Voigt with free fwhm_L */
+  int32_t free_weight;      /* EMISSION_ABSORPTION only: 0 -> absorption_weight==1
+                               (emission_absorption_model.py:46-47), 1 -> log-normal weight */
+  int32_t dtype;            /* 0 = fp64 (only value implemented) */
+  int32_t reserved;
+  double bg_temp;               /* emission_model.py:24 */
+  double depth_nth_fwhm_power;  /* hi_physical_model.py:24 */
+  double prior_fwhm2;           /* hi_model.py:96 */
+  double prior_velocity[2];     /* hi_model.py:117 */
+  double prior_log10_nHI[2];    /* hi_model.py:104 */
+  double prior_log10_n_alpha[2];/* hi_model.py:127 */
+  double prior_fwhm_L;          /* hi_model.py:134 */
+  double prior_amplitude;       /* prior_tau_total | prior_TB_fwhm | prior_NHI_fwhm2_thermal |
+                                   prior_ff_NHI, by model kind */
+} chi_config;
+
+#define CHI_MAX_CLOUDS 8
+#define CHI_MAX_BASELINE 8
+
+/* One dataset ("emission" or "absorption") of a bayes_spec SpecData dict, for
+ * n_sightlines lines of sight sharing one spectral axis. */
+typedef struct chi_dataset {
+  int32_t n_channels;        /* S >= 2; 0 = dataset absent */
+  int32_t n_baseline;        /* D+1 baseline terms, 0..CHI_MAX_BASELINE */
+  const double* spectral;    /* [S] velocity axis (km/s), SpecData.spectral */
+  const double* brightness;  /* [n_sightlines][S] observed spectrum, SpecData.brightness */
+  const double* noise;       /* [n_sightlines][S] rms per channel (>0), SpecData.noise */
+  const double* basis;       /* [n_baseline][S] baseline basis; mu += sum_i coeff_i*basis_i[s]
+                                (BaseModel.predict_baseline is affine in its coefficients) */
+  const double* offset;      /* [S] constant part of the baseline, or NULL for 0 */
+} chi_dataset;
+
+typedef struct chi_handle chi_handle;
+
+/* ---- lifetime ------------------------------------------------------------- */
+int chi_version(void);
+/* number of CUDA devices with compute capability 10.x visible to the process */
+int chi_device_count(void);
+/* Create a handle on `device`.  Fails with CHI_ENODEV if the device is not
+ * sm_100: there is no CPU fallback. */
+int chi_create(chi_handle** out, int device, const chi_config* cfg);
+void chi_destroy(chi_handle* h);
+/* Text of the last error on this handle (or of the last failed chi_create when h
+ * is NULL).  Valid until the next call on the handle. */
+const char* chi_last_error(const chi_handle* h);
+/* Upload the observed spectra (host pointers).  Replaces self.data[...] captured by
+ * add_likelihood() (emission_model.py:141,164-169 etc.).  Either dataset may be
+ * NULL / have n_channels == 0 when the model kind does not use it. */
+int chi_set_spectra(chi_handle* h, int n_sightlines, const chi_dataset* emission,
+                    const chi_dataset* absorption);
+/* The handle's CUDA stream (cudaStream_t as void*) for callers that enqueue
+ * their own work around the *_dev entry points. */
+void* chi_stream(chi_handle* h);
+int chi_synchronize(chi_handle* h);
+
+/* pinned host memory for fast host<->device copies of the host entry points */
+int chi_host_alloc(void** out, size_t bytes);
+int chi_host_free(void* p);
+
+/* ---- physics-level entry points (handle needs no spectra) ------------------ */
+/* physics.calc_spin_temp (physics.py:58-106), elementwise over n values. */
+int chi_spin_temp(chi_handle* h, int64_t n, const double* kinetic_temp, const double* density,
+                  const double* n_alpha, double* spin_temp_out);
+/* Its vector-Jacobian product: given gbar = d(cost)/d(spin_temp), the gradients
+ * with respect to the three inputs (what PyTensor's grad of physics.py:58-106
+ * produces; the switch passes gradient to the selected branch only). */
+int chi_spin_temp_vjp(chi_handle* h, int64_t n, const double* kinetic_temp, const double* density,
+                      const double* n_alpha, const double* gbar, double* g_kinetic_temp,
+                      double* g_density, double* g_n_alpha);
+/* physics.calc_pseudo_voigt (physics.py:265-309): profile_out[S][N].  fwhm_L has
+ * N entries (replicate a scalar). */
+int chi_pseudo_voigt(chi_handle* h, int S, int N, const double* velo_axis, const double* velocity,
+                     const double* fwhm2, const double* fwhm_L, double* profile_out);
+/* physics.radiative_transfer (physics.py:312-365): tau[S][N] -> tb_out[S];
+ * filling_factor has N entries (replicate a scalar). */
+int chi_radiative_transfer(chi_handle* h, int S, int N, const double* tau, const double* tspin,
+                           const double* filling_factor, double bg_temp, double* tb_out);
+
+/* ---- model-level entry points (need chi_set_spectra) ----------------------- */
+/* Likelihood logp and its gradient for B independent evaluations (draws x chains x
+ * sightlines).  Replaces one call of PyMC's compiled logp_dlogp_function restricted
+ * to the observed Normal nodes: add_likelihood() bodies (absorption_model.py:80-104,
+ * emission_model.py:140-169, emission_absorption_model.py:69-119 and the physical
+ * equivalents) + pm.Normal logp + PyTensor reverse-mode grad.
+ *   theta        [B][CHI_NSLOT][N]
+ *   coeff_e/_a   [B][n_baseline] baseline coefficients (NULL = zeros)
+ *   sightline    [B] index into the uploaded sightlines (NULL = all 0)
+ *   logp_out     [B]
+ *   grad_out     [B][CHI_NSLOT][N]   d logp / d theta   (NULL = skip the gradient)
+ *   gcoeff_e/_a  [B][n_baseline]     d logp / d coeff   (NULL = skip) */
+int chi_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                  const double* coeff_a, const int32_t* sightline, double* logp_out,
+                  double* grad_out, double* gcoeff_e, double* gcoeff_a);
+int chi_logp_grad_dev(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                      const double* coeff_a, const int32_t* sightline, double* logp_out,
+                      double* grad_out, double* gcoeff_e, double* gcoeff_a);
+
+/* Predicted spectra mu_e[B][S_e], mu_a[B][S_a] (baseline included): the `mu` of
+ * the pm.Normal nodes, i.e. what sample_posterior_predictive evaluates per draw.
+ * Either output may be NULL. */
+int chi_spectra(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                const double* coeff_a, double* mu_e_out, double* mu_a_out);
+int chi_spectra_dev(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                    const double* coeff_a, double* mu_e_out, double* mu_a_out);
+
+/* Vector-Jacobian product of chi_spectra: given cotangents gbar_e[B][S_e],
+ * gbar_a[B][S_a] (NULL = zeros) returns grad_out[B][CHI_NSLOT][N] and the baseline
+ * coefficient gradients.  This is the L_op of the spectra Op. */
+int chi_spectra_vjp(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                    const double* coeff_a, const double* gbar_e, const double* gbar_a,
+                    double* grad_out, double* gcoeff_e, double* gcoeff_a);
+int chi_spectra_vjp_dev(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                        const double* coeff_a, const double* gbar_e, const double* gbar_a,
+                        double* grad_out, double* gcoeff_e, double* gcoeff_a);
+
+/* The reference's pm.Deterministic cloud quantities for each draw:
+ * det_out[B][CHI_NDET][N] (hi_model.py:138-162, hi_physical_model.py:153-220 and the
+ * subclasses' add_priors). */
+int chi_deterministics(chi_handle* h, int64_t B, const double* theta, double* det_out);
+
+/* ---- measurement helpers --------------------------------------------------- */
+/* Milliseconds spent in the kernels of the last model-level call on this handle
+ * (CUDA events on the handle's stream; synchronises). */
+int chi_last_kernel_ms(chi_handle* h, float* ms_out);
+/* Number of kernel launches issued by this handle since creation. */
+int64_t chi_launch_count(const chi_handle* h);
+/* Own-microbenchmark peaks of the device the handle is on (the driver's
+ * MEASURED_PEAKS.json has no CUDA-core FP64 figure): dependent-free DFMA chains. */
+int chi_microbench_fp64(chi_handle* h, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHI_H */

@@ -1,0 +1,253 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerance: 1e-10 relative (fp64 path, BASELINE.json north_star), with
+atol = rtol * max|ref| over each output vector."""
+
+import numpy as np
+import pytest
+
+from helpers import RTOL64, assert_close, engine_for, make_case, oracle_logp_grad
+from oracle import models_ref as mr
+from oracle import physics_ref as ph
+
+pytestmark = pytest.mark.gpu
+
+KINDS = list(mr.KINDS)
+
+
+def _check_case(kind, N, S_e, S_a, B, seed, lorentzian, baseline_degree=1, weight=True, **kw):
+    spec, data, free, baseline = make_case(kind, N, S_e, S_a, B, seed, lorentzian, baseline_degree, weight, **kw)
+    ref_lp, ref_g = oracle_logp_grad(spec, data, free, baseline)
+    eng = engine_for(spec, data, baseline_degree)
+    theta = eng.pack(free)
+    lp, grad, gce, gca = eng.logp_grad(theta, baseline.get("baseline_emission_norm"),
+                                       baseline.get("baseline_absorption_norm"))
+    assert_close(lp, ref_lp, what=f"{kind} logp", axis=None)
+    got = eng.unpack_grad(grad)
+    finite = np.isfinite(ref_lp)
+    for name, g in got.items():
+        r = ref_g[name]
+        # draws whose logp is NaN/inf in the reference carry no gradient contract
+        assert_close(g[finite], r[finite], what=f"{kind} d/d{name}")
+    if gce is not None:
+        assert_close(gce[finite], ref_g["baseline_emission_norm"][finite], what=f"{kind} d/dbaseline_e")
+    if gca is not None:
+        assert_close(gca[finite], ref_g["baseline_absorption_norm"][finite], what=f"{kind} d/dbaseline_a")
+    # predicted spectra
+    ref_mu = mr.predict(spec, data, free, baseline)
+    mu_e, mu_a = eng.spectra(theta, baseline.get("baseline_emission_norm"),
+                             baseline.get("baseline_absorption_norm"))
+    if mu_e is not None:
+        assert_close(mu_e, ref_mu["emission"], what=f"{kind} mu_e")
+    if mu_a is not None:
+        assert_close(mu_a, ref_mu["absorption"], what=f"{kind} mu_a")
+    eng.close()
+    return int(finite.sum())
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("lorentzian", [False, True])
+def test_logp_grad_spectra_all_models(cuda_device, kind, lorentzian):
+    n_ok = _check_case(kind, 3, 200, 100, 64, seed=11, lorentzian=lorentzian)
+    assert n_ok >= 32  # most prior draws must be finite, otherwise the test is vacuous
+
+
+@pytest.mark.parametrize("N", [1, 2, 4, 5, 8])
+def test_cloud_counts(cuda_device, N):
+    _check_case("emission_absorption_physical", N, 257, 131, 16, seed=100 + N, lorentzian=(N % 2 == 0))
+
+
+def test_emission_absorption_fixed_weight(cuda_device):
+    """prior_sigma_log10_NHI=None: absorption_weight is the constant 1
+    (emission_absorption_model.py:46-47)."""
+    _check_case("emission_absorption", 2, 334, 166, 32, seed=5, lorentzian=False, weight=False)
+
+
+def test_config1_shape(cuda_device):
+    """BASELINE configs[0]: EmissionAbsorptionModel, 2 clouds, ~500 channels."""
+    _check_case("emission_absorption", 2, 334, 166, 8, seed=1234, lorentzian=False, baseline_degree=0)
+
+
+def test_config2_shape_sample(cuda_device):
+    """BASELINE configs[1] shape (4 clouds, 1000+1000 channels) on a sample of draws."""
+    _check_case("emission_absorption_physical", 4, 1000, 1000, 48, seed=2, lorentzian=False,
+                baseline_degree=0, half_width=100.0)
+
+
+def test_config3_shape_small_batch_is_chunked(cuda_device):
+    """BASELINE configs[2]: pseudo-Voigt, 8 clouds, 2048 channels, 64 chains -- small B
+    exercises the channel-chunked path (several warps per draw)."""
+    _check_case("emission_absorption_physical", 8, 2048, 2048, 8, seed=3, lorentzian=True,
+                baseline_degree=0, half_width=100.0)
+
+
+def test_nondefault_hyperparameters(cuda_device):
+    _check_case("emission_absorption_physical", 3, 150, 90, 16, seed=9, lorentzian=True,
+                bg_temp=2.7, depth_nth_fwhm_power=0.4, prior_fwhm2=200.0, prior_velocity=[2.0, 5.0],
+                prior_log10_n_alpha=[-5.0, 1.0], prior_ff_NHI=5.0e20, prior_fwhm_L=2.0)
+    _check_case("emission_absorption", 3, 150, 90, 16, seed=10, lorentzian=True,
+                bg_temp=2.7, prior_log10_nHI=[0.5, 1.0], prior_TB_fwhm=300.0)
+
+
+def test_ragged_channel_counts(cuda_device):
+    """Channel counts that are not multiples of the warp size, minimum 2 channels."""
+    _check_case("emission_absorption", 2, 33, 2, 8, seed=21, lorentzian=True)
+    _check_case("absorption", 1, 0, 31, 8, seed=22, lorentzian=False)
+    _check_case("emission", 2, 2, 0, 8, seed=23, lorentzian=False)
+
+
+def test_physics_level_logp_and_vjp(cuda_device):
+    """MODEL_PHYSICS: the seven likelihood inputs directly (the Op boundary)."""
+    import torch
+    from caribou_hi_b200 import Engine
+
+    rng = np.random.default_rng(7)
+    B, N, S_e, S_a = 24, 3, 180, 90
+    ve = np.linspace(-50, 50, S_e)
+    va = np.linspace(-25, 25, S_a)
+    inp = {
+        "velocity": rng.normal(0, 8, (B, N)),
+        "fwhm2": rng.uniform(5, 200, (B, N)),
+        "fwhm_L": rng.uniform(0.0, 3.0, (B, N)),
+        "tau_total": rng.uniform(0.05, 8, (B, N)),
+        "tspin": rng.uniform(30, 3000, (B, N)),
+        "filling_factor": rng.uniform(0.1, 1.0, (B, N)),
+        "absorption_weight": rng.uniform(0.3, 1.2, (B, N)),
+    }
+    ye = rng.normal(5, 3, S_e)
+    ya = rng.normal(0.2, 0.1, S_a)
+    data = {"emission": mr.OracleData(ve, ye, 0.3), "absorption": mr.OracleData(va, ya, 0.02)}
+    spec = mr.make_spec("emission_absorption", N, bg_temp=3.77)
+
+    # oracle on the deterministic inputs directly
+    it = {k: torch.tensor(v, requires_grad=True) for k, v in inp.items()}
+    lp = mr.logp_from_inputs(spec, data, it)
+    lp.sum().backward()
+    eng = Engine("physics", N, lorentzian=True, bg_temp=3.77)
+    eng.set_spectra(
+        emission=dict(spectral=ve, brightness=ye, noise=0.3, offset=data["emission"]._brightness_offset),
+        absorption=dict(spectral=va, brightness=ya, noise=0.02, offset=data["absorption"]._brightness_offset),
+    )
+    theta = eng.pack(inp)
+    got_lp, grad, _, _ = eng.logp_grad(theta)
+    assert_close(got_lp, lp.detach().numpy(), what="physics logp", axis=None)
+    for name, g in eng.unpack_grad(grad).items():
+        assert_close(g, it[name].grad.numpy(), what=f"physics d/d{name}")
+
+    # spectra VJP against autograd with random cotangents
+    ge = rng.standard_normal((B, S_e))
+    ga = rng.standard_normal((B, S_a))
+    it = {k: torch.tensor(v, requires_grad=True) for k, v in inp.items()}
+    mu = mr.predict_from_inputs(spec, data, it)
+    ((mu["emission"] * torch.tensor(ge)).sum() + (mu["absorption"] * torch.tensor(ga)).sum()).backward()
+    vg, _, _ = eng.spectra_vjp(theta, ge, ga)
+    for name, g in eng.unpack_grad(vg).items():
+        assert_close(g, it[name].grad.numpy(), what=f"vjp d/d{name}")
+    # emission-only cotangent
+    it = {k: torch.tensor(v, requires_grad=True) for k, v in inp.items()}
+    mu = mr.predict_from_inputs(spec, data, it)
+    (mu["emission"] * torch.tensor(ge)).sum().backward()
+    vg, _, _ = eng.spectra_vjp(theta, ge, None)
+    for name, g in eng.unpack_grad(vg).items():
+        r = it[name].grad.numpy() if it[name].grad is not None else np.zeros((B, N))
+        assert_close(g, r, what=f"vjp(e only) d/d{name}")
+    eng.close()
+
+
+def test_multiple_sightlines(cuda_device):
+    """BASELINE configs[3] in miniature: each draw is scored against its own sightline."""
+    spec, data, free, baseline = make_case("emission_physical", 5, 300, 0, 40, seed=31)
+    rng = np.random.default_rng(32)
+    n_sl = 7
+    ax = data["emission"].spectral
+    ys = data["emission"].brightness[None, :] + 0.5 * rng.standard_normal((n_sl, ax.size))
+    sig = rng.uniform(0.05, 0.2, (n_sl, ax.size))
+    sl = rng.integers(0, n_sl, size=40).astype(np.int32)
+    from caribou_hi_b200 import Engine
+
+    eng = Engine("emission_physical", 5, prior_amplitude=spec["prior_ff_NHI"])
+    eng.set_spectra(emission=dict(spectral=ax, brightness=ys, noise=sig), n_sightlines=n_sl)
+    theta = eng.pack(free)
+    lp, grad, _, _ = eng.logp_grad(theta, sightline=sl)
+    got = eng.unpack_grad(grad)
+    for i in range(n_sl):
+        sel = np.where(sl == i)[0]
+        if sel.size == 0:
+            continue
+        d = {"emission": mr.OracleData(ax, ys[i], sig[i])}
+        d["emission"]._brightness_offset = 0.0  # no baseline in this engine
+        sub = {k: v[sel] for k, v in free.items()}
+        ref_lp, ref_g = oracle_logp_grad(spec, d, sub, {})
+        fin = np.isfinite(ref_lp)
+        assert_close(lp[sel], ref_lp, what="sightline logp", axis=None)
+        for name in got:
+            assert_close(got[name][sel][fin], ref_g[name][fin], what=f"sightline d/d{name}")
+    with pytest.raises(Exception):
+        eng.logp_grad(theta, sightline=np.full(40, n_sl, dtype=np.int32))
+    eng.close()
+
+
+def test_deterministics(cuda_device):
+    for kind in KINDS:
+        spec, data, free, baseline = make_case(kind, 3, 64, 64, 32, seed=41, lorentzian=True)
+        eng = engine_for(spec, data)
+        det = eng.deterministics(eng.pack(free))
+        ref = mr.cloud_inputs(spec, free)
+        for name, r in ref.items():
+            if name in det:
+                r = np.broadcast_to(r, det[name].shape)
+                assert_close(det[name], r, what=f"{kind} det {name}", rtol=1e-12)
+        eng.close()
+
+
+def test_physics_functions(cuda_device):
+    from caribou_hi_b200 import Engine
+
+    eng = Engine("physics", 2)
+    rng = np.random.default_rng(3)
+    tk = np.concatenate([rng.uniform(10, 299, 500), rng.uniform(300, 1e4, 500), [300.0, 299.99999, 1000.0, 8000.0]])
+    dens = 10 ** rng.uniform(-2, 3, tk.size)
+    na = 10 ** rng.uniform(-9, -3, tk.size)
+    ts = eng.spin_temp(tk, dens, na)
+    assert_close(ts, ph.calc_spin_temp(tk, dens, na), rtol=1e-13, what="spin_temp")
+    import torch
+
+    t = [torch.tensor(x, requires_grad=True) for x in (tk, dens, na)]
+    gbar = rng.standard_normal(tk.size)
+    (ph.calc_spin_temp(*t) * torch.tensor(gbar)).sum().backward()
+    g = eng.spin_temp_vjp(tk, dens, na, gbar)
+    for got, ref, nm in zip(g, t, ("tk", "density", "n_alpha")):
+        assert_close(got, ref.grad.numpy(), rtol=1e-11, what=f"spin_temp vjp {nm}", axis=None)
+
+    v = np.linspace(-100, 100, 101)
+    prof = eng.pseudo_voigt(v, np.array([-5.0, 5.0]), np.array([100.0, 200.0]), 0.0)
+    assert prof.shape == (101, 2) and not np.any(np.isnan(prof))
+    assert_close(prof, ph.calc_pseudo_voigt(v, np.array([-5.0, 5.0]), np.array([100.0, 200.0]), np.zeros(2)),
+                 what="pseudo_voigt gaussian", axis=0)
+    fl = np.array([1.5, 4.0])
+    prof = eng.pseudo_voigt(v, np.array([-5.0, 5.0]), np.array([100.0, 200.0]), fl)
+    assert_close(prof, ph.calc_pseudo_voigt(v, np.array([-5.0, 5.0]), np.array([100.0, 200.0]), fl),
+                 what="pseudo_voigt", axis=0)
+    tau = np.array([5.0, 3.0]) * prof
+    tb = eng.radiative_transfer(tau, np.array([1000.0, 5000.0]), 1.0, 2.7)
+    assert tb.shape == (101,) and not np.any(np.isnan(tb))
+    assert_close(tb, ph.radiative_transfer(tau, np.array([1000.0, 5000.0]), 1.0, 2.7), what="radiative_transfer")
+    eng.close()
+
+
+def test_error_behaviour(cuda_device):
+    from caribou_hi_b200 import Engine
+    from caribou_hi_b200._lib import ChiError
+
+    with pytest.raises(ChiError):
+        Engine("emission", 9)  # > CHI_MAX_CLOUDS
+    eng = Engine("emission", 2)
+    with pytest.raises(ChiError):  # spectra not set
+        eng.logp_grad(np.zeros((1, 10, 2)))
+    with pytest.raises(ChiError):  # one channel: physics.py:294 needs two
+        eng.set_spectra(emission=dict(spectral=np.zeros(1), brightness=np.zeros(1), noise=1.0))
+    with pytest.raises(ChiError):  # missing dataset
+        eng.set_spectra(absorption=dict(spectral=np.arange(4.0), brightness=np.zeros(4), noise=1.0))
+    eng.set_spectra(emission=dict(spectral=np.arange(4.0), brightness=np.zeros(4), noise=1.0))
+    lp, g, _, _ = eng.logp_grad(np.zeros((0, 10, 2)))  # empty batch
+    assert lp.shape == (0,)
+    eng.close()
