@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- logp+grad throughput of the caribou_hi likelihood hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A *step* is one pass of the hot path (cloud map -> emission/absorption moment kernels
+-> epilogue: logp and the full gradient) over one batch of B synthetic prior draws of
+BASELINE.json configs[1]: EmissionAbsorptionPhysicalModel, 4 clouds, 1000 emission +
+1000 absorption channels, B = 1e5 draws per GPU (weak scaling over draws).
+
+Metric: draw*cloud*channel units per second, units/step = B*N*(S_e+S_a) per GPU.
+Prints ONE JSON line on rank 0 (see the driver contract in DESIGN.md section 6).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "logp+grad evals/s (draw*cloud*channel units/s)"
+UNIT = "units/s"
+KIND = "emission_absorption_physical"
+N_CLOUDS = 4
+S_E = 1000
+S_A = 1000
+DRAWS = 100_000
+N_SETS = 6  # rotated input/output buffer sets: 6 x 65 MB = 390 MB > 126 MB L2
+# canonical algorithmic flops per unit (FMA=2, exp=1, div=1), Gaussian profile
+FLOPS_EM, FLOPS_ABS = 32.0, 12.0
+SEED = 1234
+
+
+def workload_name(draws):
+    return (f"EmissionAbsorptionPhysicalModel N={N_CLOUDS} S_e={S_E} S_a={S_A} "
+            f"B={draws} prior draws per GPU, Gaussian profile (prior_fwhm_L=None), baseline_degree=0")
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        mhz, mx, reasons = [], None, set()
+        for t, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                clk, cmax = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            mx = cmax
+            if t0 <= t <= t1:
+                mhz.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[2:6]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx,
+                "samples": len(mhz), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline: the restated oracle (torch-CPU fp64 + autograd), all host threads
+# --------------------------------------------------------------------------------------
+def reference_available():
+    try:
+        import bayes_spec  # noqa: F401
+        import pymc  # noqa: F401
+        import pytensor  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def oracle_setup(draws, seed=SEED):
+    """Same seeded workload, built with the CPU oracle only (no GPU needed)."""
+    import torch  # noqa: F401
+    from oracle import models_ref as mr
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import draw_free_oracle
+
+    spec = mr.make_spec(KIND, N_CLOUDS)
+    rng = np.random.default_rng(seed)
+    ve = np.linspace(-100.0, 100.0, S_E)
+    va = np.linspace(-100.0, 100.0, S_A)
+    truth_free = draw_free_oracle(spec, 1, np.random.default_rng(seed + 1))
+    dummy = {"emission": mr.OracleData(ve, np.zeros(S_E), 0.1), "absorption": mr.OracleData(va, np.zeros(S_A), 0.01)}
+    truth = mr.predict(spec, dummy, truth_free)
+    data = {
+        "emission": mr.OracleData(ve, np.nan_to_num(truth["emission"][0]) + 0.1 * rng.standard_normal(S_E), 0.1),
+        "absorption": mr.OracleData(va, np.nan_to_num(truth["absorption"][0]) + 0.01 * rng.standard_normal(S_A), 0.01),
+    }
+    free = draw_free_oracle(spec, draws, rng)
+    return spec, data, free
+
+
+def oracle_step(spec, data, free_t):
+    import torch
+    from oracle import models_ref as mr
+
+    for v in free_t.values():
+        v.grad = None
+    lp = mr.logp(spec, data, free_t)
+    torch.nan_to_num(lp, nan=0.0, posinf=0.0, neginf=0.0).sum().backward()
+    return lp
+
+
+def time_oracle(sample_draws, steps, warmup, min_seconds=0.0):
+    import torch
+
+    spec, data, free = oracle_setup(sample_draws)
+    free_t = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in free.items()}
+    for _ in range(warmup):
+        oracle_step(spec, data, free_t)
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps or (time.perf_counter() - t0) < min_seconds:
+        oracle_step(spec, data, free_t)
+        done += 1
+    dt = time.perf_counter() - t0
+    units = sample_draws * N_CLOUDS * (S_E + S_A)
+    return units * done / dt, dt / done, done, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 512
+    if reference_available():  # a future image with PyTensor/PyMC/bayes_spec: not this one
+        note = "pytensor/pymc/bayes_spec importable but timing them is not implemented; oracle port timed"
+    else:
+        note = "reference (PyTensor/PyMC) not installable here; restated oracle port timed"
+    value, s_per_step, done, cores = time_oracle(sample, args.steps, max(args.warmup, 1))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": max(args.warmup, 1), "ms_per_step": s_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(DRAWS), "sample": f"{sample} of the {DRAWS} draws per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} draws x {done} steps, torch-CPU fp64 autograd oracle; {note}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def build_inputs(eng, draws, rank, n_sets):
+    """Seeded synthetic spectra (truth from the CUDA forward model + noise) and n_sets
+    batches of prior draws of the free RVs."""
+    from caribou_hi_b200 import synthetic
+
+    key = "fwhm2_thermal"
+
+    def thermal(trial):
+        return eng.deterministics(eng.pack(trial))[key]
+
+    ve = np.linspace(-100.0, 100.0, S_E)
+    va = np.linspace(-100.0, 100.0, S_A)
+    rng = np.random.default_rng(SEED)
+    # provisional spectra so the engine can evaluate the forward model of the truth draw
+    eng.set_spectra(emission=dict(spectral=ve, brightness=np.zeros(S_E), noise=0.1),
+                    absorption=dict(spectral=va, brightness=np.zeros(S_A), noise=0.01))
+    truth = synthetic.draw_free(KIND, N_CLOUDS, 1, np.random.default_rng(SEED + 1), thermal_fn=thermal)
+    mu_e, mu_a = eng.spectra(eng.pack(truth))
+    ye = np.nan_to_num(mu_e[0]) + 0.1 * rng.standard_normal(S_E)
+    ya = np.nan_to_num(mu_a[0]) + 0.01 * rng.standard_normal(S_A)
+    # baseline_degree = 0: one constant term per dataset (bayes_spec normalisation)
+    eng.set_spectra(
+        emission=dict(spectral=ve, brightness=ye, noise=0.1, basis=np.full((1, S_E), 0.1), offset=float(np.median(ye))),
+        absorption=dict(spectral=va, brightness=ya, noise=0.01, basis=np.full((1, S_A), 0.01), offset=float(np.median(ya))),
+    )
+    thetas = []
+    for i in range(n_sets):
+        r = np.random.default_rng([SEED, rank, i])
+        free = synthetic.draw_free(KIND, N_CLOUDS, draws, r, thermal_fn=thermal)
+        thetas.append(eng.pack(free))
+    return thetas
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from caribou_hi_b200 import Engine, PinnedArray
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    draws = args.draws
+    N = N_CLOUDS
+
+    eng = Engine(KIND, N, device=local, prior_amplitude=1.0e21)
+    thetas = build_inputs(eng, draws, rank, N_SETS)
+    dev = torch.device("cuda", local)
+    th_d = [torch.from_numpy(t).to(dev) for t in thetas]
+    ce_d = torch.zeros((draws, 1), dtype=torch.float64, device=dev)
+    ca_d = torch.zeros((draws, 1), dtype=torch.float64, device=dev)
+    lp_d = [torch.empty(draws, dtype=torch.float64, device=dev) for _ in range(N_SETS)]
+    gr_d = [torch.empty((draws, 10, N), dtype=torch.float64, device=dev) for _ in range(N_SETS)]
+    gce_d = torch.empty((draws, 1), dtype=torch.float64, device=dev)
+    gca_d = torch.empty((draws, 1), dtype=torch.float64, device=dev)
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    gathered = torch.empty((world, 1 + 10 * N), dtype=torch.float64, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    def step(i):
+        k = i % N_SETS
+        eng.logp_grad_dev(draws, th_d[k], lp_d[k], gr_d[k], coeff_e=ce_d, coeff_a=ca_d, gcoeff_e=gce_d, gcoeff_a=gca_d)
+        if world > 1:
+            # the only collective of the path: gather per-shard logp and gradient sums
+            with torch.cuda.stream(stream):
+                summary = torch.cat([torch.nan_to_num(lp_d[k]).sum().reshape(1),
+                                     torch.nan_to_num(gr_d[k]).sum(dim=0).reshape(-1)])
+                dist.all_gather_into_tensor(gathered, summary)
+
+    def barrier():
+        eng.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    t_end = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop(t_start, t_end) if rank == 0 else None
+    stage = eng.stage_ms(min(args.steps, 64)).mean(axis=0)  # events recorded during the timed steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    units_step = draws * N * (S_E + S_A)
+    value = world * units_step * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public host API: pinned host -> device -> pinned host ----
+    e2e_steps = max(2, min(args.steps, 5))
+    pin_th = [PinnedArray((draws, 10, N)) for _ in range(2)]
+    for k in range(2):
+        pin_th[k].array[...] = thetas[k]
+    pin_lp = PinnedArray((draws,))
+    pin_gr = PinnedArray((draws, 10, N))
+    ce_h = np.zeros((draws, 1))
+    ca_h = np.zeros((draws, 1))
+    out = {"logp": pin_lp.array, "grad": pin_gr.array}
+    eng.logp_grad(pin_th[0].array, ce_h, ca_h, out=out)  # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.logp_grad(pin_th[i % 2].array, ce_h, ca_h, out=out)
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    h2d = (draws * 10 * N + 2 * draws) * 8
+    d2h = (draws + draws * 10 * N + 2 * draws) * 8
+
+    if rank == 0:
+        peak = eng.microbench_fp64()
+        t_em = float(stage[1]) * 1e-3
+        flops_em = draws * N * S_E * FLOPS_EM
+        achieved = flops_em / t_em / 1e12
+        bytes_em = draws * (N * 12 * 8 + (2 + 5 * N) * 8)  # cc read + moment record written per draw
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        result = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(draws), "units_per_step_per_gpu": units_step,
+                       "l2": f"inputs/outputs rotated over {N_SETS} buffer sets ({N_SETS * 65} MB > 126 MB L2)",
+                       "parallelism": f"draws sharded over {world} GPU(s), one process per GPU"
+                                      + ("; per-step NCCL all_gather of per-shard logp/grad sums" if world > 1 else "")},
+            "clocks": clocks,
+            "e2e": {"value": world * units_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,
+                    "path": "Engine.logp_grad (C ABI chi_logp_grad) with pinned host buffers"},
+            "gpu_launches": launches,
+            "stage_ms": {"cloud_map": float(stage[0]), "moments_emission": float(stage[1]),
+                         "moments_absorption": float(stage[2]), "epilogue": float(stage[3])},
+            "roofline": {"kernel": "k_moments_em<4,false>", "bound": "fp64", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": "own DFMA microbenchmark on this GPU (chi_microbench_fp64); "
+                                        "MEASURED_PEAKS.json has no CUDA-core FP64 figure",
+                         "flops_per_unit": FLOPS_EM, "units_per_launch": draws * N * S_E,
+                         "traffic": None,
+                         "hbm": {"achieved": bytes_em / t_em / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": bytes_em / t_em / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, s_step, done, cores = time_oracle(256, 3, 1, min_seconds=10.0)
+            result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                      "sample": f"256 of the {draws} draws x {done} steps "
+                                                f"({s_step * done:.1f} s), torch-CPU fp64 autograd oracle "
+                                                "(reference PyTensor path is not installable here)"}
+        print(json.dumps(result))
+    barrier()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--draws", type=int, default=DRAWS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

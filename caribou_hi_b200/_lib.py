@@ -96,6 +96,7 @@ SYMBOLS = {
     "chi_spectra_vjp_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 8),
     "chi_deterministics": (C.c_int, [_H, C.c_int64, _dp, _dp]),
     "chi_last_kernel_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "chi_stage_ms": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float)]),
     "chi_launch_count": (C.c_int64, [_H]),
     "chi_microbench_fp64": (C.c_int, [_H, C.POINTER(C.c_double)]),
 }

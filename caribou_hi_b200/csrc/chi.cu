@@ -13,6 +13,8 @@
 #include "../../include/chi.h"
 #include "kernels.cuh"
 
+#define CHI_STAGE_RING 64
+
 using namespace chi;
 
 namespace {
@@ -56,6 +58,9 @@ struct chi_handle {
   int n_sm = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ring of stage-boundary events (map | em | abs | epilogue) of the last CHI_STAGE_RING batches
+  cudaEvent_t ring[CHI_STAGE_RING][5];
+  int64_t stage_calls = 0;
   bool ev_pending = false;
   float kernel_ms = 0.f;
   bool has_e = false, has_a = false, spectra_set = false;
@@ -72,6 +77,8 @@ struct chi_handle {
 
 namespace {
 
+bool make_ring(chi_handle* h);
+
 int fail(chi_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
   return code;
@@ -84,6 +91,15 @@ int fail(chi_handle* h, int code, const std::string& msg) {
       return fail(h, _e == cudaErrorMemoryAllocation ? CHI_ENOMEM : CHI_ECUDA,            \
                   std::string(#call) + ": " + cudaGetErrorString(_e));                    \
   } while (0)
+
+bool make_ring(chi_handle* h) {
+  for (auto& row : h->ring)
+    for (cudaEvent_t& e : row) e = nullptr;
+  for (auto& row : h->ring)
+    for (cudaEvent_t& e : row)
+      if (cudaEventCreate(&e) != cudaSuccess) return false;
+  return true;
+}
 
 bool kind_has_emission(int m) {
   return m == CHI_MODEL_EMISSION || m == CHI_MODEL_EMISSION_ABSORPTION ||
@@ -168,8 +184,11 @@ int run_backward(chi_handle* h, int64_t B, const double* theta, const double* ce
   const int N = h->cfg.n_clouds;
   const bool pv = h->cfg.lorentzian != 0;
   CK(cudaEventRecord(h->ev0, h->stream));
+  cudaEvent_t* evs = h->ring[h->stage_calls % CHI_STAGE_RING];
+  CK(cudaEventRecord(evs[0], h->stream));
   int rc = launch_cloud_map(h, B, theta);
   if (rc) return rc;
+  CK(cudaEventRecord(evs[1], h->stream));
 
   EpiArgs ea;
   memset(&ea, 0, sizeof(ea));
@@ -195,6 +214,7 @@ int run_backward(chi_handle* h, int64_t B, const double* theta, const double* ce
     ea.has_e = 1; ea.nb_e = a.n_base; ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride;
     ea.mom_e = h->mom_e.d();
   }
+  CK(cudaEventRecord(evs[2], h->stream));
   if (do_a) {
     ChanArgs a;
     memset(&a, 0, sizeof(a));
@@ -210,6 +230,7 @@ int run_backward(chi_handle* h, int64_t B, const double* theta, const double* ce
     ea.has_a = 1; ea.nb_a = a.n_base; ea.chunks_a = a.n_chunks; ea.stride_a = a.mom_stride;
     ea.mom_a = h->mom_a.d();
   }
+  CK(cudaEventRecord(evs[3], h->stream));
   // baseline-coefficient gradients of a dataset that did not run are zero
   if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), h->stream));
   if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), h->stream));
@@ -219,6 +240,8 @@ int run_backward(chi_handle* h, int64_t B, const double* theta, const double* ce
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventRecord(evs[4], h->stream));
+  h->stage_calls++;
   h->ev_pending = true;
   return CHI_OK;
 }
@@ -391,7 +414,7 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
   mc.prior_amp = cfg->prior_amplitude;
   mc.const_G = sqrt(2.0 * M_PI) / (2.0 * sqrt(2.0 * log(2.0)));  // emission_model.py:127
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || !make_ring(h)) {
     delete h;
     return fail(nullptr, CHI_ECUDA, "chi_create: stream/event creation failed");
   }
@@ -410,6 +433,9 @@ void chi_destroy(chi_handle* h) {
   for (Buf& b : h->w_misc) b.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto& row : h->ring)
+    for (cudaEvent_t e : row)
+      if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -767,6 +793,19 @@ int chi_last_kernel_ms(chi_handle* h, float* ms_out) {
   int rc = finish_timing(h);
   if (rc) return rc;
   *ms_out = h->kernel_ms;
+  return CHI_OK;
+}
+
+int chi_stage_ms(chi_handle* h, int n, float* ms_out) {
+  if (!h || !ms_out || n < 1) return CHI_EINVAL;
+  if (n > CHI_STAGE_RING || n > h->stage_calls)
+    return fail(h, CHI_ESTATE, "chi_stage_ms: fewer than n logp/vjp batches recorded (ring holds 64)");
+  CK(cudaSetDevice(h->device));
+  for (int k = 0; k < n; ++k) {
+    cudaEvent_t* evs = h->ring[(h->stage_calls - n + k) % CHI_STAGE_RING];
+    CK(cudaEventSynchronize(evs[4]));
+    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms_out[k * 4 + i], evs[i], evs[i + 1]));
+  }
   return CHI_OK;
 }
 

@@ -378,6 +378,13 @@ class Engine:
         self._check(self._lib.chi_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def stage_ms(self, n=1):
+        """Kernel milliseconds ``[n, 4]`` = (map, emission, absorption, epilogue) of the
+        ``n`` most recent logp/VJP batches (oldest first; the library keeps 64)."""
+        ms = (C.c_float * (4 * n))()
+        self._check(self._lib.chi_stage_ms(self._h, int(n), ms))
+        return np.array(ms, dtype=np.float64).reshape(n, 4)
+
     def launch_count(self):
         return int(self._lib.chi_launch_count(self._h))
 

@@ -250,6 +250,11 @@ int chi_deterministics(chi_handle* h, int64_t B, const double* theta, double* de
 /* Milliseconds spent in the kernels of the last model-level call on this handle
  * (CUDA events on the handle's stream; synchronises). */
 int chi_last_kernel_ms(chi_handle* h, float* ms_out);
+/* Kernel milliseconds of the four stages {cloud map, emission moments, absorption
+ * moments, epilogue} of the n most recent logp/VJP batches enqueued on this handle,
+ * oldest first: ms_out[n][4].  CUDA events on the handle's stream, recorded on every
+ * batch; the library keeps the last 64.  Synchronises on the newest batch asked for. */
+int chi_stage_ms(chi_handle* h, int n, float* ms_out);
 /* Number of kernel launches issued by this handle since creation. */
 int64_t chi_launch_count(const chi_handle* h);
 /* Own-microbenchmark peaks of the device the handle is on (the driver's

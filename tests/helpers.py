@@ -17,7 +17,9 @@ def assert_close(x, ref, rtol=RTOL64, what="", axis=-1):
     assert x.shape == ref.shape, f"{what}: shape {x.shape} vs {ref.shape}"
     bad_ref = ~np.isfinite(ref)
     bad_x = ~np.isfinite(x)
-    assert np.array_equal(bad_ref, bad_x), f"{what}: non-finite pattern differs"
+    if not np.array_equal(bad_ref, bad_x):
+        i = tuple(np.argwhere(bad_ref != bad_x)[0])
+        raise AssertionError(f"{what}: non-finite pattern differs at {i}: x={x[i]!r}, ref={ref[i]!r}")
     if ref.ndim == 0 or ref.size == 0:
         scale = np.abs(ref)
     else:
