@@ -18,21 +18,9 @@
 #include <stdint.h>
 
 #include "cloud_map.cuh"
+#include "moments.cuh"
 
 namespace chi {
-
-#define CHI_WARPS_PER_BLOCK 4
-#define CHI_BLOCK (32 * CHI_WARPS_PER_BLOCK)
-#define CHI_FULL 0xffffffffu
-
-// exp() used on the channel path. Argument is <= 0 on every model-level path.
-__device__ __forceinline__ double chi_exp(double x) { return exp(x); }
-
-__device__ __forceinline__ double warp_sum(double x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(CHI_FULL, x, o);
-  return x;
-}
 
 // ---------------------------------------------------------------------------
 // k_cloud_map
@@ -63,262 +51,6 @@ __global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, int64_t B, int N,
                                                 cfg.wch2_a, cfg.lorentzian != 0);
   o[CC_KA] = pa.k; o[CC_AGA] = pa.AG; o[CC_ALA] = pa.AL; o[CC_HA] = pa.h;
   o[11] = 0.0;
-}
-
-// ---------------------------------------------------------------------------
-// shared argument block of the channel kernels
-// ---------------------------------------------------------------------------
-struct ChanArgs {
-  int64_t B;
-  int S;            // channels of this dataset
-  int n_base;       // baseline terms
-  int n_chunks;     // channel chunks per draw
-  int chunk_len;    // channels per chunk (multiple of 32)
-  int mom_stride;   // doubles per (draw, chunk) record
-  double bg;
-  const double* __restrict__ vax;     // [S]
-  const double* __restrict__ yeff;    // [n_sl][S]   brightness - baseline offset
-  const double* __restrict__ wgt;     // [n_sl][S]   1/noise^2
-  const double* __restrict__ basis;   // [n_base][S]
-  const double* __restrict__ coeff;   // [B][n_base] or null
-  const int32_t* __restrict__ sl;     // [B] or null
-  const double* __restrict__ gbar;    // [B][S] cotangent (vjp mode) or null (logp mode)
-  const double* __restrict__ cc;      // [B][N][12]
-  double* __restrict__ mom;           // [B][n_chunks][mom_stride]
-};
-
-// record layout: [0]=sum -0.5 w r^2, [1..n_base]=d/dcoeff, then per cloud NE/NA moments
-template <bool PV> struct EmLayout { static constexpr int NE = PV ? 8 : 5; };
-template <bool PV> struct AbLayout { static constexpr int NA = PV ? 6 : 3; };
-
-// ---------------------------------------------------------------------------
-// k_moments_em: emission spectrum, forward + reverse in registers
-//   physics.py:294-309 (profile), emission_model.py:148 (tau), physics.py:345-365
-//   (radiative transfer), pm.Normal logp, and the adjoint of all of it.
-// ---------------------------------------------------------------------------
-template <int N, bool PV>
-__global__ void __launch_bounds__(CHI_BLOCK) k_moments_em(ChanArgs a) {
-  constexpr int NE = EmLayout<PV>::NE;
-  __shared__ double s_c[CHI_WARPS_PER_BLOCK][N][8];  // c, k, AG, AL, h, f, Ts, fTs
-  __shared__ double s_gb[CHI_MAX_BASELINE][CHI_BLOCK];
-  __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
-  if (item >= a.B * a.n_chunks) return;
-  const int64_t b = item / a.n_chunks;
-  const int chunk = (int)(item - b * a.n_chunks);
-
-  if (lane < N) {
-    const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
-    double f = p[CC_F], ts = p[CC_TS];
-    double* d = s_c[warp][lane];
-    d[0] = p[CC_C]; d[1] = p[CC_KE]; d[2] = p[CC_AGE]; d[3] = p[CC_ALE]; d[4] = p[CC_HE];
-    d[5] = f; d[6] = ts; d[7] = f * ts;
-  }
-  if (lane < a.n_base) s_beta[warp][lane] = a.coeff ? a.coeff[b * a.n_base + lane] : 0.0;
-  for (int i = 0; i < a.n_base; ++i) s_gb[i][threadIdx.x] = 0.0;
-  __syncwarp();
-
-  const int sl = a.sl ? a.sl[b] : 0;
-  const double* __restrict__ Y = a.yeff + (int64_t)sl * a.S;
-  const double* __restrict__ Wt = a.wgt + (int64_t)sl * a.S;
-  const double* __restrict__ G = a.gbar ? a.gbar + b * a.S : nullptr;
-
-  double acc[N][NE];
-#pragma unroll
-  for (int n = 0; n < N; ++n)
-#pragma unroll
-    for (int j = 0; j < NE; ++j) acc[n][j] = 0.0;
-  double lp = 0.0;
-  const double bg = a.bg;
-
-  const int s_begin = chunk * a.chunk_len;
-  const int s_end = min(a.S, s_begin + a.chunk_len);
-  for (int s = s_begin + lane; s < s_end; s += 32) {
-    const double v = a.vax[s];
-    double base = 0.0;
-    for (int i = 0; i < a.n_base; ++i) base = fma(s_beta[warp][i], a.basis[(int64_t)i * a.S + s], base);
-
-    double e[N], Pn[N], E[N], d[N], q[N];
-    double P = 1.0, T = 0.0;
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      const double* c = s_c[warp][n];
-      d[n] = v - c[0];
-      const double d2 = d[n] * d[n];
-      E[n] = chi_exp(-c[1] * d2);
-      double tau = c[2] * E[n];
-      if (PV) {
-        q[n] = 1.0 / (d2 + c[4]);
-        tau = fma(c[3], q[n], tau);
-      }
-      e[n] = chi_exp(-tau);
-      Pn[n] = P;
-      const double om = 1.0 - e[n];
-      T = fma(c[7] * om, P, T);                 // f Ts (1-e) * attenuation in front
-      P *= fma(c[5], e[n], 1.0 - c[5]);         // 1 - f + f e
-    }
-    const double mu = (bg * P + T) - bg + base;  // ON - OFF, physics.py:362-365
-    double mubar;
-    if (G) {
-      mubar = G[s];
-    } else {
-      const double r = Y[s] - mu;
-      mubar = Wt[s] * r;                        // d logp / d mu
-      lp = fma(-0.5 * mubar, r, lp);
-    }
-    for (int i = 0; i < a.n_base; ++i)
-      s_gb[i][threadIdx.x] = fma(mubar, a.basis[(int64_t)i * a.S + s], s_gb[i][threadIdx.x]);
-
-    // reverse pass, farthest cloud first; Q = brightness arriving behind cloud n
-    double Q = bg;
-#pragma unroll
-    for (int n = N - 1; n >= 0; --n) {
-      const double* c = s_c[warp][n];
-      const double om = 1.0 - e[n];
-      const double Sn = c[6] - Q;               // Ts_n - Q_n
-      const double mx = mubar * (om * Pn[n]);
-      acc[n][3] += mx;                          // -> d/dTs (times f)
-      acc[n][4] = fma(mx, Sn, acc[n][4]);       // -> d/df
-      const double g = mubar * (e[n] * Pn[n]) * Sn;  // taubar / f
-      const double t = g * E[n];
-      acc[n][0] += t;
-      acc[n][1] = fma(t, d[n], acc[n][1]);
-      acc[n][2] = fma(t * d[n], d[n], acc[n][2]);
-      if (PV) {
-        const double u = g * q[n];
-        acc[n][5] += u;
-        const double u2 = u * q[n];
-        acc[n][6] += u2;
-        acc[n][7] = fma(u2, d[n], acc[n][7]);
-      }
-      Q = fma(fma(c[5], e[n], 1.0 - c[5]), Q, c[7] * om);
-    }
-  }
-
-  double* out = a.mom + item * a.mom_stride;
-  lp = warp_sum(lp);
-  if (lane == 0) out[0] = lp;
-  for (int i = 0; i < a.n_base; ++i) {
-    double g = warp_sum(s_gb[i][threadIdx.x]);
-    if (lane == 0) out[1 + i] = g;
-  }
-  double* om_ = out + 1 + a.n_base;
-#pragma unroll
-  for (int n = 0; n < N; ++n)
-#pragma unroll
-    for (int j = 0; j < NE; ++j) {
-      double r = warp_sum(acc[n][j]);
-      if (lane == ((n * NE + j) & 31)) om_[n * NE + j] = r;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// k_moments_abs: absorption spectrum 1 - exp(-sum_n tau)
-//   absorption_model.py:88-91, emission_absorption_model.py:84-99 + physical equivalents
-// ---------------------------------------------------------------------------
-template <int N, bool PV>
-__global__ void __launch_bounds__(CHI_BLOCK) k_moments_abs(ChanArgs a) {
-  constexpr int NA = AbLayout<PV>::NA;
-  __shared__ double s_c[CHI_WARPS_PER_BLOCK][N][6];  // c, k, AG, AL, h
-  __shared__ double s_gb[CHI_MAX_BASELINE][CHI_BLOCK];
-  __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
-  if (item >= a.B * a.n_chunks) return;
-  const int64_t b = item / a.n_chunks;
-  const int chunk = (int)(item - b * a.n_chunks);
-
-  if (lane < N) {
-    const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
-    double* d = s_c[warp][lane];
-    d[0] = p[CC_C]; d[1] = p[CC_KA]; d[2] = p[CC_AGA]; d[3] = p[CC_ALA]; d[4] = p[CC_HA];
-  }
-  if (lane < a.n_base) s_beta[warp][lane] = a.coeff ? a.coeff[b * a.n_base + lane] : 0.0;
-  for (int i = 0; i < a.n_base; ++i) s_gb[i][threadIdx.x] = 0.0;
-  __syncwarp();
-
-  const int sl = a.sl ? a.sl[b] : 0;
-  const double* __restrict__ Y = a.yeff + (int64_t)sl * a.S;
-  const double* __restrict__ Wt = a.wgt + (int64_t)sl * a.S;
-  const double* __restrict__ G = a.gbar ? a.gbar + b * a.S : nullptr;
-
-  double acc[N][NA];
-#pragma unroll
-  for (int n = 0; n < N; ++n)
-#pragma unroll
-    for (int j = 0; j < NA; ++j) acc[n][j] = 0.0;
-  double lp = 0.0;
-
-  const int s_begin = chunk * a.chunk_len;
-  const int s_end = min(a.S, s_begin + a.chunk_len);
-  for (int s = s_begin + lane; s < s_end; s += 32) {
-    const double v = a.vax[s];
-    double base = 0.0;
-    for (int i = 0; i < a.n_base; ++i) base = fma(s_beta[warp][i], a.basis[(int64_t)i * a.S + s], base);
-
-    double E[N], d[N], q[N];
-    double tsum = 0.0;
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      const double* c = s_c[warp][n];
-      d[n] = v - c[0];
-      const double d2 = d[n] * d[n];
-      E[n] = chi_exp(-c[1] * d2);
-      double tau = c[2] * E[n];
-      if (PV) {
-        q[n] = 1.0 / (d2 + c[4]);
-        tau = fma(c[3], q[n], tau);
-      }
-      tsum += tau;
-    }
-    const double ea = chi_exp(-tsum);
-    const double mu = (1.0 - ea) + base;
-    double mubar;
-    if (G) {
-      mubar = G[s];
-    } else {
-      const double r = Y[s] - mu;
-      mubar = Wt[s] * r;
-      lp = fma(-0.5 * mubar, r, lp);
-    }
-    for (int i = 0; i < a.n_base; ++i)
-      s_gb[i][threadIdx.x] = fma(mubar, a.basis[(int64_t)i * a.S + s], s_gb[i][threadIdx.x]);
-
-    const double g = mubar * ea;  // taubar, identical for every cloud
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      const double t = g * E[n];
-      acc[n][0] += t;
-      acc[n][1] = fma(t, d[n], acc[n][1]);
-      acc[n][2] = fma(t * d[n], d[n], acc[n][2]);
-      if (PV) {
-        const double u = g * q[n];
-        acc[n][3] += u;
-        const double u2 = u * q[n];
-        acc[n][4] += u2;
-        acc[n][5] = fma(u2, d[n], acc[n][5]);
-      }
-    }
-  }
-
-  double* out = a.mom + item * a.mom_stride;
-  lp = warp_sum(lp);
-  if (lane == 0) out[0] = lp;
-  for (int i = 0; i < a.n_base; ++i) {
-    double g = warp_sum(s_gb[i][threadIdx.x]);
-    if (lane == 0) out[1 + i] = g;
-  }
-  double* om_ = out + 1 + a.n_base;
-#pragma unroll
-  for (int n = 0; n < N; ++n)
-#pragma unroll
-    for (int j = 0; j < NA; ++j) {
-      double r = warp_sum(acc[n][j]);
-      if (lane == ((n * NA + j) & 31)) om_[n * NA + j] = r;
-    }
 }
 
 // ---------------------------------------------------------------------------
