@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchi.so")
+# CHI_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("CHI_LIB") or os.path.join(_HERE, "libchi.so")
 
 # ---- constants mirrored from include/chi.h ------------------------------------
 CHI_VERSION = 100

@@ -26,23 +26,42 @@ namespace chi {
 //   * 2^n applied by adding n to the exponent field,
 //   * x < -708 (result would be subnormal, < 2.3e-308) returns 0; x >= 700, +inf and
 //     NaN with the sign bit clear take libm's exp (never happens for tau >= 0).
-__device__ __forceinline__ double chi_exp(double x) {
+// coefficients in the constant bank: FP64 literals would be re-materialised by two UMOVs at
+// every use once the register cap stops the compiler from keeping them resident
+__constant__ double c_exp[16] = {
+    1.4426950408889634074,       // 0 log2(e)
+    6755399441055744.0,          // 1 1.5 * 2^52
+    -6.93147180369123816490e-01, // 2 -ln2 hi
+    -1.90821492927058770002e-10, // 3 -ln2 lo
+    2.510038549551032e-08,       // 4.. g(r) high -> low degree
+    2.7620088445409746e-07, 2.7557268459997064e-06, 2.4801521295954376e-05, 0.00019841269863053618,
+    0.0013888888917213717, 0.008333333333330062, 0.04166666666662413, 0.16666666666666669,
+    0.5000000000000001, 0.0, 0.0};
+
+// The coefficients, read once per kernel into (uniform) registers.
+struct ExpK {
+  double k[14];
+};
+__device__ __forceinline__ ExpK load_expk() {
+  ExpK e;
+#pragma unroll
+  for (int i = 0; i < 14; ++i) e.k[i] = c_exp[i];
+  return e;
+}
+
+// Branch-free on purpose: a branch per call would put every exp in its own basic block and
+// stop the scheduler from interleaving the independent per-cloud chains (ILP).
+// OVERFLOW=false is for arguments that are <= 0 by construction (-k d^2).
+template <bool OVERFLOW = true>
+__device__ __forceinline__ double chi_exp(double x, const ExpK& c) {
   const int hi = __double2hiint(x);
-  if (__builtin_expect(hi >= 0x4085E000, 0)) return exp(x);
-  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
-  const double nf = t - 6755399441055744.0;
-  double r = fma(nf, -6.93147180369123816490e-01, x);
-  r = fma(nf, -1.90821492927058770002e-10, r);
-  double p = 2.510038549551032e-08;
-  p = fma(p, r, 2.7620088445409746e-07);
-  p = fma(p, r, 2.7557268459997064e-06);
-  p = fma(p, r, 2.4801521295954376e-05);
-  p = fma(p, r, 0.00019841269863053618);
-  p = fma(p, r, 0.0013888888917213717);
-  p = fma(p, r, 0.008333333333330062);
-  p = fma(p, r, 0.04166666666662413);
-  p = fma(p, r, 0.16666666666666669);
-  p = fma(p, r, 0.5000000000000001);
+  const double t = fma(x, c.k[0], c.k[1]);
+  const double nf = t - c.k[1];
+  double r = fma(nf, c.k[2], x);
+  r = fma(nf, c.k[3], r);
+  double p = fma(c.k[4], r, c.k[5]);
+#pragma unroll
+  for (int i = 6; i <= 13; ++i) p = fma(p, r, c.k[i]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const int n = __double2loint(t);
@@ -50,8 +69,16 @@ __device__ __forceinline__ double chi_exp(double x) {
   // -708 = 0xC086200000000000; negative doubles order like unsigned ints on the high word;
   // the range stops at -inf (0xFFF00000) so that NaNs still propagate through r and p
   const bool underflow = (unsigned)(hi - 0xC0862001) <= (0xFFF00000u - 0xC0862001u);
-  return underflow ? 0.0 : res;
+  double out = underflow ? 0.0 : res;
+  if (OVERFLOW) {
+    // x > 709 (0x4086280000000000) up to and including +inf gives +inf; NaNs (canonical after
+    // the first fma, so n == 0) fall outside both ranges and propagate through p
+    const bool overflow = (unsigned)(hi - 0x40862801) <= (0x7FF00000u - 0x40862801u);
+    out = overflow ? __hiloint2double(0x7FF00000, 0) : out;
+  }
+  return out;
 }
+__device__ __forceinline__ double chi_exp(double x) { return chi_exp<true>(x, load_expk()); }
 
 // 1/x for normal x > 0 (x = d^2 + W^2/4 of the Lorentzian): MUFU.RCP64H seed + two
 // Newton steps, ~1 ulp, no slow path.
@@ -108,13 +135,17 @@ template <bool PV> struct AbLayout { static constexpr int NA = PV ? 6 : 3; };
 
 // resident blocks per SM asked of the compiler: accumulators + per-cloud state are the
 // register floor of a variant, everything else is traded against occupancy
+#ifndef CHI_BLOCKS_BIAS
+#define CHI_BLOCKS_BIAS 0  // build-time experiment knob: +/- resident blocks per SM
+#endif
+constexpr int clamp_blocks(int b) { return b < 1 ? 1 : (b > 4 ? 4 : b); }
 constexpr int em_min_blocks(int N, bool pv) {
   const int regs = 2 * ((pv ? 8 : 5) * N + (pv ? 4 : 3) * N) + 64;
-  return regs <= 128 ? 4 : (regs <= 168 ? 3 : 2);
+  return clamp_blocks((regs <= 128 ? 4 : (regs <= 168 ? 3 : 2)) + CHI_BLOCKS_BIAS);
 }
 constexpr int ab_min_blocks(int N, bool pv) {
   const int regs = 2 * ((pv ? 6 : 3) * N + (pv ? 3 : 2) * N) + 56;
-  return regs <= 128 ? 4 : (regs <= 168 ? 3 : 2);
+  return clamp_blocks((regs <= 128 ? 4 : (regs <= 168 ? 3 : 2)) + CHI_BLOCKS_BIAS);
 }
 
 // first two baseline terms are kept in registers (degree 0/1 is the common case);
@@ -169,6 +200,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
   double lp = 0.0, gb0 = 0.0, gb1 = 0.0;
   const double bg = a.bg;
   const double(*sc)[8] = s_c[warp];
+  const ExpK ek = load_expk();
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
   for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
@@ -189,13 +221,13 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
       lds2(&sc[n][4], h, f);
       lds2(&sc[n][6], Ts, fTs);
       const double d = v - c0, d2 = d * d;
-      E[n] = chi_exp(nk * d2);
+      E[n] = chi_exp<false>(nk * d2, ek);
       double x = nAG * E[n];                    // -tau
       if (PV) {
         q[n] = chi_rcp(d2 + h);
         x = fma(nAL, q[n], x);
       }
-      om[n] = 1.0 - chi_exp(x);                 // 1 - e^-tau
+      om[n] = 1.0 - chi_exp(x, ek);               // 1 - e^-tau
       Pn[n] = P;
       T = fma(fTs * om[n], P, T);               // f Ts (1-e) x attenuation in front
       P *= fma(-f, om[n], 1.0);                 // 1 - f + f e
@@ -314,6 +346,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
     for (int j = 0; j < NA; ++j) acc[n][j] = 0.0;
   double lp = 0.0, gb0 = 0.0, gb1 = 0.0;
   const double(*sc)[6] = s_c[warp];
+  const ExpK ek = load_expk();
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
   for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
@@ -332,14 +365,14 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
       lds2(&sc[n][2], nAG, nAL);
       d[n] = v - c0;
       const double d2 = d[n] * d[n];
-      E[n] = chi_exp(nk * d2);
+      E[n] = chi_exp<false>(nk * d2, ek);
       xs = fma(nAG, E[n], xs);
       if (PV) {
         q[n] = chi_rcp(d2 + sc[n][4]);
         xs = fma(nAL, q[n], xs);
       }
     }
-    const double ea = chi_exp(xs);
+    const double ea = chi_exp(xs, ek);
     const double mu = (1.0 - ea) + base;
     double mubar;
     if (G) {

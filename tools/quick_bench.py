@@ -34,6 +34,7 @@ if __name__ == "__main__":
     kind = "emission_absorption_physical"
     run(kind, 4, 1000, 1000, B, False)
     run(kind, 4, 1000, 1000, B, True)
+    if os.environ.get("QUICK"): sys.exit(0)
     run(kind, 8, 2048, 2048, max(B // 8, 64), True)
     run(kind, 8, 2048, 2048, 64, True, reps=20)
     run(kind, 2, 334, 166, B, False)
