@@ -87,8 +87,11 @@ SYMBOLS = {
     "chi_host_free": (C.c_int, [C.c_void_p]),
     "chi_spin_temp": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp]),
     "chi_spin_temp_vjp": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
-    "chi_pseudo_voigt": (C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
+    "chi_elementwise": (C.c_int, [_H, C.c_int, C.c_int64, _dp, _dp, _dp, _dp]),
+    "chi_pseudo_voigt":(C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
     "chi_radiative_transfer": (C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, _dp]),
+    "chi_pseudo_voigt_vjp": (C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "chi_radiative_transfer_vjp": (C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp]),
     "chi_logp_grad": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp]),
     "chi_logp_grad_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 8),
     "chi_spectra": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp]),

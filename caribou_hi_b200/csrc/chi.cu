@@ -538,6 +538,30 @@ int chi_spin_temp_vjp(chi_handle* h, int64_t n, const double* tk, const double* 
   return CHI_OK;
 }
 
+int chi_elementwise(chi_handle* h, int fn, int64_t n, const double* a, const double* b, const double* c,
+                    double* out) {
+  if (!h) return CHI_EINVAL;
+  if (fn < CHI_FN_GAUSSIAN || fn > CHI_FN_LOG10_NONTHERMAL_PRESSURE)
+    return fail(h, CHI_EINVAL, "chi_elementwise: unknown function id");
+  const bool three = fn <= CHI_FN_LORENTZIAN;
+  if (n < 0 || (n > 0 && (!a || !b || !out || (three && !c))))
+    return fail(h, CHI_EINVAL, "chi_elementwise: NULL argument");
+  if (n == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  const size_t nb = (size_t)n * sizeof(double);
+  for (int i = 0; i < 4; ++i) CK(h->w_misc[i].ensure(nb));
+  CK(cudaMemcpyAsync(h->w_misc[0].p, a, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[1].p, b, nb, cudaMemcpyHostToDevice, h->stream));
+  if (three) CK(cudaMemcpyAsync(h->w_misc[2].p, c, nb, cudaMemcpyHostToDevice, h->stream));
+  k_elementwise<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(fn, n, h->w_misc[0].d(), h->w_misc[1].d(),
+                                                                   h->w_misc[2].d(), h->w_misc[3].d());
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->w_misc[3].p, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CHI_OK;
+}
+
 int chi_pseudo_voigt(chi_handle* h, int S, int N, const double* vax, const double* velocity,
                      const double* fwhm2, const double* fwhm_L, double* out) {
   if (!h) return CHI_EINVAL;
@@ -580,6 +604,68 @@ int chi_radiative_transfer(chi_handle* h, int S, int N, const double* tau, const
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, h->w_misc[3].p, S * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CHI_OK;
+}
+
+int chi_pseudo_voigt_vjp(chi_handle* h, int S, int N, const double* vax, const double* velocity,
+                         const double* fwhm2, const double* fwhm_L, const double* gbar, double* g_velocity,
+                         double* g_fwhm2, double* g_fwhm_L) {
+  if (!h) return CHI_EINVAL;
+  if (S < 2) return fail(h, CHI_EINVAL, "chi_pseudo_voigt_vjp: need at least 2 channels (physics.py:294)");
+  if (N < 1 || !vax || !velocity || !fwhm2 || !fwhm_L || !gbar || !g_velocity || !g_fwhm2 || !g_fwhm_L)
+    return fail(h, CHI_EINVAL, "chi_pseudo_voigt_vjp: bad argument");
+  CK(cudaSetDevice(h->device));
+  const size_t sb = S * sizeof(double), nb = N * sizeof(double), snb = (size_t)S * N * sizeof(double);
+  CK(h->w_misc[0].ensure(sb));
+  for (int i = 1; i < 4; ++i) CK(h->w_misc[i].ensure(nb));
+  CK(h->w_misc[4].ensure(snb));
+  CK(h->w_misc[5].ensure(3 * nb));
+  CK(cudaMemcpyAsync(h->w_misc[0].p, vax, sb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[1].p, velocity, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[2].p, fwhm2, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[3].p, fwhm_L, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[4].p, gbar, snb, cudaMemcpyHostToDevice, h->stream));
+  double* g = h->w_misc[5].d();
+  k_pseudo_voigt_vjp<<<N, 256, 0, h->stream>>>(S, N, h->w_misc[0].d(), h->w_misc[1].d(), h->w_misc[2].d(),
+                                               h->w_misc[3].d(), h->w_misc[4].d(), g, g + N, g + 2 * N);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(g_velocity, g, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(g_fwhm2, g + N, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(g_fwhm_L, g + 2 * N, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CHI_OK;
+}
+
+int chi_radiative_transfer_vjp(chi_handle* h, int S, int N, const double* tau, const double* tspin,
+                               const double* ff, double bg_temp, const double* gbar, double* g_tau,
+                               double* g_tspin, double* g_ff) {
+  if (!h) return CHI_EINVAL;
+  if (S < 1 || N < 1 || N > CHI_RT_MAX_CLOUDS || !tau || !tspin || !ff || !gbar || !g_tau || !g_tspin || !g_ff)
+    return fail(h, CHI_EINVAL, "chi_radiative_transfer_vjp: bad argument (N must be <= 64)");
+  CK(cudaSetDevice(h->device));
+  const size_t sb = S * sizeof(double), nb = N * sizeof(double), snb = (size_t)S * N * sizeof(double);
+  CK(h->w_misc[0].ensure(snb));
+  CK(h->w_misc[1].ensure(nb));
+  CK(h->w_misc[2].ensure(nb));
+  CK(h->w_misc[3].ensure(sb));
+  CK(h->w_misc[4].ensure(snb));
+  CK(h->w_misc[5].ensure(2 * nb));
+  CK(cudaMemcpyAsync(h->w_misc[0].p, tau, snb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[1].p, tspin, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[2].p, ff, nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->w_misc[3].p, gbar, sb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->w_misc[5].p, 0, 2 * nb, h->stream));
+  double* g = h->w_misc[5].d();
+  k_radiative_transfer_vjp<<<(S + 127) / 128, 128, 0, h->stream>>>(S, N, h->w_misc[0].d(), h->w_misc[1].d(),
+                                                                  h->w_misc[2].d(), bg_temp, h->w_misc[3].d(),
+                                                                  h->w_misc[4].d(), g, g + N);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(g_tau, h->w_misc[4].p, snb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(g_tspin, g, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(g_ff, g + N, nb, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return CHI_OK;
 }

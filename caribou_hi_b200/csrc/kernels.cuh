@@ -267,6 +267,37 @@ __global__ void k_spin_temp_vjp(int64_t n, const double* __restrict__ tk, const 
   g_na[i] = g * r.d[2];
 }
 
+// elementwise helpers of physics.py that the reference evaluates through PyTensor
+//   CHI_FN_GAUSSIAN                   physics.gaussian   (x, center, fwhm)        physics.py:16-35
+//   CHI_FN_LORENTZIAN                 physics.lorentzian (x, center, fwhm)        physics.py:38-55
+//   CHI_FN_LOG10_COLUMN_DENSITY       (tau_total, spin_temp, -)                   physics.py:191-207
+//   CHI_FN_LOG10_NONTHERMAL_PRESSURE  (log10_density, fwhm2_nonthermal, -)        physics.py:247-262
+__global__ void k_elementwise(int fn, int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                              const double* __restrict__ c, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r;
+  switch (fn) {
+    case CHI_FN_GAUSSIAN: {
+      const double d = a[i] - b[i], w2 = c[i] * c[i];
+      r = exp(-4.0 * CHI_LN2 * (d * d) / w2) * sqrt(4.0 * CHI_LN2 / (CHI_PI * w2));
+    } break;
+    case CHI_FN_LORENTZIAN: {
+      const double d = a[i] - b[i], hw = c[i] / 2.0;
+      r = c[i] / (2.0 * CHI_PI) / (d * d + hw * hw);
+    } break;
+    case CHI_FN_LOG10_COLUMN_DENSITY:
+      r = log10(CHI_COLUMN_CONST * b[i] * a[i]);
+      break;
+    case CHI_FN_LOG10_NONTHERMAL_PRESSURE:
+      r = log10(CHI_PNTH_CONST) + a[i] + log10(b[i]);
+      break;
+    default:
+      r = __longlong_as_double(0x7ff8000000000000LL);
+  }
+  out[i] = r;
+}
+
 // physics.calc_pseudo_voigt, physics.py:265-309 -> profile[S][N]
 __global__ void k_pseudo_voigt(int S, int N, const double* __restrict__ vax,
                                const double* __restrict__ velocity, const double* __restrict__ fwhm2,
@@ -295,6 +326,87 @@ __global__ void k_radiative_transfer(int S, int N, const double* __restrict__ ta
     P *= fma(f, e, 1.0 - f);
   }
   out[s] = (bg * P + T) - bg;
+}
+
+// VJP of physics.calc_pseudo_voigt: gbar[S][N] -> d/d{velocity, fwhm2, fwhm_L}[N].
+// One block per cloud; the channel sums are the same six moments the hot kernels use.
+__global__ void __launch_bounds__(256) k_pseudo_voigt_vjp(int S, int N, const double* __restrict__ vax,
+                                                          const double* __restrict__ velocity,
+                                                          const double* __restrict__ fwhm2,
+                                                          const double* __restrict__ fwhm_L,
+                                                          const double* __restrict__ gbar,
+                                                          double* __restrict__ g_velocity,
+                                                          double* __restrict__ g_fwhm2,
+                                                          double* __restrict__ g_fwhm_L) {
+  __shared__ double red[8][6];
+  const int n = blockIdx.x;
+  const double dv = fabs(vax[1] - vax[0]);
+  const double wch = 4.0 * CHI_LN2 * dv / CHI_PI;
+  const ProfConst<double> p = profile_consts<double>(fwhm2[n], fwhm_L[n], 1.0, wch * wch, true);
+  const double c0 = velocity[n];
+  double m[6] = {0, 0, 0, 0, 0, 0};
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const double g = gbar[(int64_t)s * N + n];
+    const double d = vax[s] - c0, d2 = d * d;
+    const double E = chi_exp(-p.k * d2), q = 1.0 / (d2 + p.h);
+    const double t = g * E, u = g * q, u2 = u * q;
+    m[0] += t; m[1] = fma(t, d, m[1]); m[2] = fma(t * d, d, m[2]);
+    m[3] += u; m[4] += u2; m[5] = fma(u2, d, m[5]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = 0; j < 6; ++j) {
+    const double r = warp_sum(m[j]);
+    if (lane == 0) red[warp][j] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int j = 0; j < 6; ++j) {
+    double r = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += red[w][j];
+    m[j] = r;
+  }
+  typedef Dual<2> D;  // tangents: fwhm2, fwhm_L
+  const ProfConst<D> pd = profile_consts<D>(D::variable(fwhm2[n], 0), D::variable(fwhm_L[n], 1), D(1.0),
+                                            wch * wch, true);
+  double g[2] = {0.0, 0.0};
+  const double bars[4] = {-p.AG * m[2], m[0], m[3], -p.AL * m[4]};  // kbar, AGbar, ALbar, hbar
+  const D* outs[4] = {&pd.k, &pd.AG, &pd.AL, &pd.h};
+  for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < 2; ++i) g[i] = fma(bars[j], outs[j]->d[i], g[i]);
+  g_velocity[n] = 2.0 * p.k * p.AG * m[1] + 2.0 * p.AL * m[5];
+  g_fwhm2[n] = g[0];
+  g_fwhm_L[n] = g[1];
+}
+
+// VJP of physics.radiative_transfer: gbar[S] -> g_tau[S][N] and (atomically summed over
+// channels into zeroed outputs) g_tspin[N], g_ff[N].  N <= CHI_RT_MAX_CLOUDS.
+#define CHI_RT_MAX_CLOUDS 64
+__global__ void __launch_bounds__(128) k_radiative_transfer_vjp(int S, int N, const double* __restrict__ tau,
+                                                                const double* __restrict__ tspin,
+                                                                const double* __restrict__ ff, double bg,
+                                                                const double* __restrict__ gbar,
+                                                                double* __restrict__ g_tau,
+                                                                double* __restrict__ g_tspin,
+                                                                double* __restrict__ g_ff) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double om[CHI_RT_MAX_CLOUDS], Pn[CHI_RT_MAX_CLOUDS];
+  double P = 1.0;
+  for (int n = 0; n < N; ++n) {
+    om[n] = 1.0 - chi_exp(-tau[(int64_t)s * N + n]);
+    Pn[n] = P;
+    P *= fma(-ff[n], om[n], 1.0);
+  }
+  const double mubar = gbar[s];
+  double Q = bg;
+  for (int n = N - 1; n >= 0; --n) {
+    const double f = ff[n], Ts = tspin[n];
+    const double Sn = Ts - Q, x = om[n] * Pn[n];
+    g_tau[(int64_t)s * N + n] = mubar * f * Sn * (Pn[n] - x);
+    atomicAdd(&g_tspin[n], mubar * f * x);
+    atomicAdd(&g_ff[n], mubar * x * Sn);
+    Q = fma(fma(-f, om[n], 1.0), Q, f * Ts * om[n]);
+  }
 }
 
 // chi_deterministics: every pm.Deterministic of the model class

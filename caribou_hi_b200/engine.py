@@ -347,6 +347,24 @@ class Engine:
         )
         return tuple(x.reshape(shape) for x in g)
 
+    ELEMENTWISE = {"gaussian": 0, "lorentzian": 1, "log10_column_density": 2, "log10_nonthermal_pressure": 3}
+
+    def elementwise(self, fn, a, b, c=None):
+        """``physics.gaussian/lorentzian(x, center, fwhm)``, ``calc_log10_column_density
+        (tau_total, spin_temp)`` and ``calc_log10_nonthermal_pressure(log10_density,
+        fwhm2_nonthermal)`` with NumPy broadcasting, evaluated on the device."""
+        args = [np.asarray(x, dtype=np.float64) for x in ((a, b) if c is None else (a, b, c))]
+        args = np.broadcast_arrays(*args)
+        shape = args[0].shape
+        flat = [_f64(x).ravel() for x in args]
+        out = np.empty_like(flat[0])
+        self._check(
+            self._lib.chi_elementwise(self._h, self.ELEMENTWISE[fn], flat[0].size, _lib.as_dp(flat[0]),
+                                      _lib.as_dp(flat[1]), _lib.as_dp(flat[2]) if c is not None else None,
+                                      _lib.as_dp(out))
+        )
+        return out.reshape(shape)
+
     def pseudo_voigt(self, velo_axis, velocity, fwhm2, fwhm_L):
         v = _f64(velo_axis)
         c = _f64(np.atleast_1d(velocity))
@@ -371,6 +389,39 @@ class Engine:
                                              float(bg_temp), _lib.as_dp(out))
         )
         return out
+
+    def pseudo_voigt_vjp(self, velo_axis, velocity, fwhm2, fwhm_L, gbar):
+        """Gradients of ``sum(gbar * pseudo_voigt)`` w.r.t. velocity, fwhm2, fwhm_L (``[N]``)."""
+        v = _f64(velo_axis)
+        c = _f64(np.atleast_1d(velocity))
+        N = c.shape[0]
+        w = _f64(np.broadcast_to(np.asarray(fwhm2, dtype=np.float64), (N,)))
+        fl = _f64(np.broadcast_to(np.asarray(fwhm_L, dtype=np.float64), (N,)))
+        gb = _f64(gbar, (v.shape[0], N), "gbar")
+        g = [np.empty(N, dtype=np.float64) for _ in range(3)]
+        self._check(
+            self._lib.chi_pseudo_voigt_vjp(self._h, v.shape[0], N, _lib.as_dp(v), _lib.as_dp(c), _lib.as_dp(w),
+                                           _lib.as_dp(fl), _lib.as_dp(gb), *(_lib.as_dp(x) for x in g))
+        )
+        return tuple(g)
+
+    def radiative_transfer_vjp(self, tau, tspin, filling_factor, bg_temp, gbar):
+        """Gradients of ``sum(gbar * radiative_transfer)`` w.r.t. tau ``[S, N]``, tspin and
+        filling_factor (``[N]``)."""
+        tau = _f64(tau)
+        S, N = tau.shape
+        ts = _f64(np.broadcast_to(np.asarray(tspin, dtype=np.float64), (N,)))
+        ff = _f64(np.broadcast_to(np.asarray(filling_factor, dtype=np.float64), (N,)))
+        gb = _f64(gbar, (S,), "gbar")
+        g_tau = np.empty((S, N), dtype=np.float64)
+        g_ts = np.empty(N, dtype=np.float64)
+        g_ff = np.empty(N, dtype=np.float64)
+        self._check(
+            self._lib.chi_radiative_transfer_vjp(self._h, S, N, _lib.as_dp(tau), _lib.as_dp(ts), _lib.as_dp(ff),
+                                                 float(bg_temp), _lib.as_dp(gb), _lib.as_dp(g_tau),
+                                                 _lib.as_dp(g_ts), _lib.as_dp(g_ff))
+        )
+        return g_tau, g_ts, g_ff
 
     # ---- measurement -------------------------------------------------------------
     def last_kernel_ms(self):

@@ -1,0 +1,128 @@
+"""Multi-GPU layer: one process per GPU (``torchrun``), the batch of independent
+evaluations (draws x chains x sightlines) split contiguously across ranks.
+
+The arithmetic has no exchange step: every draw is independent, so shards never talk to
+each other while computing.  ``torch.distributed`` (NCCL over NVLink on GPUs, gloo on CPU
+in the tests) is used only to *collect* results:
+
+* ``gather_rows``      all-gather per-draw ``logp[B_local]`` / ``grad[B_local, ...]`` back
+                       into batch order (uneven shards are padded for the collective)
+* ``reduce_sum``       all-reduce of per-shard sums (survey-total logp / gradient)
+
+Posterior-predictive spectra stay sharded on purpose: 1e6 draws x 8192 channels x 8 B is
+65 GB, far more than any consumer wants on one rank.
+"""
+
+import numpy as np
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous split: ranks ``< n_items % world_size`` get one extra item."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad world_size/rank")
+    base, extra = divmod(int(n_items), int(world_size))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_items, world_size):
+    return [shard_bounds(n_items, world_size, r)[1] - shard_bounds(n_items, world_size, r)[0]
+            for r in range(world_size)]
+
+
+def shard_by_sightline(sightline, world_size, rank):
+    """Survey sharding (BASELINE configs[3]): all draws of a sightline go to the rank that
+    owns the sightline, so each GPU only needs its own sightlines' spectra.  Returns the
+    indices of the draws owned by ``rank`` (ascending) and the owned sightline range."""
+    sightline = np.asarray(sightline)
+    n_sl = int(sightline.max()) + 1 if sightline.size else 0
+    lo, hi = shard_bounds(n_sl, world_size, rank)
+    idx = np.nonzero((sightline >= lo) & (sightline < hi))[0]
+    return idx, (lo, hi)
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def world():
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def gather_rows(local, n_total, device=None):
+    """All-gather row blocks of a contiguous split back into one ``[n_total, ...]`` tensor on
+    every rank.  ``local`` is a torch tensor (CUDA with NCCL, CPU with gloo) holding this
+    rank's rows."""
+    import torch
+
+    dist = _dist()
+    ws, rank = world()
+    if ws == 1:
+        return local
+    sizes = shard_sizes(n_total, ws)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank}: expected {sizes[rank]} rows, got {local.shape[0]}")
+    pad = max(sizes)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[: sizes[rank]] = local
+    out = torch.empty((ws * pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf)
+    parts = [out[r * pad : r * pad + sizes[r]] for r in range(ws)]
+    return torch.cat(parts, dim=0)
+
+
+def reduce_sum(local):
+    """All-reduce(sum) of a per-shard partial (e.g. survey-total logp and gradient)."""
+    dist = _dist()
+    ws, _ = world()
+    if ws > 1:
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+    return local
+
+
+class ShardedLikelihood:
+    """Evaluates this rank's shard of a batch on its own GPU and collects the results.
+
+    ``evaluate`` is any callable ``theta_local -> (logp_local, grad_local)`` on NumPy arrays
+    (normally ``lambda th: engine.logp_grad(th)[:2]``); keeping it a callable lets the CPU
+    test-suite drive the sharding/collection logic under gloo without a GPU.
+    """
+
+    def __init__(self, evaluate, device=None):
+        self.evaluate = evaluate
+        self.device = device
+
+    def logp_grad(self, theta):
+        """``theta [B, ...]`` is the FULL batch, identical on every rank; returns the full
+        ``(logp [B], grad [B, ...])`` on every rank."""
+        import torch
+
+        ws, rank = world()
+        B = theta.shape[0]
+        lo, hi = shard_bounds(B, ws, rank)
+        logp, grad = self.evaluate(theta[lo:hi])
+        if ws == 1:
+            return logp, grad
+        dev = self.device if self.device is not None else "cpu"
+        lp = gather_rows(torch.as_tensor(logp).to(dev), B)
+        gr = gather_rows(torch.as_tensor(grad).to(dev), B)
+        return lp.cpu().numpy(), gr.cpu().numpy()
+
+    def total_logp_grad(self, theta):
+        """Sum over the whole batch (hierarchical / survey-total use): only one scalar and
+        one gradient block cross the interconnect."""
+        import torch
+
+        ws, rank = world()
+        lo, hi = shard_bounds(theta.shape[0], ws, rank)
+        logp, grad = self.evaluate(theta[lo:hi])
+        dev = self.device if self.device is not None else "cpu"
+        packed = torch.cat([torch.as_tensor(np.nansum(logp, keepdims=True)).reshape(1),
+                            torch.as_tensor(np.nansum(grad, axis=0)).reshape(-1)]).to(dev)
+        packed = reduce_sum(packed).cpu().numpy()
+        return packed[0], packed[1:].reshape(grad.shape[1:])

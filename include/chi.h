@@ -195,6 +195,19 @@ int chi_spin_temp(chi_handle* h, int64_t n, const double* kinetic_temp, const do
 int chi_spin_temp_vjp(chi_handle* h, int64_t n, const double* kinetic_temp, const double* density,
                       const double* n_alpha, const double* gbar, double* g_kinetic_temp,
                       double* g_density, double* g_n_alpha);
+/* The elementwise helpers of physics.py that the reference evaluates through PyTensor
+ * (tests/test_physics.py .eval()s them): out[i] = fn(a[i], b[i], c[i]).
+ *   CHI_FN_GAUSSIAN                   a=x, b=center, c=fwhm          physics.py:16-35
+ *   CHI_FN_LORENTZIAN                 a=x, b=center, c=fwhm          physics.py:38-55
+ *   CHI_FN_LOG10_COLUMN_DENSITY       a=tau_total, b=spin_temp       physics.py:191-207
+ *   CHI_FN_LOG10_NONTHERMAL_PRESSURE  a=log10_density, b=fwhm2_nth   physics.py:247-262
+ * c may be NULL for the two-argument functions. */
+#define CHI_FN_GAUSSIAN 0
+#define CHI_FN_LORENTZIAN 1
+#define CHI_FN_LOG10_COLUMN_DENSITY 2
+#define CHI_FN_LOG10_NONTHERMAL_PRESSURE 3
+int chi_elementwise(chi_handle* h, int fn, int64_t n, const double* a, const double* b, const double* c,
+                    double* out);
 /* physics.calc_pseudo_voigt (physics.py:265-309): profile_out[S][N].  fwhm_L has
  * N entries (replicate a scalar). */
 int chi_pseudo_voigt(chi_handle* h, int S, int N, const double* velo_axis, const double* velocity,
@@ -203,6 +216,15 @@ int chi_pseudo_voigt(chi_handle* h, int S, int N, const double* velo_axis, const
  * filling_factor has N entries (replicate a scalar). */
 int chi_radiative_transfer(chi_handle* h, int S, int N, const double* tau, const double* tspin,
                            const double* filling_factor, double bg_temp, double* tb_out);
+/* Their vector-Jacobian products (what PyTensor's grad of physics.py:265-309 and
+ * physics.py:312-365 yields): gbar[S][N] -> gradients w.r.t. velocity, fwhm2, fwhm_L (N each);
+ * gbar[S] -> g_tau[S][N], g_tspin[N], g_filling_factor[N] (N <= 64). */
+int chi_pseudo_voigt_vjp(chi_handle* h, int S, int N, const double* velo_axis, const double* velocity,
+                         const double* fwhm2, const double* fwhm_L, const double* gbar,
+                         double* g_velocity, double* g_fwhm2, double* g_fwhm_L);
+int chi_radiative_transfer_vjp(chi_handle* h, int S, int N, const double* tau, const double* tspin,
+                               const double* filling_factor, double bg_temp, const double* gbar,
+                               double* g_tau, double* g_tspin, double* g_filling_factor);
 
 /* ---- model-level entry points (need chi_set_spectra) ----------------------- */
 /* Likelihood logp and its gradient for B independent evaluations (draws x chains x
