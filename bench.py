@@ -60,7 +60,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -300,9 +300,11 @@ def run_b200(args):
         pin_th[k].array[...] = thetas[k]
     pin_lp = PinnedArray((draws,))
     pin_gr = PinnedArray((draws, 10, N))
-    ce_h = np.zeros((draws, 1))
-    ca_h = np.zeros((draws, 1))
-    out = {"logp": pin_lp.array, "grad": pin_gr.array}
+    pins = [PinnedArray((draws, 1)) for _ in range(4)]  # coefficients in, coefficient gradients out
+    ce_h, ca_h = pins[0].array, pins[1].array
+    ce_h[...] = 0.0
+    ca_h[...] = 0.0
+    out = {"logp": pin_lp.array, "grad": pin_gr.array, "gcoeff_e": pins[2].array, "gcoeff_a": pins[3].array}
     eng.logp_grad(pin_th[0].array, ce_h, ca_h, out=out)  # warm-up (allocates staging)
     barrier()
     t0 = time.perf_counter()
@@ -369,7 +371,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--draws", type=int, default=DRAWS)

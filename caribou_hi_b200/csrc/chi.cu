@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -12,6 +13,7 @@
 
 #include "../../include/chi.h"
 #include "kernels.cuh"
+#include "moments_win.cuh"
 
 #define CHI_STAGE_RING 64
 
@@ -44,9 +46,24 @@ struct Buf {
 
 struct DevDataset {
   int S = 0, nb = 0;
+  int dir = 0;  // +1/-1 strictly ascending/descending axis, 0 otherwise
   bool has_offset = false;
   Buf vax, yeff, wgt, basis, offset;
   void release() { vax.release(); yeff.release(); wgt.release(); basis.release(); offset.release(); }
+};
+
+// One pipeline lane: a stream plus the device workspace a batch needs.  Lane 0 uses the
+// handle's public stream; the host entry points rotate sub-batches over all lanes so that
+// host->device copies, kernels and device->host copies of consecutive sub-batches overlap.
+#define CHI_LANES 3
+struct Lane {
+  cudaStream_t st = nullptr;
+  Buf cc, mom_e, mom_a;                                           // kernel workspace
+  Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca;    // staging of the host entry points
+  void release() {
+    Buf* bufs[] = {&cc, &mom_e, &mom_a, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
+    for (Buf* b : bufs) b->release();
+  }
 };
 
 }  // namespace
@@ -67,11 +84,13 @@ struct chi_handle {
   int n_sl = 0;
   DevDataset e, a;
   Buf lconst;
-  // workspace for host entry points
-  Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca, w_gbe, w_gba, w_mue, w_mua, w_misc[8];
-  // internal workspace
-  Buf cc, mom_e, mom_a;
+  Lane lanes[CHI_LANES];
+  // further staging of the host entry points (single-lane paths)
+  Buf w_gbe, w_gba, w_mue, w_mua, w_misc[8];
+  int64_t call_first_stage = 0;  // stage_calls at the start of the current model-level call
   int64_t launches = 0;
+  int kernel_family = 1;  // 1: moments.cuh (default), 2: moments_win.cuh (env CHI_KERNEL=2)
+  int cpt = 2;            // channels per thread of family 2
   std::string err;
 };
 
@@ -137,21 +156,23 @@ int dispatch_np(int N, bool pv, A... args) {
   return -1;
 }
 
+inline unsigned warp_grid(const ChanArgs& a) {
+  int64_t items = a.B * a.n_chunks;
+  return (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
+}
 template <int N, bool PV>
 struct LaunchEm {
-  static int run(const ChanArgs& a, cudaStream_t st) {
-    int64_t items = a.B * a.n_chunks;
-    unsigned grid = (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
-    k_moments_em<N, PV><<<grid, CHI_BLOCK, 0, st>>>(a);
+  static int run(const ChanArgs& a, cudaStream_t st, int family, int cpt) {
+    if (family == 1) k_moments_em<N, PV><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
+    else k_moments_em2<N, PV, 2><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
     return 0;
   }
 };
 template <int N, bool PV>
 struct LaunchAb {
-  static int run(const ChanArgs& a, cudaStream_t st) {
-    int64_t items = a.B * a.n_chunks;
-    unsigned grid = (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
-    k_moments_abs<N, PV><<<grid, CHI_BLOCK, 0, st>>>(a);
+  static int run(const ChanArgs& a, cudaStream_t st, int family, int cpt) {
+    if (family == 1) k_moments_abs<N, PV><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
+    else k_moments_abs2<N, PV, 2><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
     return 0;
   }
 };
@@ -167,28 +188,27 @@ struct LaunchAb {
     case CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL: { constexpr int M = CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL; STMT; } break; \
   }
 
-int launch_cloud_map(chi_handle* h, int64_t B, const double* theta) {
+int launch_cloud_map(chi_handle* h, Lane& L, int64_t B, const double* theta) {
   const int N = h->cfg.n_clouds;
-  CK(h->cc.ensure((size_t)B * N * CHI_CC_STRIDE * sizeof(double)));
+  CK(L.cc.ensure((size_t)B * N * CHI_CC_STRIDE * sizeof(double)));
   unsigned grid = (unsigned)((B * N + 127) / 128);
-  MODEL_SWITCH(h->cfg.model, (k_cloud_map<M><<<grid, 128, 0, h->stream>>>(h->map, B, N, theta, h->cc.d())));
+  MODEL_SWITCH(h->cfg.model, (k_cloud_map<M><<<grid, 128, 0, L.st>>>(h->map, B, N, theta, L.cc.d())));
   h->launches++;
   CK(cudaGetLastError());
   return CHI_OK;
 }
 
 // moments (+ optional logp) + epilogue; gbar_* != null selects the VJP mode
-int run_backward(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const double* ce, const double* ca,
                  const int32_t* sl, const double* gbar_e, const double* gbar_a, bool vjp, double* logp,
                  double* grad, double* gce, double* gca) {
   const int N = h->cfg.n_clouds;
   const bool pv = h->cfg.lorentzian != 0;
-  CK(cudaEventRecord(h->ev0, h->stream));
   cudaEvent_t* evs = h->ring[h->stage_calls % CHI_STAGE_RING];
-  CK(cudaEventRecord(evs[0], h->stream));
-  int rc = launch_cloud_map(h, B, theta);
+  CK(cudaEventRecord(evs[0], L.st));
+  int rc = launch_cloud_map(h, L, B, theta);
   if (rc) return rc;
-  CK(cudaEventRecord(evs[1], h->stream));
+  CK(cudaEventRecord(evs[1], L.st));
 
   EpiArgs ea;
   memset(&ea, 0, sizeof(ea));
@@ -205,56 +225,57 @@ int run_backward(chi_handle* h, int64_t B, const double* theta, const double* ce
     a.B = B; a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp;
     pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = em_record(h);
-    CK(h->mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
+    a.axis_dir = h->e.dir;
+    CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.vax = h->e.vax.d(); a.yeff = h->e.yeff.d(); a.wgt = h->e.wgt.d(); a.basis = h->e.basis.d();
-    a.coeff = ce; a.sl = sl; a.gbar = vjp ? gbar_e : nullptr; a.cc = h->cc.d(); a.mom = h->mom_e.d();
-    if (dispatch_np<LaunchEm>(N, pv, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    a.coeff = ce; a.sl = sl; a.gbar = vjp ? gbar_e : nullptr; a.cc = L.cc.d(); a.mom = L.mom_e.d();
+    if (dispatch_np<LaunchEm>(N, pv, a, L.st, h->kernel_family, h->cpt)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
     ea.has_e = 1; ea.nb_e = a.n_base; ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride;
-    ea.mom_e = h->mom_e.d();
+    ea.mom_e = L.mom_e.d();
   }
-  CK(cudaEventRecord(evs[2], h->stream));
+  CK(cudaEventRecord(evs[2], L.st));
   if (do_a) {
     ChanArgs a;
     memset(&a, 0, sizeof(a));
     a.B = B; a.S = h->a.S; a.n_base = h->a.nb; a.bg = 0.0;
     pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = ab_record(h);
-    CK(h->mom_a.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
+    a.axis_dir = h->a.dir;
+    CK(L.mom_a.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.vax = h->a.vax.d(); a.yeff = h->a.yeff.d(); a.wgt = h->a.wgt.d(); a.basis = h->a.basis.d();
-    a.coeff = ca; a.sl = sl; a.gbar = vjp ? gbar_a : nullptr; a.cc = h->cc.d(); a.mom = h->mom_a.d();
-    if (dispatch_np<LaunchAb>(N, pv, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    a.coeff = ca; a.sl = sl; a.gbar = vjp ? gbar_a : nullptr; a.cc = L.cc.d(); a.mom = L.mom_a.d();
+    if (dispatch_np<LaunchAb>(N, pv, a, L.st, h->kernel_family, h->cpt)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
     ea.has_a = 1; ea.nb_a = a.n_base; ea.chunks_a = a.n_chunks; ea.stride_a = a.mom_stride;
-    ea.mom_a = h->mom_a.d();
+    ea.mom_a = L.mom_a.d();
   }
-  CK(cudaEventRecord(evs[3], h->stream));
+  CK(cudaEventRecord(evs[3], L.st));
   // baseline-coefficient gradients of a dataset that did not run are zero
-  if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), h->stream));
-  if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), h->stream));
+  if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), L.st));
+  if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), L.st));
 
   unsigned grid = (unsigned)((B * N + 127) / 128);
-  MODEL_SWITCH(h->cfg.model, (k_epilogue<M><<<grid, 128, 0, h->stream>>>(h->map, ea)));
+  MODEL_SWITCH(h->cfg.model, (k_epilogue<M><<<grid, 128, 0, L.st>>>(h->map, ea)));
   h->launches++;
   CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev1, h->stream));
-  CK(cudaEventRecord(evs[4], h->stream));
+  CK(cudaEventRecord(evs[4], L.st));
   h->stage_calls++;
-  h->ev_pending = true;
   return CHI_OK;
 }
 
 int run_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
                 double* mu_e, double* mu_a) {
   const int N = h->cfg.n_clouds;
+  h->call_first_stage = h->stage_calls;  // no logp/VJP stage events belong to this call
   CK(cudaEventRecord(h->ev0, h->stream));
-  int rc = launch_cloud_map(h, B, theta);
+  int rc = launch_cloud_map(h, h->lanes[0], B, theta);
   if (rc) return rc;
   SpecArgs a;
   memset(&a, 0, sizeof(a));
-  a.B = B; a.N = N; a.pv = h->cfg.lorentzian != 0; a.cc = h->cc.d();
+  a.B = B; a.N = N; a.pv = h->cfg.lorentzian != 0; a.cc = h->lanes[0].cc.d();
   if (mu_e && h->has_e) {
     a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp; a.vax = h->e.vax.d();
     a.basis = h->e.basis.d(); a.offset = h->e.has_offset ? h->e.offset.d() : nullptr;
@@ -295,6 +316,15 @@ int upload_dataset(chi_handle* h, DevDataset& d, const chi_dataset* src, int n_s
   d.S = S;
   d.nb = src->n_baseline;
   d.has_offset = src->offset != nullptr;
+  {
+    bool up = true, down = true;
+    for (int s = 1; s < S; ++s) {
+      up = up && src->spectral[s] > src->spectral[s - 1];
+      down = down && src->spectral[s] < src->spectral[s - 1];
+    }
+    d.dir = up ? 1 : (down ? -1 : 0);
+    if (getenv("CHI_NOWIN")) d.dir = 0;  // experiment knob: disable the active-window skipping
+  }
   std::vector<double> yeff((size_t)n_sl * S), wgt((size_t)n_sl * S);
   const double half_log_2pi = 0.5 * log(2.0 * M_PI);
   for (int i = 0; i < n_sl; ++i) {
@@ -394,6 +424,7 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
   h->cfg = *cfg;
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
+  if (const char* e = getenv("CHI_KERNEL")) h->kernel_family = atoi(e) == 2 ? 2 : 1;
   const int m = cfg->model;
   h->has_e = (m == CHI_MODEL_PHYSICS) ? cfg->has_emission != 0 : kind_has_emission(m);
   h->has_a = (m == CHI_MODEL_PHYSICS) ? cfg->has_absorption != 0 : kind_has_absorption(m);
@@ -413,8 +444,12 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
   mc.prior_fwhm_L = cfg->prior_fwhm_L;
   mc.prior_amp = cfg->prior_amplitude;
   mc.const_G = sqrt(2.0 * M_PI) / (2.0 * sqrt(2.0 * log(2.0)));  // emission_model.py:127
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || !make_ring(h)) {
+  bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess && make_ring(h);
+  h->lanes[0].st = h->stream;
+  for (int i = 1; ok && i < CHI_LANES; ++i)
+    ok = cudaStreamCreateWithFlags(&h->lanes[i].st, cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) {
     delete h;
     return fail(nullptr, CHI_ECUDA, "chi_create: stream/event creation failed");
   }
@@ -425,10 +460,11 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
 void chi_destroy(chi_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (Lane& L : h->lanes)
+    if (L.st) cudaStreamSynchronize(L.st);
   h->e.release(); h->a.release(); h->lconst.release();
-  Buf* bufs[] = {&h->w_theta, &h->w_ce, &h->w_ca, &h->w_sl, &h->w_logp, &h->w_grad, &h->w_gce, &h->w_gca,
-                 &h->w_gbe, &h->w_gba, &h->w_mue, &h->w_mua, &h->cc, &h->mom_e, &h->mom_a};
+  for (Lane& L : h->lanes) L.release();
+  Buf* bufs[] = {&h->w_gbe, &h->w_gba, &h->w_mue, &h->w_mua};
   for (Buf* b : bufs) b->release();
   for (Buf& b : h->w_misc) b.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -436,7 +472,8 @@ void chi_destroy(chi_handle* h) {
   for (auto& row : h->ring)
     for (cudaEvent_t e : row)
       if (e) cudaEventDestroy(e);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  for (Lane& L : h->lanes)
+    if (L.st) cudaStreamDestroy(L.st);
   delete h;
 }
 
@@ -445,7 +482,7 @@ void* chi_stream(chi_handle* h) { return h ? (void*)h->stream : nullptr; }
 int chi_synchronize(chi_handle* h) {
   if (!h) return CHI_EINVAL;
   CK(cudaSetDevice(h->device));
-  CK(cudaStreamSynchronize(h->stream));
+  for (Lane& L : h->lanes) CK(cudaStreamSynchronize(L.st));
   return CHI_OK;
 }
 
@@ -678,8 +715,9 @@ int chi_logp_grad_dev(chi_handle* h, int64_t B, const double* theta, const doubl
   if (!logp) return fail(h, CHI_EINVAL, "chi_logp_grad: logp_out is NULL");
   if (B == 0) return CHI_OK;
   CK(cudaSetDevice(h->device));
+  h->call_first_stage = h->stage_calls;
   h->kernel_ms = 0.f;
-  return run_backward(h, B, theta, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca);
+  return run_backward(h, h->lanes[0], B, theta, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca);
 }
 
 int chi_spectra_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
@@ -699,8 +737,9 @@ int chi_spectra_vjp_dev(chi_handle* h, int64_t B, const double* theta, const dou
   if (!grad) return fail(h, CHI_EINVAL, "chi_spectra_vjp: grad_out is NULL");
   if (B == 0) return CHI_OK;
   CK(cudaSetDevice(h->device));
+  h->call_first_stage = h->stage_calls;
   h->kernel_ms = 0.f;
-  return run_backward(h, B, theta, ce, ca, nullptr, gbar_e, gbar_a, true, nullptr, grad, gce, gca);
+  return run_backward(h, h->lanes[0], B, theta, ce, ca, nullptr, gbar_e, gbar_a, true, nullptr, grad, gce, gca);
 }
 
 // ---- model-level, host pointers ---------------------------------------------------
@@ -716,44 +755,51 @@ int chi_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* c
   const int N = h->cfg.n_clouds;
   const size_t th_b = (size_t)CHI_NSLOT * N * sizeof(double);
   const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
-  const int64_t sub = host_sub_batch(h, 4096);
+  // Sub-batches rotate over the lanes: while one lane computes, the next one uploads its
+  // parameters and the previous one downloads its results (stream order keeps each lane's
+  // buffers safe).  Large batches are cut into at least 2*CHI_LANES pieces.
+  int64_t sub = host_sub_batch(h, 4096);
+  int pieces = 2 * CHI_LANES;
+  if (const char* e = getenv("CHI_PIPE_PIECES")) pieces = std::max(1, atoi(e));  // tuning knob
+  if (B >= 8192) sub = std::min<int64_t>(sub, std::max<int64_t>(4096, (B + pieces - 1) / pieces));
+  h->call_first_stage = h->stage_calls;
   h->kernel_ms = 0.f;
-  for (int64_t b0 = 0; b0 < B; b0 += sub) {
+  int lane_i = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += sub, lane_i = (lane_i + 1) % CHI_LANES) {
+    Lane& L = h->lanes[lane_i];
     const int64_t nb = std::min(sub, B - b0);
-    CK(h->w_theta.ensure(nb * th_b));
-    CK(h->w_logp.ensure(nb * sizeof(double)));
-    CK(cudaMemcpyAsync(h->w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    CK(L.w_theta.ensure(nb * th_b));
+    CK(L.w_logp.ensure(nb * sizeof(double)));
+    CK(cudaMemcpyAsync(L.w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, L.st));
     double *d_ce = nullptr, *d_ca = nullptr, *d_grad = nullptr, *d_gce = nullptr, *d_gca = nullptr;
     int32_t* d_sl = nullptr;
     if (ce && nbe) {
-      CK(h->w_ce.ensure(nb * nbe * sizeof(double)));
-      CK(cudaMemcpyAsync(h->w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      d_ce = h->w_ce.d();
+      CK(L.w_ce.ensure(nb * nbe * sizeof(double)));
+      CK(cudaMemcpyAsync(L.w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, L.st));
+      d_ce = L.w_ce.d();
     }
     if (ca && nba) {
-      CK(h->w_ca.ensure(nb * nba * sizeof(double)));
-      CK(cudaMemcpyAsync(h->w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      d_ca = h->w_ca.d();
+      CK(L.w_ca.ensure(nb * nba * sizeof(double)));
+      CK(cudaMemcpyAsync(L.w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, L.st));
+      d_ca = L.w_ca.d();
     }
     if (sl) {
-      CK(h->w_sl.ensure(nb * sizeof(int32_t)));
-      CK(cudaMemcpyAsync(h->w_sl.p, sl + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-      d_sl = (int32_t*)h->w_sl.p;
+      CK(L.w_sl.ensure(nb * sizeof(int32_t)));
+      CK(cudaMemcpyAsync(L.w_sl.p, sl + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, L.st));
+      d_sl = (int32_t*)L.w_sl.p;
     }
-    if (grad) { CK(h->w_grad.ensure(nb * th_b)); d_grad = h->w_grad.d(); }
-    if (gce && nbe) { CK(h->w_gce.ensure(nb * nbe * sizeof(double))); d_gce = h->w_gce.d(); }
-    if (gca && nba) { CK(h->w_gca.ensure(nb * nba * sizeof(double))); d_gca = h->w_gca.d(); }
-    rc = run_backward(h, nb, h->w_theta.d(), d_ce, d_ca, d_sl, nullptr, nullptr, false, h->w_logp.d(), d_grad,
+    if (grad) { CK(L.w_grad.ensure(nb * th_b)); d_grad = L.w_grad.d(); }
+    if (gce && nbe) { CK(L.w_gce.ensure(nb * nbe * sizeof(double))); d_gce = L.w_gce.d(); }
+    if (gca && nba) { CK(L.w_gca.ensure(nb * nba * sizeof(double))); d_gca = L.w_gca.d(); }
+    rc = run_backward(h, L, nb, L.w_theta.d(), d_ce, d_ca, d_sl, nullptr, nullptr, false, L.w_logp.d(), d_grad,
                       d_gce, d_gca);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(logp + b0, h->w_logp.p, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (d_grad) CK(cudaMemcpyAsync(grad + b0 * CHI_NSLOT * N, d_grad, nb * th_b, cudaMemcpyDeviceToHost, h->stream));
-    if (d_gce) CK(cudaMemcpyAsync(gce + b0 * nbe, d_gce, nb * nbe * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    rc = finish_timing(h);
-    if (rc) return rc;
+    CK(cudaMemcpyAsync(logp + b0, L.w_logp.p, nb * sizeof(double), cudaMemcpyDeviceToHost, L.st));
+    if (d_grad) CK(cudaMemcpyAsync(grad + b0 * CHI_NSLOT * N, d_grad, nb * th_b, cudaMemcpyDeviceToHost, L.st));
+    if (d_gce) CK(cudaMemcpyAsync(gce + b0 * nbe, d_gce, nb * nbe * sizeof(double), cudaMemcpyDeviceToHost, L.st));
+    if (d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, L.st));
   }
+  for (Lane& L : h->lanes) CK(cudaStreamSynchronize(L.st));
   return CHI_OK;
 }
 
@@ -770,22 +816,22 @@ int chi_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce,
   h->kernel_ms = 0.f;
   for (int64_t b0 = 0; b0 < B; b0 += sub) {
     const int64_t nb = std::min(sub, B - b0);
-    CK(h->w_theta.ensure(nb * th_b));
-    CK(cudaMemcpyAsync(h->w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    CK(h->lanes[0].w_theta.ensure(nb * th_b));
+    CK(cudaMemcpyAsync(h->lanes[0].w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
     double *d_ce = nullptr, *d_ca = nullptr, *d_me = nullptr, *d_ma = nullptr;
     if (ce && nbe) {
-      CK(h->w_ce.ensure(nb * nbe * sizeof(double)));
-      CK(cudaMemcpyAsync(h->w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      d_ce = h->w_ce.d();
+      CK(h->lanes[0].w_ce.ensure(nb * nbe * sizeof(double)));
+      CK(cudaMemcpyAsync(h->lanes[0].w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ce = h->lanes[0].w_ce.d();
     }
     if (ca && nba) {
-      CK(h->w_ca.ensure(nb * nba * sizeof(double)));
-      CK(cudaMemcpyAsync(h->w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      d_ca = h->w_ca.d();
+      CK(h->lanes[0].w_ca.ensure(nb * nba * sizeof(double)));
+      CK(cudaMemcpyAsync(h->lanes[0].w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ca = h->lanes[0].w_ca.d();
     }
     if (mu_e && Se) { CK(h->w_mue.ensure((size_t)nb * Se * sizeof(double))); d_me = h->w_mue.d(); }
     if (mu_a && Sa) { CK(h->w_mua.ensure((size_t)nb * Sa * sizeof(double))); d_ma = h->w_mua.d(); }
-    rc = run_spectra(h, nb, h->w_theta.d(), d_ce, d_ca, d_me, d_ma);
+    rc = run_spectra(h, nb, h->lanes[0].w_theta.d(), d_ce, d_ca, d_me, d_ma);
     if (rc) return rc;
     if (d_me) CK(cudaMemcpyAsync(mu_e + b0 * Se, d_me, (size_t)nb * Se * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (d_ma) CK(cudaMemcpyAsync(mu_a + b0 * Sa, d_ma, (size_t)nb * Sa * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -810,19 +856,19 @@ int chi_spectra_vjp(chi_handle* h, int64_t B, const double* theta, const double*
   h->kernel_ms = 0.f;
   for (int64_t b0 = 0; b0 < B; b0 += sub) {
     const int64_t nb = std::min(sub, B - b0);
-    CK(h->w_theta.ensure(nb * th_b));
-    CK(h->w_grad.ensure(nb * th_b));
-    CK(cudaMemcpyAsync(h->w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    CK(h->lanes[0].w_theta.ensure(nb * th_b));
+    CK(h->lanes[0].w_grad.ensure(nb * th_b));
+    CK(cudaMemcpyAsync(h->lanes[0].w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
     double *d_ce = nullptr, *d_ca = nullptr, *d_ge = nullptr, *d_ga = nullptr, *d_gce = nullptr, *d_gca = nullptr;
     if (ce && nbe) {
-      CK(h->w_ce.ensure(nb * nbe * sizeof(double)));
-      CK(cudaMemcpyAsync(h->w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      d_ce = h->w_ce.d();
+      CK(h->lanes[0].w_ce.ensure(nb * nbe * sizeof(double)));
+      CK(cudaMemcpyAsync(h->lanes[0].w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ce = h->lanes[0].w_ce.d();
     }
     if (ca && nba) {
-      CK(h->w_ca.ensure(nb * nba * sizeof(double)));
-      CK(cudaMemcpyAsync(h->w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      d_ca = h->w_ca.d();
+      CK(h->lanes[0].w_ca.ensure(nb * nba * sizeof(double)));
+      CK(cudaMemcpyAsync(h->lanes[0].w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ca = h->lanes[0].w_ca.d();
     }
     if (gbar_e && Se) {
       CK(h->w_gbe.ensure((size_t)nb * Se * sizeof(double)));
@@ -834,11 +880,11 @@ int chi_spectra_vjp(chi_handle* h, int64_t B, const double* theta, const double*
       CK(cudaMemcpyAsync(h->w_gba.p, gbar_a + b0 * Sa, (size_t)nb * Sa * sizeof(double), cudaMemcpyHostToDevice, h->stream));
       d_ga = h->w_gba.d();
     }
-    if (gce && nbe) { CK(h->w_gce.ensure(nb * nbe * sizeof(double))); d_gce = h->w_gce.d(); }
-    if (gca && nba) { CK(h->w_gca.ensure(nb * nba * sizeof(double))); d_gca = h->w_gca.d(); }
-    rc = run_backward(h, nb, h->w_theta.d(), d_ce, d_ca, nullptr, d_ge, d_ga, true, nullptr, h->w_grad.d(), d_gce, d_gca);
+    if (gce && nbe) { CK(h->lanes[0].w_gce.ensure(nb * nbe * sizeof(double))); d_gce = h->lanes[0].w_gce.d(); }
+    if (gca && nba) { CK(h->lanes[0].w_gca.ensure(nb * nba * sizeof(double))); d_gca = h->lanes[0].w_gca.d(); }
+    rc = run_backward(h, h->lanes[0], nb, h->lanes[0].w_theta.d(), d_ce, d_ca, nullptr, d_ge, d_ga, true, nullptr, h->lanes[0].w_grad.d(), d_gce, d_gca);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(grad + b0 * CHI_NSLOT * N, h->w_grad.p, nb * th_b, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(grad + b0 * CHI_NSLOT * N, h->lanes[0].w_grad.p, nb * th_b, cudaMemcpyDeviceToHost, h->stream));
     if (d_gce) CK(cudaMemcpyAsync(gce + b0 * nbe, d_gce, nb * nbe * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -858,11 +904,11 @@ int chi_deterministics(chi_handle* h, int64_t B, const double* theta, double* de
   const int64_t sub = host_sub_batch(h, 4096);
   for (int64_t b0 = 0; b0 < B; b0 += sub) {
     const int64_t nb = std::min(sub, B - b0);
-    CK(h->w_theta.ensure(nb * th_b));
+    CK(h->lanes[0].w_theta.ensure(nb * th_b));
     CK(h->w_misc[0].ensure(nb * det_b));
-    CK(cudaMemcpyAsync(h->w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->lanes[0].w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
     unsigned grid = (unsigned)((nb * N + 127) / 128);
-    MODEL_SWITCH(h->cfg.model, (k_deterministics<M><<<grid, 128, 0, h->stream>>>(h->map, nb, N, h->w_theta.d(),
+    MODEL_SWITCH(h->cfg.model, (k_deterministics<M><<<grid, 128, 0, h->stream>>>(h->map, nb, N, h->lanes[0].w_theta.d(),
                                                                                  h->w_misc[0].d())));
     h->launches++;
     CK(cudaGetLastError());
@@ -876,9 +922,19 @@ int chi_deterministics(chi_handle* h, int64_t B, const double* theta, double* de
 int chi_last_kernel_ms(chi_handle* h, float* ms_out) {
   if (!h || !ms_out) return CHI_EINVAL;
   CK(cudaSetDevice(h->device));
-  int rc = finish_timing(h);
+  int rc = finish_timing(h);  // spectra path (ev0/ev1 on the public stream)
   if (rc) return rc;
-  *ms_out = h->kernel_ms;
+  float total = h->kernel_ms;
+  // logp / VJP path: sum of the stage events of the sub-batches of the last call
+  int64_t first = std::max(h->call_first_stage, h->stage_calls - CHI_STAGE_RING);
+  for (int64_t k = first; k < h->stage_calls; ++k) {
+    cudaEvent_t* evs = h->ring[k % CHI_STAGE_RING];
+    CK(cudaEventSynchronize(evs[4]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, evs[0], evs[4]));
+    total += ms;
+  }
+  *ms_out = total;
   return CHI_OK;
 }
 

@@ -13,7 +13,9 @@
 
 namespace chi {
 
+#ifndef CHI_WARPS_PER_BLOCK
 #define CHI_WARPS_PER_BLOCK 4
+#endif
 #define CHI_BLOCK (32 * CHI_WARPS_PER_BLOCK)
 #define CHI_FULL 0xffffffffu
 
@@ -80,6 +82,87 @@ __device__ __forceinline__ double chi_exp(double x, const ExpK& c) {
 }
 __device__ __forceinline__ double chi_exp(double x) { return chi_exp<true>(x, load_expk()); }
 
+// Table-driven variant used by the hot kernels: exp(x) = 2^m * T[j] * exp(r) with
+// n = rint(x * 64/ln2) = 64 m + j, |r| <= ln2/128, T[j] = 2^(j/64) in shared memory and
+// exp(r) - 1 = r + r^2 g(r), g of degree 3 (fit error 5e-18).  10 FP64-pipe instructions and a
+// dependent chain of 9 instead of 16 and 15: the pipe is the bound of these kernels and the
+// chain length sets how much parallelism is needed to fill it.  Result within ~1 ulp.
+__constant__ double c_expt[8] = {
+    92.33248261689366,        // 0  64/ln2
+    6755399441055744.0,       // 1  1.5 * 2^52
+    -0.010830424667801708,    // 2  -(ln2/64) hi (29 significant bits: n * hi is exact)
+    -2.8447437476627285e-11,  // 3  -(ln2/64) lo
+    0.008333339386755335,     // 4  g3
+    0.041666709040625166,     // 5  g2
+    0.1666666666666436,       // 6  g1
+    0.4999999999998384};      // 7  g0
+__constant__ double c_exp_table[64] = {
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+
+struct ExpT {
+  double k[8];
+  const double* T;  // shared-memory copy of c_exp_table
+};
+__device__ __forceinline__ ExpT load_expt(const double* shared_table) {
+  ExpT e;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e.k[i] = c_expt[i];
+  e.T = shared_table;
+  return e;
+}
+// every thread of the block must call this before any early exit (block barrier inside)
+__device__ __forceinline__ void fill_exp_table(double* shared_table) {
+  if (threadIdx.x < 64) shared_table[threadIdx.x] = c_exp_table[threadIdx.x];
+  __syncthreads();
+}
+
+template <bool OVERFLOW = true>
+__device__ __forceinline__ double chi_exp(double x, const ExpT& c) {
+  const int hi = __double2hiint(x);
+  const double t = fma(x, c.k[0], c.k[1]);
+  const double nf = t - c.k[1];
+  double r = fma(nf, c.k[2], x);
+  r = fma(nf, c.k[3], r);
+  const int n = __double2loint(t);
+  const double Tj = c.T[n & 63];
+  double q = fma(c.k[4], r, c.k[5]);
+  q = fma(q, r, c.k[6]);
+  q = fma(q, r, c.k[7]);
+  const double e = fma(r * r, q, r);  // exp(r) - 1
+  const double p = fma(Tj, e, Tj);
+  const double res = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+  const bool underflow = (unsigned)(hi - 0xC0862001) <= (0xFFF00000u - 0xC0862001u);
+  double out = underflow ? 0.0 : res;
+  if (OVERFLOW) {
+    const bool overflow = (unsigned)(hi - 0x40862801) <= (0x7FF00000u - 0x40862801u);
+    out = overflow ? __hiloint2double(0x7FF00000, 0) : out;
+  }
+  return out;
+}
+
+#ifndef CHI_EXP_POLY
+typedef ExpT ExpCtx;   // hot kernels: table-driven exp
+#define CHI_LOAD_EXPCTX(tab) load_expt(tab)
+#else
+typedef ExpK ExpCtx;   // -DCHI_EXP_POLY: pure-polynomial exp (A/B builds)
+#define CHI_LOAD_EXPCTX(tab) load_expk()
+#endif
+
 // 1/x for normal x > 0 (x = d^2 + W^2/4 of the Lorentzian): MUFU.RCP64H seed + two
 // Newton steps, ~1 ulp, no slow path.
 __device__ __forceinline__ double chi_rcp(double x) {
@@ -115,6 +198,7 @@ struct ChanArgs {
   int n_chunks;     // channel chunks per draw
   int chunk_len;    // channels per chunk (multiple of 32)
   int mom_stride;   // doubles per (draw, chunk) record
+  int axis_dir;     // +1 / -1: spectral axis strictly ascending / descending, 0: neither
   double bg;
   const double* __restrict__ vax;     // [S]
   const double* __restrict__ yeff;    // [n_sl][S]   brightness - baseline offset
@@ -138,14 +222,14 @@ template <bool PV> struct AbLayout { static constexpr int NA = PV ? 6 : 3; };
 #ifndef CHI_BLOCKS_BIAS
 #define CHI_BLOCKS_BIAS 0  // build-time experiment knob: +/- resident blocks per SM
 #endif
-constexpr int clamp_blocks(int b) { return b < 1 ? 1 : (b > 4 ? 4 : b); }
+constexpr int clamp_blocks(int b) { return b < 1 ? 1 : (b > 6 ? 6 : b); }
 constexpr int em_min_blocks(int N, bool pv) {
   const int regs = 2 * ((pv ? 8 : 5) * N + (pv ? 4 : 3) * N) + 64;
-  return clamp_blocks((regs <= 128 ? 4 : (regs <= 168 ? 3 : 2)) + CHI_BLOCKS_BIAS);
+  return clamp_blocks((regs <= 128 ? 4 : (regs <= 168 ? 3 : 2)) + CHI_BLOCKS_BIAS) * 4 / CHI_WARPS_PER_BLOCK;
 }
 constexpr int ab_min_blocks(int N, bool pv) {
   const int regs = 2 * ((pv ? 6 : 3) * N + (pv ? 3 : 2) * N) + 56;
-  return clamp_blocks((regs <= 128 ? 4 : (regs <= 168 ? 3 : 2)) + CHI_BLOCKS_BIAS);
+  return clamp_blocks((regs <= 128 ? 4 : (regs <= 168 ? 3 : 2)) + CHI_BLOCKS_BIAS) * 4 / CHI_WARPS_PER_BLOCK;
 }
 
 // first two baseline terms are kept in registers (degree 0/1 is the common case);
@@ -164,6 +248,8 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][8];
   __shared__ double s_gb[CHI_MAX_BASELINE - CHI_BASE_REG][CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
+  __shared__ double s_T[64];
+  fill_exp_table(s_T);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
@@ -200,7 +286,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
   double lp = 0.0, gb0 = 0.0, gb1 = 0.0;
   const double bg = a.bg;
   const double(*sc)[8] = s_c[warp];
-  const ExpK ek = load_expk();
+  const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
   for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
@@ -312,6 +398,8 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][6];
   __shared__ double s_gb[CHI_MAX_BASELINE - CHI_BASE_REG][CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
+  __shared__ double s_T[64];
+  fill_exp_table(s_T);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
@@ -346,7 +434,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
     for (int j = 0; j < NA; ++j) acc[n][j] = 0.0;
   double lp = 0.0, gb0 = 0.0, gb1 = 0.0;
   const double(*sc)[6] = s_c[warp];
-  const ExpK ek = load_expk();
+  const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
   for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {

@@ -210,7 +210,9 @@ class Engine:
     def logp_grad(self, theta, coeff_e=None, coeff_a=None, sightline=None, want_grad=True, out=None):
         """Likelihood logp ``[B]`` and gradients for ``theta [B, NSLOT, N]``.
         Returns ``(logp, grad, gcoeff_e, gcoeff_a)`` (``None`` where not applicable).
-        ``out`` may supply preallocated (e.g. pinned) ``logp``/``grad`` arrays."""
+        ``out`` may supply preallocated ``logp``/``grad``/``gcoeff_e``/``gcoeff_a`` arrays; with
+        page-locked inputs and outputs (:class:`PinnedArray`) the library overlaps the copies of
+        consecutive sub-batches with the kernels."""
         N = self.n_clouds
         theta = _f64(theta)
         if theta.ndim != 3 or theta.shape[1:] != (layout.NSLOT, N):
@@ -233,9 +235,11 @@ class Engine:
             if grad is None:
                 grad = np.empty((B, layout.NSLOT, N), dtype=np.float64)
             if self.nb_e:
-                gce = np.empty((B, self.nb_e), dtype=np.float64)
+                gce = out.get("gcoeff_e")
+                gce = np.empty((B, self.nb_e), dtype=np.float64) if gce is None else gce
             if self.nb_a:
-                gca = np.empty((B, self.nb_a), dtype=np.float64)
+                gca = out.get("gcoeff_a")
+                gca = np.empty((B, self.nb_a), dtype=np.float64) if gca is None else gca
         self._check(
             self._lib.chi_logp_grad(
                 self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca), _lib.as_ip(sl),
