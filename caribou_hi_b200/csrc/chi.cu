@@ -58,6 +58,9 @@ struct DevDataset {
 #define CHI_LANES 3
 struct Lane {
   cudaStream_t st = nullptr;
+  // small batches run the absorption kernel on `aux`, concurrently with the emission kernel
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Buf cc, mom_e, mom_a;                                           // kernel workspace
   Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca;    // staging of the host entry points
   void release() {
@@ -209,6 +212,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   int rc = launch_cloud_map(h, L, B, theta);
   if (rc) return rc;
   CK(cudaEventRecord(evs[1], L.st));
+  CK(cudaEventRecord(L.ev_fork, L.st));  // the cloud constants are ready from here on
 
   EpiArgs ea;
   memset(&ea, 0, sizeof(ea));
@@ -236,6 +240,10 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     ea.mom_e = L.mom_e.d();
   }
   CK(cudaEventRecord(evs[2], L.st));
+  // under-filled launches (few chains): absorption runs next to emission on the aux stream
+  const bool fork = do_e && do_a && B * 8 < (int64_t)h->n_sm * 16;
+  cudaStream_t st_a = fork ? L.aux : L.st;
+  if (fork) CK(cudaStreamWaitEvent(L.aux, L.ev_fork, 0));
   if (do_a) {
     ChanArgs a;
     memset(&a, 0, sizeof(a));
@@ -246,19 +254,31 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     CK(L.mom_a.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.vax = h->a.vax.d(); a.yeff = h->a.yeff.d(); a.wgt = h->a.wgt.d(); a.basis = h->a.basis.d();
     a.coeff = ca; a.sl = sl; a.gbar = vjp ? gbar_a : nullptr; a.cc = L.cc.d(); a.mom = L.mom_a.d();
-    if (dispatch_np<LaunchAb>(N, pv, a, L.st, h->kernel_family, h->cpt)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    if (dispatch_np<LaunchAb>(N, pv, a, st_a, h->kernel_family, h->cpt)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
     ea.has_a = 1; ea.nb_a = a.n_base; ea.chunks_a = a.n_chunks; ea.stride_a = a.mom_stride;
     ea.mom_a = L.mom_a.d();
+  }
+  if (fork) {
+    CK(cudaEventRecord(L.ev_join, L.aux));
+    CK(cudaStreamWaitEvent(L.st, L.ev_join, 0));
   }
   CK(cudaEventRecord(evs[3], L.st));
   // baseline-coefficient gradients of a dataset that did not run are zero
   if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), L.st));
   if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), L.st));
 
-  unsigned grid = (unsigned)((B * N + 127) / 128);
-  MODEL_SWITCH(h->cfg.model, (k_epilogue<M><<<grid, 128, 0, L.st>>>(h->map, ea)));
+  // small batches are bound by the dependent chain of the per-cloud map: split the tangent
+  // directions over threads; large batches take the fused form (half the arithmetic)
+  const int K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
+  if (B * N * K <= (int64_t)h->n_sm * 1024) {
+    unsigned grid = (unsigned)((B * N * K + 127) / 128);
+    MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true><<<grid, 128, 0, L.st>>>(h->map, ea)));
+  } else {
+    unsigned grid = (unsigned)((B * N + 127) / 128);
+    MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false><<<grid, 128, 0, L.st>>>(h->map, ea)));
+  }
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(evs[4], L.st));
@@ -449,6 +469,10 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
   h->lanes[0].st = h->stream;
   for (int i = 1; ok && i < CHI_LANES; ++i)
     ok = cudaStreamCreateWithFlags(&h->lanes[i].st, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; ok && i < CHI_LANES; ++i)
+    ok = cudaStreamCreateWithFlags(&h->lanes[i].aux, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->lanes[i].ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->lanes[i].ev_join, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     delete h;
     return fail(nullptr, CHI_ECUDA, "chi_create: stream/event creation failed");
@@ -472,8 +496,12 @@ void chi_destroy(chi_handle* h) {
   for (auto& row : h->ring)
     for (cudaEvent_t e : row)
       if (e) cudaEventDestroy(e);
-  for (Lane& L : h->lanes)
+  for (Lane& L : h->lanes) {
+    if (L.ev_fork) cudaEventDestroy(L.ev_fork);
+    if (L.ev_join) cudaEventDestroy(L.ev_join);
+    if (L.aux) cudaStreamDestroy(L.aux);
     if (L.st) cudaStreamDestroy(L.st);
+  }
   delete h;
 }
 

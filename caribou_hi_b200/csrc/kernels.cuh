@@ -75,13 +75,21 @@ struct EpiArgs {
   double* __restrict__ gcoeff_a;
 };
 
-template <int MODEL>
+// SPLIT = false: one thread per (draw, cloud) carries all K tangent directions (least work,
+// used for large batches).  SPLIT = true: one thread per (draw, cloud, direction) carries a
+// single tangent -- ~2x the arithmetic but a ~5x shorter dependent chain, which is what a
+// small batch (a few dozen chains) is bound by.
+template <int MODEL, bool SPLIT>
 __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   constexpr int K = (MODEL == CHI_MODEL_PHYSICS) ? 7 : CHI_NSLOT;
+  constexpr int KD = SPLIT ? 1 : K;   // tangent directions per thread
+  constexpr int NJ = K / KD;          // threads per (draw, cloud)
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.B * a.N) return;
-  const int64_t b = t / a.N;
-  const int n = (int)(t - b * a.N);
+  if (t >= a.B * a.N * NJ) return;
+  const int j0 = SPLIT ? (int)(t % NJ) : 0;  // first direction of this thread
+  const int64_t bn = SPLIT ? t / NJ : t;
+  const int64_t b = bn / a.N;
+  const int n = (int)(bn - b * a.N);
   const int NE = a.pv ? 8 : 5, NA = a.pv ? 6 : 3;
 
   // --- sums over channel chunks (fixed order: deterministic) ---
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
     for (int c = 0; c < a.chunks_a; ++c, p += a.stride_a)
       for (int j = 0; j < NA; ++j) ma[j] += p[j];
   }
-  if (n == 0) {
+  if (n == 0 && j0 == 0) {
     // logp and baseline-coefficient gradients: one thread per draw
     double lp = 0.0;
     if (a.has_e) {
@@ -124,22 +132,23 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   if (!a.grad) return;
 
   // --- Jacobian of the per-cloud map by forward-mode duals ---
-  typedef Dual<K> D;
+  typedef Dual<KD> D;
   D th[CHI_NSLOT];
   const double* tp = a.theta + (b * CHI_NSLOT) * a.N + n;
 #pragma unroll
   for (int s = 0; s < CHI_NSLOT; ++s) {
-    double x = tp[(int64_t)s * a.N];
-    th[s] = (s < K) ? D::variable(x, s) : D(x);
+    th[s] = D(tp[(int64_t)s * a.N]);
+#pragma unroll
+    for (int i = 0; i < KD; ++i) th[s].d[i] = (s == j0 + i) ? 1.0 : 0.0;
   }
   CloudPhys<D> ph = cloud_phys<MODEL, D>(cfg, th);
 
-  double g[K];
+  double g[KD];
 #pragma unroll
-  for (int i = 0; i < K; ++i) g[i] = 0.0;
+  for (int i = 0; i < KD; ++i) g[i] = 0.0;
   auto addc = [&](double bar, const D& x) {
 #pragma unroll
-    for (int i = 0; i < K; ++i) g[i] = fma(bar, x.d[i], g[i]);
+    for (int i = 0; i < KD; ++i) g[i] = fma(bar, x.d[i], g[i]);
   };
 
   double cbar = 0.0;
@@ -171,7 +180,9 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
 
   double* go = a.grad + (b * CHI_NSLOT) * a.N + n;
 #pragma unroll
-  for (int s = 0; s < CHI_NSLOT; ++s) go[(int64_t)s * a.N] = (s < K) ? g[s < K ? s : 0] : 0.0;
+  for (int i = 0; i < KD; ++i) go[(int64_t)(j0 + i) * a.N] = g[i];
+  if (j0 == 0)
+    for (int s = K; s < CHI_NSLOT; ++s) go[(int64_t)s * a.N] = 0.0;  // slots the model kind does not use
 }
 
 // ---------------------------------------------------------------------------
