@@ -27,5 +27,5 @@ for blk in blocks[1:]:
     for op, n in hist.most_common(22):
         print(f"  {op:10s} {n:12d} {100.0 * n / tot:5.1f}%")
     print("  -- top stall lines")
-    for s, src in sorted(stall, reverse=True)[:14]:
+    for s, src in sorted(stall, reverse=True)[:14]:  # noqa
         print(f"  {s:6d}  {src[:90]}")
