@@ -66,6 +66,16 @@ class ChiDataset(C.Structure):
     ]
 
 
+class ChiPriors(C.Structure):
+    _fields_ = [
+        ("beta", C.c_double * 2),
+        ("nth_fwhm_1pc", C.c_double * 2),
+        ("sigma_log10_NHI", C.c_double),
+        ("baseline_sigma_e", C.c_double * 8),
+        ("baseline_sigma_a", C.c_double * 8),
+    ]
+
+
 class ChiError(RuntimeError):
     def __init__(self, code, text):
         self.code = code
@@ -99,6 +109,10 @@ SYMBOLS = {
     "chi_spectra_vjp": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "chi_spectra_vjp_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 8),
     "chi_deterministics": (C.c_int, [_H, C.c_int64, _dp, _dp]),
+    "chi_set_priors": (C.c_int, [_H, C.POINTER(ChiPriors)]),
+    "chi_model_logp_grad": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp]),
+    "chi_model_logp_grad_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 8),
+    "chi_transform": (C.c_int, [_H, C.c_int64, C.c_int, _dp, _dp]),
     "chi_last_kernel_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "chi_stage_ms": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float)]),
     "chi_launch_count": (C.c_int64, [_H]),

@@ -62,9 +62,10 @@ struct Lane {
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Buf cc, mom_e, mom_a;                                           // kernel workspace
+  Buf xcon, prior;                                                // constrained values, per-cloud priors
   Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca;    // staging of the host entry points
   void release() {
-    Buf* bufs[] = {&cc, &mom_e, &mom_a, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
+    Buf* bufs[] = {&cc, &mom_e, &mom_a, &xcon, &prior, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
     for (Buf* b : bufs) b->release();
   }
 };
@@ -90,6 +91,8 @@ struct chi_handle {
   Lane lanes[CHI_LANES];
   // further staging of the host entry points (single-lane paths)
   Buf w_gbe, w_gba, w_mue, w_mua, w_misc[8];
+  bool priors_set = false;
+  double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];
   int64_t call_first_stage = 0;  // stage_calls at the start of the current model-level call
   int64_t launches = 0;
   int kernel_family = 1;  // 1: moments.cuh (default), 2: moments_win.cuh (env CHI_KERNEL=2)
@@ -191,26 +194,34 @@ struct LaunchAb {
     case CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL: { constexpr int M = CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL; STMT; } break; \
   }
 
-int launch_cloud_map(chi_handle* h, Lane& L, int64_t B, const double* theta) {
+int launch_cloud_map(chi_handle* h, Lane& L, int64_t B, const double* theta, double* constrained = nullptr) {
   const int N = h->cfg.n_clouds;
   CK(L.cc.ensure((size_t)B * N * CHI_CC_STRIDE * sizeof(double)));
   unsigned grid = (unsigned)((B * N + 127) / 128);
-  MODEL_SWITCH(h->cfg.model, (k_cloud_map<M><<<grid, 128, 0, L.st>>>(h->map, B, N, theta, L.cc.d())));
+  MODEL_SWITCH(h->cfg.model, (k_cloud_map<M><<<grid, 128, 0, L.st>>>(h->map, B, N, theta, L.cc.d(), constrained)));
   h->launches++;
   CK(cudaGetLastError());
   return CHI_OK;
 }
 
 // moments (+ optional logp) + epilogue; gbar_* != null selects the VJP mode
+// `model` = true: theta holds unconstrained values; priors and Jacobians are added (chi_model_logp_grad)
 int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const double* ce, const double* ca,
                  const int32_t* sl, const double* gbar_e, const double* gbar_a, bool vjp, double* logp,
-                 double* grad, double* gce, double* gca) {
+                 double* grad, double* gce, double* gca, bool model = false) {
   const int N = h->cfg.n_clouds;
   const bool pv = h->cfg.lorentzian != 0;
   cudaEvent_t* evs = h->ring[h->stage_calls % CHI_STAGE_RING];
   CK(cudaEventRecord(evs[0], L.st));
-  int rc = launch_cloud_map(h, L, B, theta);
+  const double* u = nullptr;
+  if (model) {
+    CK(L.xcon.ensure((size_t)B * CHI_NSLOT * N * sizeof(double)));
+    CK(L.prior.ensure((size_t)B * N * sizeof(double)));
+    u = theta;
+  }
+  int rc = launch_cloud_map(h, L, B, theta, model ? L.xcon.d() : nullptr);
   if (rc) return rc;
+  if (model) theta = L.xcon.d();  // everything downstream works on the constrained values
   CK(cudaEventRecord(evs[1], L.st));
   CK(cudaEventRecord(L.ev_fork, L.st));  // the cloud constants are ready from here on
 
@@ -219,6 +230,11 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   ea.B = B; ea.N = N; ea.pv = pv;
   ea.theta = theta; ea.sl = sl; ea.logp = logp; ea.grad = grad; ea.gcoeff_e = gce; ea.gcoeff_a = gca;
   ea.lconst = vjp ? nullptr : h->lconst.d();
+  if (model) {
+    ea.u = u; ea.prior_part = L.prior.d(); ea.coeff_e = ce; ea.coeff_a = ca;
+    memcpy(ea.bsig_e, h->bsig_e, sizeof(ea.bsig_e));
+    memcpy(ea.bsig_a, h->bsig_a, sizeof(ea.bsig_a));
+  }
 
   // in VJP mode a dataset without cotangent contributes nothing
   const bool do_e = h->has_e && (!vjp || gbar_e);
@@ -279,6 +295,10 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     unsigned grid = (unsigned)((B * N + 127) / 128);
     MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false><<<grid, 128, 0, L.st>>>(h->map, ea)));
   }
+  if (model) {
+    k_add_prior<<<(unsigned)((B + 127) / 128), 128, 0, L.st>>>(B, N, L.prior.d(), logp);
+    h->launches++;
+  }
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(evs[4], L.st));
@@ -321,6 +341,13 @@ int check_model_call(chi_handle* h, int64_t B, const double* theta) {
   if (!h) return CHI_EINVAL;
   if (B < 0 || (B > 0 && !theta)) return fail(h, CHI_EINVAL, "theta is NULL or B < 0");
   if (!h->spectra_set) return fail(h, CHI_ESTATE, "chi_set_spectra has not been called");
+  return CHI_OK;
+}
+
+int check_prior_call(chi_handle* h) {
+  if (h->cfg.model == CHI_MODEL_PHYSICS)
+    return fail(h, CHI_EINVAL, "chi_model_logp_grad: not available for CHI_MODEL_PHYSICS");
+  if (!h->priors_set) return fail(h, CHI_ESTATE, "chi_set_priors has not been called");
   return CHI_OK;
 }
 
@@ -771,10 +798,14 @@ int chi_spectra_vjp_dev(chi_handle* h, int64_t B, const double* theta, const dou
 }
 
 // ---- model-level, host pointers ---------------------------------------------------
-int chi_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
-                  const int32_t* sl, double* logp, double* grad, double* gce, double* gca) {
+static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                          const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model) {
   int rc = check_model_call(h, B, theta);
   if (rc) return rc;
+  if (model) {
+    rc = check_prior_call(h);
+    if (rc) return rc;
+  }
   if (!logp) return fail(h, CHI_EINVAL, "chi_logp_grad: logp_out is NULL");
   CK(cudaSetDevice(h->device));
   if (sl)
@@ -820,7 +851,7 @@ int chi_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* c
     if (gce && nbe) { CK(L.w_gce.ensure(nb * nbe * sizeof(double))); d_gce = L.w_gce.d(); }
     if (gca && nba) { CK(L.w_gca.ensure(nb * nba * sizeof(double))); d_gca = L.w_gca.d(); }
     rc = run_backward(h, L, nb, L.w_theta.d(), d_ce, d_ca, d_sl, nullptr, nullptr, false, L.w_logp.d(), d_grad,
-                      d_gce, d_gca);
+                      d_gce, d_gca, model);
     if (rc) return rc;
     CK(cudaMemcpyAsync(logp + b0, L.w_logp.p, nb * sizeof(double), cudaMemcpyDeviceToHost, L.st));
     if (d_grad) CK(cudaMemcpyAsync(grad + b0 * CHI_NSLOT * N, d_grad, nb * th_b, cudaMemcpyDeviceToHost, L.st));
@@ -828,6 +859,82 @@ int chi_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* c
     if (d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, L.st));
   }
   for (Lane& L : h->lanes) CK(cudaStreamSynchronize(L.st));
+  return CHI_OK;
+}
+
+int chi_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                  const int32_t* sl, double* logp, double* grad, double* gce, double* gca) {
+  return host_logp_grad(h, B, theta, ce, ca, sl, logp, grad, gce, gca, false);
+}
+
+int chi_model_logp_grad(chi_handle* h, int64_t B, const double* u, const double* ce, const double* ca,
+                        const int32_t* sl, double* logp, double* grad, double* gce, double* gca) {
+  return host_logp_grad(h, B, u, ce, ca, sl, logp, grad, gce, gca, true);
+}
+
+int chi_model_logp_grad_dev(chi_handle* h, int64_t B, const double* u, const double* ce, const double* ca,
+                            const int32_t* sl, double* logp, double* grad, double* gce, double* gca) {
+  int rc = check_model_call(h, B, u);
+  if (rc) return rc;
+  rc = check_prior_call(h);
+  if (rc) return rc;
+  if (!logp) return fail(h, CHI_EINVAL, "chi_model_logp_grad: logp_out is NULL");
+  if (B == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  h->call_first_stage = h->stage_calls;
+  h->kernel_ms = 0.f;
+  return run_backward(h, h->lanes[0], B, u, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca, true);
+}
+
+int chi_set_priors(chi_handle* h, const chi_priors* p) {
+  if (!h || !p) return CHI_EINVAL;
+  if (h->cfg.model == CHI_MODEL_PHYSICS)
+    return fail(h, CHI_EINVAL, "chi_set_priors: CHI_MODEL_PHYSICS has no free RVs with priors");
+  if (!(p->beta[0] > 0.0 && p->beta[1] > 0.0)) return fail(h, CHI_EINVAL, "chi_set_priors: Beta parameters must be > 0");
+  if (!(p->nth_fwhm_1pc[1] > 0.0)) return fail(h, CHI_EINVAL, "chi_set_priors: nth_fwhm_1pc sigma must be > 0");
+  const bool coupled = h->cfg.model == CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL ||
+                       (h->cfg.model == CHI_MODEL_EMISSION_ABSORPTION && h->cfg.free_weight);
+  if (coupled && !(p->sigma_log10_NHI > 0.0))
+    return fail(h, CHI_EINVAL, "chi_set_priors: sigma_log10_NHI must be > 0 for a free absorption weight");
+  for (int i = 0; i < CHI_MAX_BASELINE; ++i) {
+    h->bsig_e[i] = p->baseline_sigma_e[i] > 0.0 ? p->baseline_sigma_e[i] : 1.0;
+    h->bsig_a[i] = p->baseline_sigma_a[i] > 0.0 ? p->baseline_sigma_a[i] : 1.0;
+  }
+  MapCfg& mc = h->map;
+  const double half_log_2pi = 0.5 * log(2.0 * M_PI);
+  mc.beta_a = p->beta[0];
+  mc.beta_b = p->beta[1];
+  mc.beta_lnB = lgamma(mc.beta_a) + lgamma(mc.beta_b) - lgamma(mc.beta_a + mc.beta_b);
+  mc.nth_mu = p->nth_fwhm_1pc[0];
+  mc.nth_sigma = p->nth_fwhm_1pc[1];
+  const double alpha = (0.0 - mc.nth_mu) / mc.nth_sigma;  // lower bound 0, hi_physical_model.py:142
+  mc.nth_const = -log(mc.nth_sigma) - half_log_2pi - log(0.5 * erfc(alpha / sqrt(2.0)));
+  mc.wt_sigma = coupled ? p->sigma_log10_NHI : 1.0;
+  mc.wt_mu0 = -log(10.0) * mc.wt_sigma * mc.wt_sigma / 2.0;  // emission_absorption_model.py:50
+  mc.wt_const = -log(mc.wt_sigma) - half_log_2pi;
+  mc.fwhm_L_weight = h->cfg.model >= CHI_MODEL_ABSORPTION_PHYSICAL ? 1.0 / h->cfg.n_clouds : 1.0;
+  h->priors_set = true;
+  return CHI_OK;
+}
+
+int chi_transform(chi_handle* h, int64_t B, int direction, const double* in, double* out) {
+  if (!h) return CHI_EINVAL;
+  if (B < 0 || (B > 0 && (!in || !out)) || (direction != 1 && direction != -1))
+    return fail(h, CHI_EINVAL, "chi_transform: bad argument");
+  if (B == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.n_clouds;
+  const int64_t total = B * CHI_NSLOT * N;
+  CK(h->w_misc[0].ensure(total * sizeof(double)));
+  CK(h->w_misc[1].ensure(total * sizeof(double)));
+  CK(cudaMemcpyAsync(h->w_misc[0].p, in, total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  unsigned grid = (unsigned)((total + 255) / 256);
+  MODEL_SWITCH(h->cfg.model, (k_transform<M><<<grid, 256, 0, h->stream>>>(h->map, total, N, direction,
+                                                                        h->w_misc[0].d(), h->w_misc[1].d())));
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->w_misc[1].p, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return CHI_OK;
 }
 

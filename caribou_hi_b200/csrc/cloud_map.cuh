@@ -28,7 +28,87 @@ struct MapCfg {
   double prior_fwhm2, pv0, pv1, pn0, pn1, pa0, pa1, prior_fwhm_L, prior_amp;
   double wch2_e, wch2_a;  // (4 ln2 |v1-v0| / pi)^2 per dataset, physics.py:294-295
   double const_G;         // sqrt(2 pi)/(2 sqrt(2 ln 2)), emission_model.py:127 (host-computed)
+  // prior terms of the unconstrained-space model logp (chi_set_priors; host-computed constants)
+  double beta_a, beta_b, beta_lnB;      // Beta(a, b) of the thermal fraction / tkin factor
+  double nth_mu, nth_sigma, nth_const;  // TruncatedNormal(mu, sigma, lower=0): -ln sigma - .5 ln 2pi - ln(1-Phi)
+  double wt_sigma, wt_const, wt_mu0;    // coupled Normal: mu = wt_mu0 - log10(T), const = -ln sigma - .5 ln 2pi
+  double fwhm_L_weight;                 // 1/N when fwhm_L_norm is one RV per draw (physical models), else 1
 };
+
+// ---- priors and default transforms of PyMC's unconstrained space ------
+// Distribution of the free RV in each theta slot; the transform follows from it:
+//   CHI2 / HALFNORMAL / TRUNCNORMAL(lower=0): x = exp(u), log|J| = u
+//   BETA / UNIFORM(0,1):                      x = sigmoid(u), log|J| = log x + log(1-x)
+enum { PD_NONE = 0, PD_NORMAL01, PD_CHI2, PD_HALFNORMAL, PD_BETA, PD_UNIFORM, PD_TRUNCNORMAL, PD_COUPLED };
+
+template <int MODEL>
+CHI_HD int slot_dist(const MapCfg& c, int s) {
+  if (MODEL == CHI_MODEL_PHYSICS) return PD_NONE;
+  constexpr bool physical = (MODEL >= CHI_MODEL_ABSORPTION_PHYSICAL);
+  constexpr bool emission = (MODEL == CHI_MODEL_EMISSION || MODEL == CHI_MODEL_EMISSION_ABSORPTION ||
+                             MODEL == CHI_MODEL_EMISSION_PHYSICAL || MODEL == CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL);
+  switch (s) {
+    case CHI_FR_FWHM2_NORM: return PD_CHI2;                                   // hi_model.py:95
+    case CHI_FR_VELOCITY_NORM: return PD_NORMAL01;                            // hi_model.py:109
+    case CHI_FR_LOG10_NHI_NORM: return physical ? PD_NONE : PD_NORMAL01;      // hi_model.py:99
+    case CHI_FR_LOG10_N_ALPHA_NORM: return PD_NORMAL01;                       // hi_model.py:122
+    case CHI_FR_NTH_FWHM_1PC: return physical ? PD_TRUNCNORMAL : PD_NONE;     // hi_physical_model.py:138
+    case CHI_FR_FWHM_L_NORM: return c.lorentzian ? PD_HALFNORMAL : PD_NONE;   // hi_model.py:133
+    case CHI_FR_AMPLITUDE_NORM: return PD_HALFNORMAL;                         // e.g. emission_model.py:62
+    case CHI_FR_THERMAL: return PD_BETA;                                      // e.g. emission_model.py:76
+    case CHI_FR_FILLING_FACTOR_NORM: return emission ? PD_UNIFORM : PD_NONE;  // emission_model.py:107
+    case CHI_FR_LOG10_WT:
+      if (MODEL == CHI_MODEL_EMISSION_ABSORPTION) return c.free_weight ? PD_COUPLED : PD_NONE;
+      return MODEL == CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL ? PD_COUPLED : PD_NONE;
+  }
+  return PD_NONE;
+}
+
+// unconstrained u -> constrained x, with dx/du and the Jacobian term and its derivative
+struct Transformed {
+  double x, dxdu, logj, dlogj;
+};
+CHI_HD Transformed slot_backward(int dist, double u) {
+  Transformed t;
+  if (dist == PD_CHI2 || dist == PD_HALFNORMAL || dist == PD_TRUNCNORMAL) {
+    t.x = exp(u); t.dxdu = t.x; t.logj = u; t.dlogj = 1.0;
+  } else if (dist == PD_BETA || dist == PD_UNIFORM) {
+    const double e = exp(-fabs(u));                 // stable sigmoid and log-sigmoids
+    const double s_pos = 1.0 / (1.0 + e);           // sigmoid(|u|)
+    t.x = u >= 0.0 ? s_pos : e * s_pos;
+    const double l1pe = log1p(e);
+    t.logj = -fabs(u) - 2.0 * l1pe;                 // log x + log(1-x)
+    t.dxdu = e * s_pos * s_pos;                     // x (1 - x)
+    t.dlogj = 1.0 - 2.0 * t.x;
+  } else {
+    t.x = u; t.dxdu = 1.0; t.logj = 0.0; t.dlogj = 0.0;
+  }
+  return t;
+}
+
+#define CHI_HALF_LOG_2PI 0.918938533204672741780
+// log density of the free RV in slot `dist` at its constrained value x (PyMC definitions,
+// third-party: restated in oracle/priors_ref.py); T is the thermal quantity the coupled
+// Normal's mean depends on (tkin or fwhm2_thermal).
+template <class T>
+CHI_HD T slot_density(const MapCfg& c, int dist, const T& x, const T& thermal) {
+  switch (dist) {
+    case PD_NORMAL01: return -0.5 * (x * x) - CHI_HALF_LOG_2PI;
+    case PD_CHI2: return -0.5 * m_log(x) - 0.5 * x - (0.5 * CHI_LN2 + 0.5 * 1.1447298858494001741);  // ln Gamma(1/2) = .5 ln pi
+    case PD_HALFNORMAL: return -0.5 * (x * x) + 0.5 * (CHI_LN2 - 1.1447298858494001741);            // .5 ln(2/pi)
+    case PD_BETA: return (c.beta_a - 1.0) * m_log(x) + (c.beta_b - 1.0) * m_log(T(1.0 - x)) - c.beta_lnB;
+    case PD_UNIFORM: return 0.0 * x;
+    case PD_TRUNCNORMAL: {
+      T z = (x - c.nth_mu) / c.nth_sigma;
+      return -0.5 * (z * z) + c.nth_const;
+    }
+    case PD_COUPLED: {
+      T z = (x - (c.wt_mu0 - m_log10(thermal))) / c.wt_sigma;
+      return -0.5 * (z * z) + c.wt_const;
+    }
+  }
+  return 0.0 * x;
+}
 
 // physics.py:58-106 (Kim+14 eq. 4, Draine 2011 rate coefficient). The reference
 // evaluates both switch branches and selects; selecting first gives the same value

@@ -25,10 +25,14 @@ namespace chi {
 // ---------------------------------------------------------------------------
 // k_cloud_map
 // ---------------------------------------------------------------------------
+// `constrained` != null: theta holds UNCONSTRAINED values (PyMC's value variables); they are
+// mapped back through the default transforms first and the constrained values are kept for
+// the epilogue.
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, int64_t B, int N,
                                                    const double* __restrict__ theta,
-                                                   double* __restrict__ cc) {
+                                                   double* __restrict__ cc,
+                                                   double* __restrict__ constrained) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * N) return;
   int64_t b = t / N;
@@ -37,6 +41,14 @@ __global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, int64_t B, int N,
   const double* tp = theta + (b * CHI_NSLOT) * N + n;
 #pragma unroll
   for (int s = 0; s < CHI_NSLOT; ++s) th[s] = tp[(int64_t)s * N];
+  if (constrained) {
+    double* xp = constrained + (b * CHI_NSLOT) * N + n;
+#pragma unroll
+    for (int s = 0; s < CHI_NSLOT; ++s) {
+      th[s] = slot_backward(slot_dist<MODEL>(cfg, s), th[s]).x;
+      xp[(int64_t)s * N] = th[s];
+    }
+  }
   CloudPhys<double> ph = cloud_phys<MODEL, double>(cfg, th);
   double* o = cc + t * CHI_CC_STRIDE;
   o[CC_C] = ph.velocity;
@@ -73,6 +85,12 @@ struct EpiArgs {
   double* __restrict__ grad;          // [B][NSLOT][N] or null
   double* __restrict__ gcoeff_e;      // [B][nb_e] or null
   double* __restrict__ gcoeff_a;
+  // unconstrained-space model logp (priors + Jacobians), null/0 otherwise
+  const double* __restrict__ u;        // [B][NSLOT][N] unconstrained values (theta = constrained)
+  double* __restrict__ prior_part;     // [B][N] per-cloud prior + Jacobian, summed by k_add_prior
+  const double* __restrict__ coeff_e;  // [B][nb_e] baseline coefficients (their Normal priors)
+  const double* __restrict__ coeff_a;
+  double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];  // prior widths of the coefficients
 };
 
 // SPLIT = false: one thread per (draw, cloud) carries all K tangent directions (least work,
@@ -127,9 +145,22 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
           a.gcoeff_a[b * a.nb_a + i] = g;
         }
     }
+    if (a.u) {
+      // Normal(0, sigma_i) priors of the baseline coefficients (bayes_spec add_baseline_priors)
+      for (int i = 0; i < a.nb_e; ++i) {
+        const double c = a.coeff_e ? a.coeff_e[b * a.nb_e + i] : 0.0, s = a.bsig_e[i];
+        lp += -0.5 * (c / s) * (c / s) - log(s) - CHI_HALF_LOG_2PI;
+        if (a.gcoeff_e) a.gcoeff_e[b * a.nb_e + i] -= c / (s * s);
+      }
+      for (int i = 0; i < a.nb_a; ++i) {
+        const double c = a.coeff_a ? a.coeff_a[b * a.nb_a + i] : 0.0, s = a.bsig_a[i];
+        lp += -0.5 * (c / s) * (c / s) - log(s) - CHI_HALF_LOG_2PI;
+        if (a.gcoeff_a) a.gcoeff_a[b * a.nb_a + i] -= c / (s * s);
+      }
+    }
     if (a.logp) a.logp[b] = lp + (a.lconst ? a.lconst[a.sl ? a.sl[b] : 0] : 0.0);
   }
-  if (!a.grad) return;
+  if (!a.grad && !a.u) return;
 
   // --- Jacobian of the per-cloud map by forward-mode duals ---
   typedef Dual<KD> D;
@@ -178,11 +209,67 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   }
   addc(cbar, ph.velocity);
 
+  if (a.u) {
+    // priors of this cloud's free RVs at their constrained values (Dual: the coupled Normal's
+    // mean depends on tkin / fwhm2_thermal), then the chain rule through the transforms
+    const double* up = a.u + (b * CHI_NSLOT) * a.N + n;
+    const D thermal = (MODEL == CHI_MODEL_EMISSION_ABSORPTION) ? ph.tkin : ph.fwhm2_thermal;
+    D lp(0.0);
+    double logj = 0.0;
+#pragma unroll
+    for (int s = 0; s < CHI_NSLOT; ++s) {
+      const int dist = slot_dist<MODEL>(cfg, s);
+      if (dist == PD_NONE) continue;
+      const double w = (s == CHI_FR_FWHM_L_NORM) ? cfg.fwhm_L_weight : 1.0;
+      lp = lp + w * slot_density<D>(cfg, dist, th[s], thermal);
+      logj += w * slot_backward(dist, up[(int64_t)s * a.N]).logj;
+    }
+    if (j0 == 0) a.prior_part[b * a.N + n] = lp.v + logj;
+#pragma unroll
+    for (int i = 0; i < KD; ++i) {
+      const int s = j0 + i;
+      const int dist = slot_dist<MODEL>(cfg, s);
+      const double w = (s == CHI_FR_FWHM_L_NORM) ? cfg.fwhm_L_weight : 1.0;
+      const Transformed tr = slot_backward(dist, up[(int64_t)s * a.N]);
+      g[i] = (g[i] + lp.d[i]) * tr.dxdu + w * tr.dlogj;
+    }
+  }
+  if (!a.grad) return;
+
   double* go = a.grad + (b * CHI_NSLOT) * a.N + n;
 #pragma unroll
   for (int i = 0; i < KD; ++i) go[(int64_t)(j0 + i) * a.N] = g[i];
   if (j0 == 0)
     for (int s = K; s < CHI_NSLOT; ++s) go[(int64_t)s * a.N] = 0.0;  // slots the model kind does not use
+}
+
+// adds the per-cloud prior + Jacobian terms to logp in cloud order (deterministic)
+__global__ void k_add_prior(int64_t B, int N, const double* __restrict__ prior_part, double* __restrict__ logp) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double s = 0.0;
+  for (int n = 0; n < N; ++n) s += prior_part[b * N + n];
+  logp[b] += s;
+}
+
+// unconstrained <-> constrained values of the free RVs (direction = +1: u -> x, -1: x -> u)
+template <int MODEL>
+__global__ void k_transform(MapCfg cfg, int64_t total, int N, int direction, const double* __restrict__ in,
+                            double* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int s = (int)((t / N) % CHI_NSLOT);
+  const int dist = slot_dist<MODEL>(cfg, s);
+  const double v = in[t];
+  double r = v;
+  if (direction > 0) {
+    r = slot_backward(dist, v).x;
+  } else if (dist == PD_CHI2 || dist == PD_HALFNORMAL || dist == PD_TRUNCNORMAL) {
+    r = log(v);
+  } else if (dist == PD_BETA || dist == PD_UNIFORM) {
+    r = log(v) - log1p(-v);
+  }
+  out[t] = r;
 }
 
 // ---------------------------------------------------------------------------

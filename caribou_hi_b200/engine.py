@@ -284,6 +284,63 @@ class Engine:
         )
         return grad, gce, gca
 
+    # ---- total model logp in PyMC's unconstrained space ------------------------------
+    def set_priors(self, beta=(2.0, 2.0), nth_fwhm_1pc=(1.75, 0.25), sigma_log10_NHI=0.5,
+                   baseline_sigma_e=None, baseline_sigma_a=None):
+        """Hyper-parameters of the prior densities that are not already part of the parameter
+        maps: Beta(alpha, beta) of the thermal factor, TruncatedNormal(mu, sigma, lower=0) of
+        ``nth_fwhm_1pc``, the width of the coupled Normal of ``log10_wt_ff_*`` and the Normal
+        widths of the baseline coefficients (default 1)."""
+        p = _lib.ChiPriors()
+        p.beta = (C.c_double * 2)(*map(float, beta))
+        p.nth_fwhm_1pc = (C.c_double * 2)(*map(float, nth_fwhm_1pc))
+        p.sigma_log10_NHI = float(sigma_log10_NHI or 0.0)
+        for dst, src in ((p.baseline_sigma_e, baseline_sigma_e), (p.baseline_sigma_a, baseline_sigma_a)):
+            vals = [1.0] * _lib.CHI_MAX_BASELINE
+            if src is not None:
+                vals[: len(src)] = [float(v) for v in src]
+            for i, v in enumerate(vals):
+                dst[i] = v
+        self._check(self._lib.chi_set_priors(self._h, C.byref(p)))
+
+    def model_logp_grad(self, u, coeff_e=None, coeff_a=None, sightline=None, want_grad=True):
+        """Total model logp (likelihood + priors + transform Jacobians) and its gradient with
+        respect to the UNCONSTRAINED block ``u [B, NSLOT, N]`` -- what PyMC's
+        ``logp_dlogp_function`` evaluates inside NUTS.  Returns ``(logp, grad, gcoeff_e, gcoeff_a)``."""
+        N = self.n_clouds
+        u = _f64(u)
+        if u.ndim != 3 or u.shape[1:] != (layout.NSLOT, N):
+            raise ValueError(f"u: expected [B, {layout.NSLOT}, {N}], got {u.shape}")
+        B = u.shape[0]
+        ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
+        ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
+        sl = None if sightline is None else np.ascontiguousarray(sightline, dtype=np.int32)
+        logp = np.empty(B, dtype=np.float64)
+        grad = np.empty((B, layout.NSLOT, N), dtype=np.float64) if want_grad else None
+        gce = np.empty((B, self.nb_e), dtype=np.float64) if (want_grad and self.nb_e) else None
+        gca = np.empty((B, self.nb_a), dtype=np.float64) if (want_grad and self.nb_a) else None
+        self._check(
+            self._lib.chi_model_logp_grad(self._h, B, _lib.as_dp(u), _lib.as_dp(ce), _lib.as_dp(ca), _lib.as_ip(sl),
+                                          _lib.as_dp(logp), _lib.as_dp(grad), _lib.as_dp(gce), _lib.as_dp(gca))
+        )
+        return logp, grad, gce, gca
+
+    def model_logp_grad_dev(self, B, u, logp, grad=None, coeff_e=None, coeff_a=None, sightline=None,
+                            gcoeff_e=None, gcoeff_a=None):
+        p = self._ptr
+        self._check(
+            self._lib.chi_model_logp_grad_dev(self._h, int(B), p(u), p(coeff_e), p(coeff_a), p(sightline),
+                                              p(logp), p(grad), p(gcoeff_e), p(gcoeff_a))
+        )
+
+    def transform(self, block, direction=1):
+        """PyMC's default transforms on ``[B, NSLOT, N]``: ``direction=+1`` unconstrained ->
+        constrained, ``-1`` the inverse."""
+        block = _f64(block)
+        out = np.empty_like(block)
+        self._check(self._lib.chi_transform(self._h, block.shape[0], int(direction), _lib.as_dp(block), _lib.as_dp(out)))
+        return out
+
     def deterministics(self, theta):
         """dict of the reference's per-cloud Deterministics, each ``[B, N]``."""
         theta = _f64(theta)

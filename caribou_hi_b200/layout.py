@@ -103,6 +103,23 @@ def slot_names(kind, lorentzian, free_weight=True):
     return s
 
 
+_LOG = {"fwhm2_norm", "fwhm_L_norm", "tau_total_norm", "TB_fwhm_norm", "NHI_fwhm2_thermal_norm", "ff_NHI_norm"}
+_LOGODDS = {"tkin_factor", "tkin_factor_norm", "fwhm2_thermal_fraction", "fwhm2_thermal_fraction_norm"}
+_INTERVAL = {"nth_fwhm_1pc", "filling_factor_norm"}
+
+
+def value_name(rv):
+    """PyMC's name for the unconstrained value variable of free RV ``rv`` (its default
+    transform: log for positive, logodds for Beta, interval for bounded RVs)."""
+    if rv in _LOG:
+        return rv + "_log__"
+    if rv in _LOGODDS:
+        return rv + "_logodds__"
+    if rv in _INTERVAL:
+        return rv + "_interval__"
+    return rv
+
+
 def scalar_rvs(kind):
     """RVs that are one value per draw (shared by all clouds) in the reference:
     ``fwhm_L_norm`` of the physical models (hi_physical_model.py:148-149)."""

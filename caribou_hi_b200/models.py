@@ -85,6 +85,57 @@ class _HIBase(ABC):
             if key in self._required_keys:
                 sets[key] = self.data[key].as_dataset(self.baseline_degree)
         self.engine.set_spectra(emission=sets.get("emission"), absorption=sets.get("absorption"))
+        # prior densities + default transforms for the unconstrained-space model logp
+        bc = p.get("prior_baseline_coeffs") or {}
+        self.engine.set_priors(
+            beta=p.get("prior_fwhm2_thermal_fraction" if self._physical else "prior_tkin_factor", (2.0, 2.0)),
+            nth_fwhm_1pc=p.get("prior_nth_fwhm_1pc", (1.75, 0.25)),
+            sigma_log10_NHI=p.get("prior_sigma_log10_NHI") or 0.5,
+            baseline_sigma_e=bc.get("emission"),
+            baseline_sigma_a=bc.get("absorption"),
+        )
+
+    # -- unconstrained space (what PyMC's NUTS works in) -------------------------------
+    @property
+    def value_vars(self):
+        """PyMC's names of the unconstrained value variables, in ``free_RVs`` order."""
+        return [layout.value_name(k) for k in self.free_RVs]
+
+    def _strip(self, point):
+        """Accept either RV names or PyMC value-variable names as keys."""
+        back = {layout.value_name(k): k for k in self.engine.slots}
+        return {back.get(k, k): v for k, v in point.items()}
+
+    def to_unconstrained(self, point):
+        """Free-RV values -> unconstrained values (keys: PyMC value-variable names)."""
+        theta, ce, ca, _ = self._split(point)
+        u = self.engine.transform(theta, -1)
+        out = {layout.value_name(k): (u[:, s, :1] if k in layout.scalar_rvs(self.kind) else u[:, s, :])
+               for k, s in self.engine.slots.items()}
+        out.update({k: v for k, v in point.items() if k.startswith("baseline_")})
+        return out
+
+    def to_constrained(self, point):
+        point = self._strip(point)
+        theta, ce, ca, _ = self._split(point)
+        x = self.engine.transform(theta, +1)
+        out = {k: (x[:, s, :1] if k in layout.scalar_rvs(self.kind) else x[:, s, :])
+               for k, s in self.engine.slots.items()}
+        out.update({k: v for k, v in point.items() if k.startswith("baseline_")})
+        return out
+
+    def model_logp_dlogp(self, point):
+        """Total model logp (likelihood + priors + Jacobians) ``[B]`` and its gradient for a
+        dict of UNCONSTRAINED values -- PyMC's ``model.logp_dlogp_function`` per draw."""
+        point = self._strip(point)
+        theta, ce, ca, _ = self._split(point)
+        logp, grad, gce, gca = self.engine.model_logp_grad(theta, ce, ca)
+        grads = {layout.value_name(k): v for k, v in self.engine.unpack_grad(grad).items()}
+        if gce is not None:
+            grads["baseline_emission_norm"] = gce
+        if gca is not None:
+            grads["baseline_absorption_norm"] = gca
+        return logp, grads
 
     # -- evaluation ---------------------------------------------------------------
     @property

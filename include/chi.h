@@ -268,6 +268,39 @@ int chi_spectra_vjp_dev(chi_handle* h, int64_t B, const double* theta, const dou
  * subclasses' add_priors). */
 int chi_deterministics(chi_handle* h, int64_t B, const double* theta, double* det_out);
 
+/* ---- total model logp in PyMC's unconstrained space ----------
+ * What PyMC's compiled logp_dlogp_function returns for the whole model: the likelihood
+ * above + the prior density of every free RV + the log-Jacobian of PyMC's default
+ * transforms, as a function of the UNCONSTRAINED value variables
+ *   fwhm2_norm_log__, *_norm_log__ (HalfNormal), nth_fwhm_1pc_interval__ : x = exp(u)
+ *   tkin_factor*_logodds__, fwhm2_thermal_fraction*_logodds__, filling_factor_norm_interval__ :
+ *                                                                          x = sigmoid(u)
+ *   Normal RVs (velocity_norm, log10_nHI_norm, log10_n_alpha_norm, log10_wt_ff_*) untransformed
+ * in the same slots as theta.  Distributions: hi_model.py:95-134, hi_physical_model.py:111-149,
+ * absorption_model.py:46-61, emission_model.py:62-110, emission_absorption_model.py:50-55,
+ * absorption_physical_model.py:45-56, emission_physical_model.py:61-112,
+ * emission_absorption_physical_model.py:43-52; densities/transforms are PyMC's (third-party). */
+typedef struct chi_priors {
+  double beta[2];               /* prior_tkin_factor | prior_fwhm2_thermal_fraction (alpha, beta) */
+  double nth_fwhm_1pc[2];       /* prior_nth_fwhm_1pc (mu, sigma), TruncatedNormal lower = 0 */
+  double sigma_log10_NHI;       /* prior_sigma_log10_NHI of the coupled Normal (log10_wt_ff_*) */
+  double baseline_sigma_e[8];   /* prior_baseline_coeffs["emission"] (CHI_MAX_BASELINE entries) */
+  double baseline_sigma_a[8];   /* prior_baseline_coeffs["absorption"] */
+} chi_priors;
+int chi_set_priors(chi_handle* h, const chi_priors* priors);
+/* u[B][CHI_NSLOT][N] unconstrained; grad_out is d logp / d u (for a per-draw scalar RV replicated
+ * over clouds -- fwhm_L of the physical models -- sum the slot over clouds).  Not available for
+ * CHI_MODEL_PHYSICS.  Needs chi_set_spectra and chi_set_priors. */
+int chi_model_logp_grad(chi_handle* h, int64_t B, const double* u, const double* coeff_e,
+                        const double* coeff_a, const int32_t* sightline, double* logp_out,
+                        double* grad_out, double* gcoeff_e, double* gcoeff_a);
+int chi_model_logp_grad_dev(chi_handle* h, int64_t B, const double* u, const double* coeff_e,
+                            const double* coeff_a, const int32_t* sightline, double* logp_out,
+                            double* grad_out, double* gcoeff_e, double* gcoeff_a);
+/* PyMC's default transforms on a parameter block: direction +1 maps unconstrained -> constrained
+ * (theta usable by chi_logp_grad / chi_spectra), -1 the inverse.  in/out: [B][CHI_NSLOT][N] host. */
+int chi_transform(chi_handle* h, int64_t B, int direction, const double* in, double* out);
+
 /* ---- measurement helpers --------------------------------------------------- */
 /* Milliseconds spent in the kernels of the last model-level call on this handle
  * (CUDA events on the handle's stream; synchronises). */

@@ -47,6 +47,8 @@ DEFAULTS = {
     "prior_TB_fwhm": 1000.0,
     "prior_ff_NHI": 1.0e21,
     "prior_NHI_fwhm2_thermal": 1.0e20,
+    "prior_tkin_factor": [2.0, 2.0],
+    "prior_fwhm2_thermal_fraction": [2.0, 2.0],
     "prior_sigma_log10_NHI": None,  # physical EA model default is 0.5 (set in make_spec)
     "bg_temp": 3.77,
     "depth_nth_fwhm_power": 1.0 / 3.0,

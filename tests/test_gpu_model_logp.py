@@ -1,0 +1,120 @@
+"""Total model logp in PyMC's unconstrained space (priors + default transforms + likelihood):
+CUDA path vs the oracle restatement (oracle/priors_ref.py + torch autograd).  PyMC itself is
+not installable here, so the prior/transform definitions are pinned only to their published
+formulas (the oracle header says so)."""
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, engine_for, make_case
+from oracle import models_ref as mr
+from oracle import priors_ref as pr
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(spec, data, u, baseline):
+    ut = {k: torch.tensor(v, requires_grad=True) for k, v in u.items()}
+    bt = {k: torch.tensor(v, requires_grad=True) for k, v in baseline.items()}
+    lp = pr.model_logp(spec, data, ut, bt)
+    torch.nan_to_num(lp, nan=0.0, posinf=0.0, neginf=0.0).sum().backward()
+    g = {k: (v.grad.numpy() if v.grad is not None else np.zeros_like(u[k])) for k, v in ut.items()}
+    g.update({k: v.grad.numpy() for k, v in bt.items()})
+    return lp.detach().numpy(), g
+
+
+@pytest.mark.parametrize("kind", list(mr.KINDS))
+@pytest.mark.parametrize("lorentzian", [False, True])
+def test_model_logp_grad(cuda_device, kind, lorentzian):
+    spec, data, free, baseline = make_case(kind, 3, 120, 80, 48, seed=77, lorentzian=lorentzian, baseline_degree=1,
+                                           prior_tkin_factor=[2.0, 3.0], prior_fwhm2_thermal_fraction=[1.5, 2.5],
+                                           prior_nth_fwhm_1pc=[1.6, 0.3],
+                                           prior_baseline_coeffs={"emission": [1.0, 0.5], "absorption": [2.0, 1.0]})
+    u = {k: pr.forward(k, v) for k, v in free.items()}
+    ref_lp, ref_g = _oracle(spec, data, u, baseline)
+
+    eng = engine_for(spec, data, baseline_degree=1)
+    beta = spec["prior_tkin_factor"] if not mr.is_physical(spec) else spec["prior_fwhm2_thermal_fraction"]
+    eng.set_priors(beta=beta, nth_fwhm_1pc=spec["prior_nth_fwhm_1pc"],
+                   sigma_log10_NHI=spec["prior_sigma_log10_NHI"] or 0.5,
+                   baseline_sigma_e=[1.0, 0.5], baseline_sigma_a=[2.0, 1.0])
+    ublock = eng.pack(u)
+    lp, grad, gce, gca = eng.model_logp_grad(ublock, baseline.get("baseline_emission_norm"),
+                                             baseline.get("baseline_absorption_norm"))
+    assert_close(lp, ref_lp, what=f"{kind} model logp", axis=None)
+    fin = np.isfinite(ref_lp)
+    assert fin.sum() >= 16
+    got = eng.unpack_grad(grad)
+    names = sorted(got)
+    x = [got[n][fin] for n in names]
+    r = [ref_g[n][fin] for n in names]
+    if gce is not None:
+        x.append(gce[fin]); r.append(ref_g["baseline_emission_norm"][fin])
+    if gca is not None:
+        x.append(gca[fin]); r.append(ref_g["baseline_absorption_norm"][fin])
+    assert_close(np.concatenate(x, axis=1), np.concatenate(r, axis=1), what=f"{kind} model grad {names}")
+
+    # transforms round-trip and agree with the constrained draws
+    theta = eng.transform(ublock, +1)
+    assert_close(theta, eng.pack(free), rtol=1e-12, what="backward transform", axis=None)
+    assert_close(eng.transform(theta, -1), ublock, rtol=1e-12, what="forward transform", axis=None)
+    eng.close()
+
+
+def test_model_logp_small_batch_and_errors(cuda_device):
+    from caribou_hi_b200 import Engine
+    from caribou_hi_b200._lib import ChiError
+
+    spec, data, free, baseline = make_case("emission_absorption_physical", 4, 300, 300, 3, seed=5, lorentzian=True)
+    u = {k: pr.forward(k, v) for k, v in free.items()}
+    ref_lp, ref_g = _oracle(spec, data, u, baseline)
+    eng = engine_for(spec, data, baseline_degree=0)
+    with pytest.raises(ChiError):  # priors not set
+        eng.model_logp_grad(eng.pack(u))
+    eng.set_priors(beta=spec["prior_fwhm2_thermal_fraction"], nth_fwhm_1pc=spec["prior_nth_fwhm_1pc"],
+                   sigma_log10_NHI=spec["prior_sigma_log10_NHI"])
+    lp, grad, gce, gca = eng.model_logp_grad(eng.pack(u), baseline["baseline_emission_norm"],
+                                             baseline["baseline_absorption_norm"])
+    assert_close(lp, ref_lp, what="small-batch model logp", axis=None)
+    eng.close()
+    phys = Engine("physics", 2)
+    with pytest.raises(ChiError):
+        phys.set_priors()
+    phys.close()
+
+
+def test_model_class_unconstrained_api(cuda_device):
+    """Class-level API with PyMC's value-variable names (fwhm2_norm_log__ ...)."""
+    from caribou_hi_b200 import EmissionAbsorptionModel, SpecData
+
+    rng = np.random.default_rng(3)
+    ve, va = np.linspace(-40, 40, 160), np.linspace(-20, 20, 90)
+    data = {"emission": SpecData(ve, rng.normal(3, 1, 160), 0.2), "absorption": SpecData(va, rng.normal(0.1, 0.05, 90), 0.02)}
+    model = EmissionAbsorptionModel(data, 2, baseline_degree=1)
+    model.add_priors(prior_sigma_log10_NHI=0.4, prior_tkin_factor=[3.0, 2.0], prior_fwhm_L=1.0,
+                     prior_baseline_coeffs={"emission": [1.0, 2.0], "absorption": [0.5, 0.5]})
+    model.add_likelihood()
+    point = model.sample_prior(20, rng)
+    upoint = model.to_unconstrained(point)
+    assert "fwhm2_norm_log__" in upoint and "tkin_factor_norm_logodds__" in upoint
+    assert "filling_factor_norm_interval__" in upoint and "velocity_norm" in upoint
+    assert set(model.value_vars) == set(upoint)
+    back = model.to_constrained(upoint)
+    for k in point:
+        assert_close(back[k], point[k], rtol=1e-12, what=f"round trip {k}", axis=None)
+    logp, grads = model.model_logp_dlogp(upoint)
+
+    spec = mr.make_spec("emission_absorption", 2, prior_sigma_log10_NHI=0.4, prior_tkin_factor=[3.0, 2.0],
+                        prior_fwhm_L=1.0, prior_baseline_coeffs={"emission": [1.0, 2.0], "absorption": [0.5, 0.5]})
+    odata = {k: mr.OracleData(d.spectral, d.brightness, d.noise) for k, d in data.items()}
+    free = {k: v for k, v in point.items() if not k.startswith("baseline_")}
+    base = {k: v for k, v in point.items() if k.startswith("baseline_")}
+    u = {k: pr.forward(k, v) for k, v in free.items()}
+    ref_lp, ref_g = _oracle(spec, odata, u, base)
+    assert_close(logp, ref_lp, what="class model logp", axis=None)
+    fin = np.isfinite(ref_lp)
+    names = sorted(free)
+    got = np.concatenate([grads[pr.value_name(n)][fin] for n in names] + [grads[k][fin] for k in sorted(base)], axis=1)
+    ref = np.concatenate([ref_g[n][fin] for n in names] + [ref_g[k][fin] for k in sorted(base)], axis=1)
+    assert_close(got, ref, what="class model grads")
