@@ -76,6 +76,19 @@ class ChiPriors(C.Structure):
     ]
 
 
+class ChiNutsConfig(C.Structure):
+    _fields_ = [
+        ("chains", C.c_int64),
+        ("n_tune", C.c_int32),
+        ("n_draws", C.c_int32),
+        ("max_treedepth", C.c_int32),
+        ("reserved", C.c_int32),
+        ("seed", C.c_uint64),
+        ("target_accept", C.c_double),
+        ("init_step", C.c_double),
+    ]
+
+
 class ChiError(RuntimeError):
     def __init__(self, code, text):
         self.code = code
@@ -113,7 +126,9 @@ SYMBOLS = {
     "chi_model_logp_grad": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp]),
     "chi_model_logp_grad_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 8),
     "chi_transform": (C.c_int, [_H, C.c_int64, C.c_int, _dp, _dp]),
-    "chi_last_kernel_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "chi_nuts_sample": (C.c_int, [_H, C.POINTER(ChiNutsConfig), _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _ip, _ip,
+                                  _dp, _dp]),
+    "chi_last_kernel_ms":(C.c_int, [_H, C.POINTER(C.c_float)]),
     "chi_stage_ms": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float)]),
     "chi_launch_count": (C.c_int64, [_H]),
     "chi_microbench_fp64": (C.c_int, [_H, C.POINTER(C.c_double)]),

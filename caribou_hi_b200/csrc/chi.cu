@@ -14,6 +14,7 @@
 #include "../../include/chi.h"
 #include "kernels.cuh"
 #include "moments_win.cuh"
+#include "nuts.cuh"
 
 #define CHI_STAGE_RING 64
 
@@ -1111,6 +1112,192 @@ int chi_microbench_fp64(chi_handle* h, double* tflops_out) {
   cudaEventDestroy(b);
   const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
   *tflops_out = flops / (best * 1e-3) / 1e12;
+  return CHI_OK;
+}
+
+// ---- chain-batched NUTS ---------------------------------------------------
+int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* init_u, const double* init_ce,
+                    const double* init_ca, const int32_t* sightline, double* draws_u, double* draws_ce,
+                    double* draws_ca, double* stat_accept, int32_t* stat_depth, int32_t* stat_diverged,
+                    double* stat_logp, double* stat_step) {
+  int rc = check_model_call(h, cfg ? cfg->chains : -1, init_u);
+  if (rc) return rc;
+  rc = check_prior_call(h);
+  if (rc) return rc;
+  if (!cfg || cfg->chains < 1 || cfg->n_tune < 0 || cfg->n_draws < 1 || !draws_u)
+    return fail(h, CHI_EINVAL, "chi_nuts_sample: bad configuration");
+  const int max_depth = cfg->max_treedepth > 0 ? std::min(cfg->max_treedepth, CHI_NUTS_MAX_DEPTH) : 10;
+  const double target = cfg->target_accept > 0.0 ? cfg->target_accept : 0.8;
+  CK(cudaSetDevice(h->device));
+  const int64_t B = cfg->chains;
+  const int N = h->cfg.n_clouds, nu = CHI_NSLOT * N;
+  const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
+  const int D = nu + nbe + nba;
+  cudaStream_t st = h->stream;
+
+  // roles of the position vector's dimensions
+  std::vector<int> role(D, 0);
+  int n_free = 0;
+  for (int s = 0; s < CHI_NSLOT; ++s) {
+    int dist = PD_NONE;
+    MODEL_SWITCH(h->cfg.model, (dist = slot_dist<M>(h->map, s)));
+    if (dist == PD_NONE) continue;
+    const bool tied = s == CHI_FR_FWHM_L_NORM && h->cfg.model >= CHI_MODEL_ABSORPTION_PHYSICAL;
+    for (int n = 0; n < N; ++n) {
+      role[s * N + n] = (tied && n > 0) ? 2 : 1;
+      n_free += role[s * N + n] == 1;
+    }
+  }
+  for (int i = 0; i < nbe + nba; ++i) { role[nu + i] = 1; ++n_free; }
+
+  // one arena for the whole sampler state
+  const size_t vecs = 22, scal_d = 11, scal_i = 8;
+  const size_t n_vec = (size_t)B * D, n_ck = (size_t)B * CHI_NUTS_MAX_DEPTH * D;
+  const size_t bytes_d = (vecs * n_vec + 2 * n_ck + scal_d * B + 2 * (size_t)B * nu + 2 * (size_t)B * (nbe + nba) + B) * sizeof(double);
+  const size_t bytes_i = (scal_i * B + D + 2) * sizeof(int) + (size_t)B * sizeof(unsigned long long);
+  const int64_t n_keep = cfg->n_draws;
+  const size_t bytes_out = (size_t)n_keep * B * (D + 3) * sizeof(double) + (size_t)n_keep * B * 2 * sizeof(int);
+  Buf arena;
+  CK(arena.ensure(bytes_d + bytes_i + bytes_out + 4096));
+  CK(cudaMemsetAsync(arena.p, 0, bytes_d + bytes_i + 1024, st));
+  char* cur = (char*)arena.p;
+  auto take_d = [&](size_t n) { double* p = (double*)cur; cur += n * sizeof(double); return p; };
+  NutsState s;
+  memset(&s, 0, sizeof(s));
+  s.B = B; s.N = N; s.D = D; s.nbe = nbe; s.nba = nba;
+  s.eu = take_d((size_t)B * nu); s.egu = take_d((size_t)B * nu);
+  s.ece = take_d((size_t)B * std::max(nbe, 1)); s.egce = take_d((size_t)B * std::max(nbe, 1));
+  s.eca = take_d((size_t)B * std::max(nba, 1)); s.egca = take_d((size_t)B * std::max(nba, 1));
+  s.elogp = take_d(B);
+  double** vec_ptrs[] = {&s.q, &s.g, &s.ql, &s.pl, &s.gl, &s.qr, &s.pr, &s.gr, &s.qp, &s.gp, &s.qs, &s.gs,
+                         &s.qc, &s.pc, &s.gc, &s.ph, &s.rsum, &s.rsum_s, &s.inv_mass, &s.w_mean, &s.w_m2};
+  for (double** pp : vec_ptrs) *pp = take_d(n_vec);
+  s.ck_r = take_d(n_ck); s.ck_rs = take_d(n_ck);
+  double** sc_ptrs[] = {&s.logp, &s.logp_p, &s.logp_s, &s.energy0, &s.lw_tree, &s.lw_sub, &s.sum_acc, &s.eps,
+                        &s.da_mu, &s.da_hbar, &s.da_logeps_bar};
+  for (double** pp : sc_ptrs) *pp = take_d(B);
+  s.rng = (unsigned long long*)cur; cur += (size_t)B * sizeof(unsigned long long);
+  auto take_i = [&](size_t n) { int* p = (int*)cur; cur += n * sizeof(int); return p; };
+  int** int_ptrs[] = {&s.n_leap, &s.dir, &s.active, &s.sub_stop, &s.diverged, &s.depth, &s.da_count, &s.w_count};
+  for (int** pp : int_ptrs) *pp = take_i(B);
+  int* d_role = take_i(D);
+  s.role = d_role;
+  s.n_active = take_i(1);
+  s.n_stopped = take_i(1);
+  cur = (char*)(((uintptr_t)cur + 255) & ~(uintptr_t)255);
+  double* d_draws = (double*)cur; cur += (size_t)n_keep * B * D * sizeof(double);
+  double* d_acc = (double*)cur; cur += (size_t)n_keep * B * sizeof(double);
+  double* d_lp = (double*)cur; cur += (size_t)n_keep * B * sizeof(double);
+  double* d_eps = (double*)cur; cur += (size_t)n_keep * B * sizeof(double);
+  int* d_depth = (int*)cur; cur += (size_t)n_keep * B * sizeof(int);
+  int* d_div = (int*)cur; cur += (size_t)n_keep * B * sizeof(int);
+  int32_t* d_sl = nullptr;
+  Buf slbuf;
+  if (sightline) {
+    for (int64_t i = 0; i < B; ++i)
+      if (sightline[i] < 0 || sightline[i] >= h->n_sl) return fail(h, CHI_EINVAL, "chi_nuts_sample: sightline out of range");
+    CK(slbuf.ensure(B * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(slbuf.p, sightline, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    d_sl = (int32_t*)slbuf.p;
+  }
+  CK(cudaMemcpyAsync(d_role, role.data(), D * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s.eu, init_u, (size_t)B * nu * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (nbe && init_ce) CK(cudaMemcpyAsync(s.ece, init_ce, (size_t)B * nbe * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (nba && init_ca) CK(cudaMemcpyAsync(s.eca, init_ca, (size_t)B * nba * sizeof(double), cudaMemcpyHostToDevice, st));
+
+  const unsigned grid = (unsigned)((B + 63) / 64);
+  auto evaluate = [&]() -> int {
+    h->call_first_stage = h->stage_calls;
+    return run_backward(h, h->lanes[0], B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, nullptr, nullptr,
+                        false, s.elogp, s.egu, nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true);
+  };
+  const double eps0 = cfg->init_step > 0.0 ? cfg->init_step : 0.25 / pow((double)std::max(n_free, 1), 0.25);
+  k_nuts_init<<<grid, 64, 0, st>>>(s, (unsigned long long)cfg->seed, eps0);
+  rc = evaluate();
+  if (rc) return rc;
+  k_nuts_adopt<<<grid, 64, 0, st>>>(s);
+  h->launches += 2;
+
+  // Stan-style warm-up schedule: fast buffer | doubling slow windows | fast buffer
+  const int n_tune = cfg->n_tune;
+  int init_buf = 75, term_buf = 50, base_win = 25;
+  if (n_tune < 150) { init_buf = (int)(0.15 * n_tune); term_buf = (int)(0.1 * n_tune); base_win = n_tune - init_buf - term_buf; }
+  std::vector<char> closes(std::max(n_tune, 1), 0);
+  {
+    int start = init_buf, win = base_win;
+    const int slow_end = n_tune - term_buf;
+    while (win > 0 && start < slow_end) {
+      int end = start + win;
+      if (end + 2 * win > slow_end) end = slow_end;  // the last window absorbs the remainder
+      closes[end - 1] = 1;
+      start = end;
+      win *= 2;
+    }
+  }
+  int* h_flags = nullptr;
+  CK(cudaMallocHost(&h_flags, 2 * sizeof(int)));
+  const int total = n_tune + cfg->n_draws;
+  for (int it = 0; it < total; ++it) {
+    k_nuts_begin_iter<<<grid, 64, 0, st>>>(s);
+    h->launches++;
+    for (int depth = 0; depth < max_depth; ++depth) {
+      CK(cudaMemsetAsync(s.n_stopped, 0, sizeof(int), st));
+      k_nuts_begin_subtree<<<grid, 64, 0, st>>>(s);
+      h->launches++;
+      const int leaves = 1 << depth;
+      for (int leaf = 0; leaf < leaves; ++leaf) {
+        k_nuts_leap_a<<<grid, 64, 0, st>>>(s);
+        rc = evaluate();
+        if (rc) { cudaFreeHost(h_flags); return rc; }
+        k_nuts_leap_b<<<grid, 64, 0, st>>>(s, leaf);
+        h->launches += 2;
+        if (depth >= 4 && (leaf & 7) == 7 && leaf + 1 < leaves) {  // every chain's sub-tree stopped early?
+          CK(cudaMemcpyAsync(h_flags + 1, s.n_stopped, sizeof(int), cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
+          if (h_flags[1] >= B) break;
+        }
+      }
+      k_nuts_end_subtree<<<grid, 64, 0, st>>>(s, max_depth);
+      h->launches++;
+      CK(cudaMemcpyAsync(h_flags, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (h_flags[0] <= 0) break;
+    }
+    NutsAdapt a;
+    memset(&a, 0, sizeof(a));
+    a.target_accept = target;
+    const bool tuning = it < n_tune;
+    a.tuning = tuning;
+    a.adapt_step = tuning;
+    a.collect_mass = tuning && it >= init_buf && it < n_tune - term_buf;
+    a.close_window = tuning && closes[it];
+    a.finalize = tuning && it == n_tune - 1;
+    const int64_t k = it - n_tune;
+    k_nuts_end_iter<<<grid, 64, 0, st>>>(s, a, tuning ? nullptr : d_draws, d_acc, d_depth, d_div, d_lp, d_eps, tuning ? 0 : k);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  cudaFreeHost(h_flags);
+  // draws back to the host in the layout of the API blocks
+  CK(cudaStreamSynchronize(st));
+  std::vector<double> tmp((size_t)n_keep * B * D);
+  CK(cudaMemcpy(tmp.data(), d_draws, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n_keep * B; ++i) {
+    const double* src = tmp.data() + i * D;
+    memcpy(draws_u + i * nu, src, nu * sizeof(double));
+    // replicas of a per-draw scalar mirror cloud 0
+    for (int d = 0; d < nu; ++d)
+      if (role[d] == 2) draws_u[i * nu + d] = src[d - (d % N)];
+    if (draws_ce && nbe) memcpy(draws_ce + i * nbe, src + nu, nbe * sizeof(double));
+    if (draws_ca && nba) memcpy(draws_ca + i * nba, src + nu + nbe, nba * sizeof(double));
+  }
+  if (stat_accept) CK(cudaMemcpy(stat_accept, d_acc, (size_t)n_keep * B * sizeof(double), cudaMemcpyDeviceToHost));
+  if (stat_logp) CK(cudaMemcpy(stat_logp, d_lp, (size_t)n_keep * B * sizeof(double), cudaMemcpyDeviceToHost));
+  if (stat_step) CK(cudaMemcpy(stat_step, d_eps, (size_t)n_keep * B * sizeof(double), cudaMemcpyDeviceToHost));
+  if (stat_depth) CK(cudaMemcpy(stat_depth, d_depth, (size_t)n_keep * B * sizeof(int), cudaMemcpyDeviceToHost));
+  if (stat_diverged) CK(cudaMemcpy(stat_diverged, d_div, (size_t)n_keep * B * sizeof(int), cudaMemcpyDeviceToHost));
+  arena.release();
+  slbuf.release();
   return CHI_OK;
 }
 

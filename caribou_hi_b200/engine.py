@@ -333,6 +333,43 @@ class Engine:
                                               p(logp), p(grad), p(gcoeff_e), p(gcoeff_a))
         )
 
+    def nuts_sample(self, init_u, init_ce=None, init_ca=None, *, n_tune=1000, n_draws=1000, seed=1234,
+                    target_accept=0.8, max_treedepth=10, init_step=0.0, sightline=None):
+        """Chain-batched NUTS on the device.  ``init_u [chains, NSLOT, N]`` are unconstrained
+        starting points with finite model logp.  Returns a dict with ``u [n_draws, chains, NSLOT,
+        N]`` (unconstrained draws), ``coeff_e``/``coeff_a`` and the sampler statistics
+        ``accept``, ``depth``, ``diverging``, ``logp``, ``step_size`` (``[n_draws, chains]``)."""
+        N = self.n_clouds
+        init_u = _f64(init_u)
+        chains = init_u.shape[0]
+        if init_u.shape[1:] != (layout.NSLOT, N):
+            raise ValueError("init_u: bad shape")
+        ce = self._coeffs(np.zeros((chains, self.nb_e)) if init_ce is None else init_ce, self.nb_e, chains, "init_ce")
+        ca = self._coeffs(np.zeros((chains, self.nb_a)) if init_ca is None else init_ca, self.nb_a, chains, "init_ca")
+        sl = None if sightline is None else np.ascontiguousarray(sightline, dtype=np.int32)
+        cfg = _lib.ChiNutsConfig(chains=chains, n_tune=int(n_tune), n_draws=int(n_draws),
+                                 max_treedepth=int(max_treedepth), seed=int(seed),
+                                 target_accept=float(target_accept), init_step=float(init_step))
+        out = {
+            "u": np.empty((n_draws, chains, layout.NSLOT, N)),
+            "coeff_e": np.empty((n_draws, chains, self.nb_e)) if self.nb_e else None,
+            "coeff_a": np.empty((n_draws, chains, self.nb_a)) if self.nb_a else None,
+            "accept": np.empty((n_draws, chains)),
+            "depth": np.empty((n_draws, chains), dtype=np.int32),
+            "diverging": np.empty((n_draws, chains), dtype=np.int32),
+            "logp": np.empty((n_draws, chains)),
+            "step_size": np.empty((n_draws, chains)),
+        }
+        self._check(
+            self._lib.chi_nuts_sample(
+                self._h, C.byref(cfg), _lib.as_dp(init_u), _lib.as_dp(ce), _lib.as_dp(ca), _lib.as_ip(sl),
+                _lib.as_dp(out["u"]), _lib.as_dp(out["coeff_e"]), _lib.as_dp(out["coeff_a"]),
+                _lib.as_dp(out["accept"]), _lib.as_ip(out["depth"]), _lib.as_ip(out["diverging"]),
+                _lib.as_dp(out["logp"]), _lib.as_dp(out["step_size"]),
+            )
+        )
+        return out
+
     def transform(self, block, direction=1):
         """PyMC's default transforms on ``[B, NSLOT, N]``: ``direction=+1`` unconstrained ->
         constrained, ``-1`` the inverse."""

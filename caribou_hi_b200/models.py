@@ -137,6 +137,81 @@ class _HIBase(ABC):
             grads["baseline_absorption_norm"] = gca
         return logp, grads
 
+    def sample(self, draws=1000, tune=1000, chains=8, seed=None, target_accept=0.8, max_treedepth=10,
+               init_point=None, jitter=None):
+        """Batched NUTS over ``chains`` on the device -- the role of ``BaseModel.sample`` /
+        ``pm.sample`` in the reference (optimization.ipynb cell 12), but with all chains in one
+        process and one batched logp+grad kernel pipeline per leapfrog step.
+
+        Starting points follow PyMC's "jitter" initialisation: the model's initial point (the
+        origin of the unconstrained space, i.e. the moment of each prior -- or ``init_point``, a
+        dict of constrained values such as an optimiser/ADVI result) plus Uniform(-jitter, jitter)
+        noise per chain in the unconstrained space, redrawn for chains whose model logp is not
+        finite.  Returns ``(posterior, stats)``: dicts of ``[chains, draws, ...]`` arrays keyed by
+        free-RV name (constrained values) and by statistic."""
+        seed = self.seed if seed is None else seed
+        rng = np.random.default_rng(seed)
+        eng = self.engine
+        N, nb = self.n_clouds, self.baseline_degree + 1
+        if init_point is None:
+            base = {}
+            for k in eng.slots:
+                shape = (1, 1) if k in layout.scalar_rvs(self.kind) else (1, N)
+                if k == "nth_fwhm_1pc":  # TruncatedNormal: start at its location parameter
+                    base[k] = np.full(shape, np.log(self._priors.get("prior_nth_fwhm_1pc", (1.75, 0.25))[0]))
+                else:
+                    base[k] = np.zeros(shape)
+            for key in self._required_keys:
+                base[f"baseline_{key}_norm"] = np.zeros((1, nb))
+            # the coupled Normal (log10_wt_ff_*) starts at its prior mean given the other values
+            wt = [k for k in eng.slots if k.startswith("log10_wt_ff")]
+            if wt:
+                x0 = self.to_constrained({layout.value_name(k): v for k, v in base.items()})
+                det = self.deterministics(x0)
+                T = det["fwhm2_thermal" if self._physical else "tkin"]
+                sig = self._priors.get("prior_sigma_log10_NHI") or 0.5
+                base[wt[0]] = -np.log(10.0) * sig**2 / 2.0 - np.log10(T)
+        else:
+            base = self._strip(self.to_unconstrained(init_point))
+        if jitter is None:
+            jitter = 1.0 if init_point is None else 0.1
+
+        def jittered(scale):
+            out = {}
+            for k, v in base.items():
+                v = np.asarray(v, dtype=np.float64)
+                full = np.broadcast_to(v, (chains,) + v.shape[1:]) if v.shape[0] in (1, chains) else v
+                out[k] = full + rng.uniform(-scale, scale, size=full.shape)
+            return out
+
+        start, scale = jittered(jitter), jitter
+        lp = self.model_logp_dlogp(start)[0]
+        for _ in range(30):
+            bad = ~np.isfinite(lp)
+            if not bad.any():
+                break
+            scale *= 0.8
+            cand = jittered(scale)
+            for k in start:
+                start[k][bad] = cand[k][bad]
+            lp = self.model_logp_dlogp(start)[0]
+        else:
+            raise RuntimeError("could not find starting points with finite model logp")
+        start = self._strip(start)
+        u0, ce, ca, _ = self._split(start)
+        res = eng.nuts_sample(u0, ce, ca, n_tune=tune, n_draws=draws, seed=int(rng.integers(1 << 62)),
+                              target_accept=target_accept, max_treedepth=max_treedepth)
+        x = eng.transform(res["u"].reshape(draws * chains, layout.NSLOT, self.n_clouds), +1)
+        x = x.reshape(draws, chains, layout.NSLOT, self.n_clouds).transpose(1, 0, 2, 3)
+        post = {k: (x[:, :, s, :1] if k in layout.scalar_rvs(self.kind) else x[:, :, s, :])
+                for k, s in eng.slots.items()}
+        if res["coeff_e"] is not None:
+            post["baseline_emission_norm"] = res["coeff_e"].transpose(1, 0, 2)
+        if res["coeff_a"] is not None:
+            post["baseline_absorption_norm"] = res["coeff_a"].transpose(1, 0, 2)
+        stats = {k: res[k].T for k in ("accept", "depth", "diverging", "logp", "step_size")}
+        return post, stats
+
     # -- evaluation ---------------------------------------------------------------
     @property
     def free_RVs(self):

@@ -301,6 +301,30 @@ int chi_model_logp_grad_dev(chi_handle* h, int64_t B, const double* u, const dou
  * (theta usable by chi_logp_grad / chi_spectra), -1 the inverse.  in/out: [B][CHI_NSLOT][N] host. */
 int chi_transform(chi_handle* h, int64_t B, int direction, const double* in, double* out);
 
+/* ---- chain-batched NUTS -------------------------------------------
+ * Replaces PyMC's process-per-chain pm.sample(...) loop (optimization.ipynb cell 12) for the model
+ * logp above: all `chains` advance in lock step on the device, one batched logp+grad evaluation
+ * per leapfrog step; multinomial NUTS with iterative U-turn checks, dual-averaging step size and
+ * windowed diagonal mass adaptation during the n_tune warm-up iterations.  Draws come back in
+ * the unconstrained space (chi_transform maps them), host pointers:
+ *   init_u[chains][CHI_NSLOT][N], init_ce/_ca[chains][n_baseline]   starting points (finite logp!)
+ *   draws_u[n_draws][chains][CHI_NSLOT][N], draws_ce/_ca[n_draws][chains][n_baseline]
+ *   stat_*[n_draws][chains]: mean acceptance probability, tree depth, divergence flag, model logp,
+ *   step size (any may be NULL). */
+typedef struct chi_nuts_config {
+  int64_t chains;
+  int32_t n_tune, n_draws;
+  int32_t max_treedepth;   /* <= 12; 0 -> 10 */
+  int32_t reserved;
+  uint64_t seed;
+  double target_accept;    /* 0 -> 0.8 */
+  double init_step;        /* 0 -> 0.25 / n_free^(1/4) (PyMC's default scaling) */
+} chi_nuts_config;
+int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* init_u, const double* init_ce,
+                    const double* init_ca, const int32_t* sightline, double* draws_u, double* draws_ce,
+                    double* draws_ca, double* stat_accept, int32_t* stat_depth, int32_t* stat_diverged,
+                    double* stat_logp, double* stat_step);
+
 /* ---- measurement helpers --------------------------------------------------- */
 /* Milliseconds spent in the kernels of the last model-level call on this handle
  * (CUDA events on the handle's stream; synchronises). */
