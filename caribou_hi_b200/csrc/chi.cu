@@ -93,6 +93,7 @@ struct chi_handle {
   // further staging of the host entry points (single-lane paths)
   Buf w_gbe, w_gba, w_mue, w_mua, w_misc[8];
   bool priors_set = false;
+  bool capturing = false;  // inside a stream capture: no timing events
   double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];
   int64_t call_first_stage = 0;  // stage_calls at the start of the current model-level call
   int64_t launches = 0;
@@ -213,7 +214,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   const int N = h->cfg.n_clouds;
   const bool pv = h->cfg.lorentzian != 0;
   cudaEvent_t* evs = h->ring[h->stage_calls % CHI_STAGE_RING];
-  CK(cudaEventRecord(evs[0], L.st));
+  if (!h->capturing) CK(cudaEventRecord(evs[0], L.st));
   const double* u = nullptr;
   if (model) {
     CK(L.xcon.ensure((size_t)B * CHI_NSLOT * N * sizeof(double)));
@@ -223,7 +224,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   int rc = launch_cloud_map(h, L, B, theta, model ? L.xcon.d() : nullptr);
   if (rc) return rc;
   if (model) theta = L.xcon.d();  // everything downstream works on the constrained values
-  CK(cudaEventRecord(evs[1], L.st));
+  if (!h->capturing) CK(cudaEventRecord(evs[1], L.st));
   CK(cudaEventRecord(L.ev_fork, L.st));  // the cloud constants are ready from here on
 
   EpiArgs ea;
@@ -256,7 +257,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     ea.has_e = 1; ea.nb_e = a.n_base; ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride;
     ea.mom_e = L.mom_e.d();
   }
-  CK(cudaEventRecord(evs[2], L.st));
+  if (!h->capturing) CK(cudaEventRecord(evs[2], L.st));
   // under-filled launches (few chains): absorption runs next to emission on the aux stream
   const bool fork = do_e && do_a && B * 8 < (int64_t)h->n_sm * 16;
   cudaStream_t st_a = fork ? L.aux : L.st;
@@ -281,7 +282,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     CK(cudaEventRecord(L.ev_join, L.aux));
     CK(cudaStreamWaitEvent(L.st, L.ev_join, 0));
   }
-  CK(cudaEventRecord(evs[3], L.st));
+  if (!h->capturing) CK(cudaEventRecord(evs[3], L.st));
   // baseline-coefficient gradients of a dataset that did not run are zero
   if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), L.st));
   if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), L.st));
@@ -302,8 +303,8 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   }
   h->launches++;
   CK(cudaGetLastError());
-  CK(cudaEventRecord(evs[4], L.st));
-  h->stage_calls++;
+  if (!h->capturing) CK(cudaEventRecord(evs[4], L.st));
+  if (!h->capturing) h->stage_calls++;
   return CHI_OK;
 }
 
@@ -1151,7 +1152,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   for (int i = 0; i < nbe + nba; ++i) { role[nu + i] = 1; ++n_free; }
 
   // one arena for the whole sampler state
-  const size_t vecs = 22, scal_d = 11, scal_i = 8;
+  const size_t vecs = 22, scal_d = 11, scal_i = 10;
   const size_t n_vec = (size_t)B * D, n_ck = (size_t)B * CHI_NUTS_MAX_DEPTH * D;
   const size_t bytes_d = (vecs * n_vec + 2 * n_ck + scal_d * B + 2 * (size_t)B * nu + 2 * (size_t)B * (nbe + nba) + B) * sizeof(double);
   const size_t bytes_i = (scal_i * B + D + 2) * sizeof(int) + (size_t)B * sizeof(unsigned long long);
@@ -1178,7 +1179,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   for (double** pp : sc_ptrs) *pp = take_d(B);
   s.rng = (unsigned long long*)cur; cur += (size_t)B * sizeof(unsigned long long);
   auto take_i = [&](size_t n) { int* p = (int*)cur; cur += n * sizeof(int); return p; };
-  int** int_ptrs[] = {&s.n_leap, &s.dir, &s.active, &s.sub_stop, &s.diverged, &s.depth, &s.da_count, &s.w_count};
+  int** int_ptrs[] = {&s.n_leap, &s.dir, &s.active, &s.sub_stop, &s.diverged, &s.depth, &s.da_count, &s.w_count, &s.leaf};
   for (int** pp : int_ptrs) *pp = take_i(B);
   int* d_role = take_i(D);
   s.role = d_role;
@@ -1234,6 +1235,23 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
       win *= 2;
     }
   }
+  // one leapfrog step (half kick + drift, batched logp+grad, half kick + tree bookkeeping) as a
+  // CUDA graph: ~8 dependent launches per step would otherwise be pure launch latency for a few
+  // dozen chains
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  h->capturing = true;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  k_nuts_leap_a<<<grid, 64, 0, st>>>(s);
+  rc = evaluate();
+  k_nuts_leap_b<<<grid, 64, 0, st>>>(s);
+  cudaError_t cap_err = cudaStreamEndCapture(st, &graph);
+  h->capturing = false;
+  if (rc) return rc;
+  CK(cap_err);
+  CK(cudaGraphInstantiate(&gexec, graph, 0));
+  size_t n_nodes = 0;
+  CK(cudaGraphGetNodes(graph, nullptr, &n_nodes));
   int* h_flags = nullptr;
   CK(cudaMallocHost(&h_flags, 2 * sizeof(int)));
   const int total = n_tune + cfg->n_draws;
@@ -1246,11 +1264,8 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
       h->launches++;
       const int leaves = 1 << depth;
       for (int leaf = 0; leaf < leaves; ++leaf) {
-        k_nuts_leap_a<<<grid, 64, 0, st>>>(s);
-        rc = evaluate();
-        if (rc) { cudaFreeHost(h_flags); return rc; }
-        k_nuts_leap_b<<<grid, 64, 0, st>>>(s, leaf);
-        h->launches += 2;
+        CK(cudaGraphLaunch(gexec, st));
+        h->launches += (int64_t)n_nodes;
         if (depth >= 4 && (leaf & 7) == 7 && leaf + 1 < leaves) {  // every chain's sub-tree stopped early?
           CK(cudaMemcpyAsync(h_flags + 1, s.n_stopped, sizeof(int), cudaMemcpyDeviceToHost, st));
           CK(cudaStreamSynchronize(st));
@@ -1278,6 +1293,8 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     CK(cudaGetLastError());
   }
   cudaFreeHost(h_flags);
+  cudaGraphExecDestroy(gexec);
+  cudaGraphDestroy(graph);
   // draws back to the host in the layout of the API blocks
   CK(cudaStreamSynchronize(st));
   std::vector<double> tmp((size_t)n_keep * B * D);

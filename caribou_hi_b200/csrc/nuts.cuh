@@ -50,6 +50,7 @@ struct NutsState {
   double *logp, *logp_p, *logp_s, *energy0, *lw_tree, *lw_sub, *sum_acc, *eps;
   double *da_mu, *da_hbar, *da_logeps_bar;
   int *n_leap, *dir, *active, *sub_stop, *diverged, *depth, *da_count, *w_count;
+  int* leaf;                   // [B] index of the next leaf of the sub-tree being built
   unsigned long long* rng;
   int* n_active;               // [1] chains whose tree is still growing
   int* n_stopped;              // [1] chains idle in the current doubling (inactive or sub-tree stopped)
@@ -178,6 +179,7 @@ __global__ void k_nuts_begin_subtree(NutsState s) {
     s.rsum_s[o + d] = 0.0;
   }
   s.lw_sub[b] = -INFINITY;
+  s.leaf[b] = 0;
 }
 
 // ---- leapfrog, first half: half kick + drift; the new position becomes the evaluation point ---
@@ -198,10 +200,12 @@ __global__ void k_nuts_leap_a(NutsState s) {
   nuts_set_eval(s, b, x);
 }
 
-// ---- leapfrog, second half + sub-tree bookkeeping for leaf number `leaf` -------------------
-__global__ void k_nuts_leap_b(NutsState s, int leaf) {
+// ---- leapfrog, second half + sub-tree bookkeeping of the chain's next leaf -------------------
+// (the leaf index lives on the device so that one captured CUDA graph serves every leapfrog step)
+__global__ void k_nuts_leap_b(NutsState s) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B || s.sub_stop[b]) return;
+  const int leaf = s.leaf[b]++;
   const int64_t o = b * s.D;
   const double h = s.dir[b] * s.eps[b];
   const double lp = s.elogp[b];
