@@ -13,7 +13,7 @@
 
 #include "../../include/chi.h"
 #include "kernels.cuh"
-#include "moments_win.cuh"
+#include "launch.cuh"
 #include "nuts.cuh"
 
 #define CHI_STAGE_RING 64
@@ -152,39 +152,6 @@ void pick_chunks(const chi_handle* h, int64_t B, int S, int* n_chunks, int* chun
   *n_chunks = (S + len - 1) / len;
 }
 
-template <template <int, bool> class Launcher, class... A>
-int dispatch_np(int N, bool pv, A... args) {
-  switch (N * 2 + (pv ? 1 : 0)) {
-#define CASE(n)                                        \
-  case (n)*2: return Launcher<n, false>::run(args...); \
-  case (n)*2 + 1: return Launcher<n, true>::run(args...);
-    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
-#undef CASE
-  }
-  return -1;
-}
-
-inline unsigned warp_grid(const ChanArgs& a) {
-  int64_t items = a.B * a.n_chunks;
-  return (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
-}
-template <int N, bool PV>
-struct LaunchEm {
-  static int run(const ChanArgs& a, cudaStream_t st, int family, int cpt) {
-    if (family == 1) k_moments_em<N, PV><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
-    else k_moments_em2<N, PV, 2><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
-    return 0;
-  }
-};
-template <int N, bool PV>
-struct LaunchAb {
-  static int run(const ChanArgs& a, cudaStream_t st, int family, int cpt) {
-    if (family == 1) k_moments_abs<N, PV><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
-    else k_moments_abs2<N, PV, 2><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
-    return 0;
-  }
-};
-
 #define MODEL_SWITCH(model, STMT)                                                                 \
   switch (model) {                                                                                \
     case CHI_MODEL_PHYSICS: { constexpr int M = CHI_MODEL_PHYSICS; STMT; } break;                 \
@@ -251,7 +218,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.vax = h->e.vax.d(); a.yeff = h->e.yeff.d(); a.wgt = h->e.wgt.d(); a.basis = h->e.basis.d();
     a.coeff = ce; a.sl = sl; a.gbar = vjp ? gbar_e : nullptr; a.cc = L.cc.d(); a.mom = L.mom_e.d();
-    if (dispatch_np<LaunchEm>(N, pv, a, L.st, h->kernel_family, h->cpt)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    if (launch_moments_em(N, pv, a, L.st, h->kernel_family)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
     ea.has_e = 1; ea.nb_e = a.n_base; ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride;
@@ -272,7 +239,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     CK(L.mom_a.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.vax = h->a.vax.d(); a.yeff = h->a.yeff.d(); a.wgt = h->a.wgt.d(); a.basis = h->a.basis.d();
     a.coeff = ca; a.sl = sl; a.gbar = vjp ? gbar_a : nullptr; a.cc = L.cc.d(); a.mom = L.mom_a.d();
-    if (dispatch_np<LaunchAb>(N, pv, a, st_a, h->kernel_family, h->cpt)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    if (launch_moments_abs(N, pv, a, st_a, h->kernel_family)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
     ea.has_a = 1; ea.nb_a = a.n_base; ea.chunks_a = a.n_chunks; ea.stride_a = a.mom_stride;

@@ -1,0 +1,30 @@
+// k_moments_abs<N, PV> instantiations (N = 1..8, Gaussian / pseudo-Voigt).
+// -DCHI_WINDOWED additionally builds the experimental windowed family (moments_win.cuh).
+#include "launch.cuh"
+#ifdef CHI_WINDOWED
+#include "moments_win.cuh"
+#endif
+
+namespace chi {
+template <int N, bool PV>
+static void run(const ChanArgs& a, cudaStream_t st, int family) {
+#ifdef CHI_WINDOWED
+  if (family == 2) {
+    k_moments_abs2<N, PV, 2><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
+    return;
+  }
+#endif
+  k_moments_abs<N, PV><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
+}
+
+int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st, int family) {
+  switch (N * 2 + (pv ? 1 : 0)) {
+#define CASE(n)                                \
+  case (n)*2: run<n, false>(a, st, family); return 0; \
+  case (n)*2 + 1: run<n, true>(a, st, family); return 0;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  return -1;
+}
+}  // namespace chi
