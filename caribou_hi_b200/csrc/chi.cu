@@ -289,7 +289,7 @@ int run_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce,
     a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp; a.vax = h->e.vax.d();
     a.basis = h->e.basis.d(); a.offset = h->e.has_offset ? h->e.offset.d() : nullptr;
     a.coeff = ce; a.mu = mu_e; a.emission = 1;
-    k_spectra<true><<<(unsigned)B, 256, 0, h->stream>>>(a);
+    if (launch_spectra(N, a.pv != 0, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
   }
@@ -297,7 +297,7 @@ int run_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce,
     a.S = h->a.S; a.n_base = h->a.nb; a.bg = 0.0; a.vax = h->a.vax.d();
     a.basis = h->a.basis.d(); a.offset = h->a.has_offset ? h->a.offset.d() : nullptr;
     a.coeff = ca; a.mu = mu_a; a.emission = 0;
-    k_spectra<false><<<(unsigned)B, 256, 0, h->stream>>>(a);
+    if (launch_spectra(N, a.pv != 0, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
   }

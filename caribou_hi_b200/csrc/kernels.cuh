@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #include "cloud_map.cuh"
-#include "moments.cuh"
+#include "launch.cuh"
 
 namespace chi {
 
@@ -270,75 +270,6 @@ __global__ void k_transform(MapCfg cfg, int64_t total, int N, int direction, con
     r = log(v) - log1p(-v);
   }
   out[t] = r;
-}
-
-// ---------------------------------------------------------------------------
-// k_spectra: predicted spectra only (posterior / prior predictive)
-// ---------------------------------------------------------------------------
-struct SpecArgs {
-  int64_t B;
-  int N;
-  int S;
-  int n_base;
-  int pv;
-  int emission;  // 1: radiative transfer, 0: absorption
-  double bg;
-  const double* __restrict__ vax;
-  const double* __restrict__ basis;
-  const double* __restrict__ offset;  // [S] or null
-  const double* __restrict__ coeff;   // [B][n_base] or null
-  const double* __restrict__ cc;
-  double* __restrict__ mu;            // [B][S]
-};
-
-template <bool EMISSION>
-__global__ void __launch_bounds__(256) k_spectra(SpecArgs a) {
-  __shared__ double s_c[CHI_MAX_CLOUDS][8];
-  __shared__ double s_beta[CHI_MAX_BASELINE];
-  const int64_t b = blockIdx.x;
-  if (threadIdx.x < a.N) {
-    const double* p = a.cc + (b * a.N + threadIdx.x) * CHI_CC_STRIDE;
-    double* d = s_c[threadIdx.x];
-    d[0] = p[CC_C];
-    if (EMISSION) {
-      d[1] = p[CC_KE]; d[2] = p[CC_AGE]; d[3] = p[CC_ALE]; d[4] = p[CC_HE];
-      d[5] = p[CC_F]; d[6] = p[CC_TS]; d[7] = p[CC_F] * p[CC_TS];
-    } else {
-      d[1] = p[CC_KA]; d[2] = p[CC_AGA]; d[3] = p[CC_ALA]; d[4] = p[CC_HA];
-    }
-  }
-  if (threadIdx.x < a.n_base) s_beta[threadIdx.x] = a.coeff ? a.coeff[b * a.n_base + threadIdx.x] : 0.0;
-  __syncthreads();
-  for (int s = threadIdx.x; s < a.S; s += blockDim.x) {
-    const double v = a.vax[s];
-    double base = a.offset ? a.offset[s] : 0.0;
-    for (int i = 0; i < a.n_base; ++i) base = fma(s_beta[i], a.basis[(int64_t)i * a.S + s], base);
-    double out;
-    if (EMISSION) {
-      double P = 1.0, T = 0.0;
-      for (int n = 0; n < a.N; ++n) {
-        const double* c = s_c[n];
-        const double d = v - c[0], d2 = d * d;
-        double tau = c[2] * chi_exp(-c[1] * d2);
-        if (a.pv) tau = fma(c[3], 1.0 / (d2 + c[4]), tau);
-        const double e = chi_exp(-tau);
-        T = fma(c[7] * (1.0 - e), P, T);
-        P *= fma(c[5], e, 1.0 - c[5]);
-      }
-      out = (a.bg * P + T) - a.bg + base;
-    } else {
-      double tsum = 0.0;
-      for (int n = 0; n < a.N; ++n) {
-        const double* c = s_c[n];
-        const double d = v - c[0], d2 = d * d;
-        double tau = c[2] * chi_exp(-c[1] * d2);
-        if (a.pv) tau = fma(c[3], 1.0 / (d2 + c[4]), tau);
-        tsum += tau;
-      }
-      out = (1.0 - chi_exp(-tsum)) + base;
-    }
-    a.mu[b * a.S + s] = out;
-  }
 }
 
 // ---------------------------------------------------------------------------

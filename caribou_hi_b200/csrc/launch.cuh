@@ -7,6 +7,23 @@
 #include "moments.cuh"
 
 namespace chi {
+// argument block of the spectra-only kernels
+struct SpecArgs {
+  int64_t B;
+  int N;
+  int S;
+  int n_base;
+  int pv;
+  int emission;  // 1: radiative transfer, 0: absorption
+  double bg;
+  const double* __restrict__ vax;
+  const double* __restrict__ basis;
+  const double* __restrict__ offset;  // [S] or null
+  const double* __restrict__ coeff;   // [B][n_base] or null
+  const double* __restrict__ cc;
+  double* __restrict__ mu;            // [B][S]
+};
+int launch_spectra(int N, bool pv, const SpecArgs& a, cudaStream_t st);
 int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st, int family);
 int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st, int family);
 

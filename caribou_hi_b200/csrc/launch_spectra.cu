@@ -1,0 +1,85 @@
+// k_spectra_t<N, PV, EMISSION>: predicted spectra only (posterior / prior predictive,
+// BASELINE configs[4]) -- the forward half of moments.cuh with the cloud loop unrolled (the N
+// independent exp chains give the instruction-level parallelism), the table-driven branch-free
+// exp and the Newton reciprocal; one block per draw, threads walk channels, 8-byte coalesced
+// stores of mu.  emission: physics.py:294-309 + physics.py:345-365; absorption:
+// absorption_model.py:88-91.
+#include "launch.cuh"
+
+namespace chi {
+
+template <int N, bool PV, bool EMISSION>
+__global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
+  __shared__ __align__(16) double s_c[N][8];
+  __shared__ double s_beta[CHI_MAX_BASELINE];
+  __shared__ double s_T[64];
+  const int64_t b = blockIdx.x;
+  if (threadIdx.x < N) {
+    const double* p = a.cc + (b * N + threadIdx.x) * CHI_CC_STRIDE;
+    double* d = s_c[threadIdx.x];
+    d[0] = p[CC_C];
+    if (EMISSION) {
+      d[1] = -p[CC_KE]; d[2] = -p[CC_AGE]; d[3] = -p[CC_ALE]; d[4] = p[CC_HE];
+      d[5] = p[CC_F]; d[6] = p[CC_TS]; d[7] = p[CC_F] * p[CC_TS];
+    } else {
+      d[1] = -p[CC_KA]; d[2] = -p[CC_AGA]; d[3] = -p[CC_ALA]; d[4] = p[CC_HA];
+      d[5] = d[6] = d[7] = 0.0;
+    }
+  }
+  if (threadIdx.x < a.n_base) s_beta[threadIdx.x] = a.coeff ? a.coeff[b * a.n_base + threadIdx.x] : 0.0;
+  fill_exp_table(s_T);  // contains the block barrier
+  const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
+  const int S = a.S;
+  double* __restrict__ out = a.mu + b * S;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const double v = a.vax[s];
+    double base = a.offset ? a.offset[s] : 0.0;
+    for (int i = 0; i < a.n_base; ++i) base = fma(s_beta[i], a.basis[(int64_t)i * S + s], base);
+    double E[N], x[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      double c0, nk, nAG, nAL;
+      lds2(&s_c[n][0], c0, nk);
+      lds2(&s_c[n][2], nAG, nAL);
+      const double d = v - c0, d2 = d * d;
+      E[n] = chi_exp<false>(nk * d2, ek);
+      x[n] = nAG * E[n];  // -tau
+      if (PV) x[n] = fma(nAL, chi_rcp(d2 + s_c[n][4]), x[n]);
+    }
+    double r;
+    if (EMISSION) {
+      double P = 1.0, T = 0.0;
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        const double om = 1.0 - chi_exp<true>(x[n], ek);
+        T = fma(s_c[n][7] * om, P, T);
+        P *= fma(-s_c[n][5], om, 1.0);
+      }
+      r = (a.bg * P + T) - a.bg + base;
+    } else {
+      double xs = 0.0;
+#pragma unroll
+      for (int n = 0; n < N; ++n) xs += x[n];
+      r = (1.0 - chi_exp<true>(xs, ek)) + base;
+    }
+    out[s] = r;
+  }
+}
+
+template <int N, bool PV>
+static void run(const SpecArgs& a, cudaStream_t st) {
+  if (a.emission) k_spectra_t<N, PV, true><<<(unsigned)a.B, 256, 0, st>>>(a);
+  else k_spectra_t<N, PV, false><<<(unsigned)a.B, 256, 0, st>>>(a);
+}
+
+int launch_spectra(int N, bool pv, const SpecArgs& a, cudaStream_t st) {
+  switch (N * 2 + (pv ? 1 : 0)) {
+#define CASE(n)                           \
+  case (n)*2: run<n, false>(a, st); return 0; \
+  case (n)*2 + 1: run<n, true>(a, st); return 0;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  return -1;
+}
+}  // namespace chi
