@@ -14,6 +14,7 @@
 #include "../../include/chi.h"
 #include "kernels.cuh"
 #include "launch.cuh"
+#include "moments_ea.cuh"
 #include "nuts.cuh"
 
 #define CHI_STAGE_RING 64
@@ -92,6 +93,7 @@ struct chi_handle {
   Lane lanes[CHI_LANES];
   // further staging of the host entry points (single-lane paths)
   Buf w_gbe, w_gba, w_mue, w_mua, w_misc[8];
+  bool shared_axis = false;  // both datasets on the same spectral axis: fused kernel
   bool priors_set = false;
   bool capturing = false;  // inside a stream capture: no timing events
   double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];
@@ -208,7 +210,32 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   // in VJP mode a dataset without cotangent contributes nothing
   const bool do_e = h->has_e && (!vjp || gbar_e);
   const bool do_a = h->has_a && (!vjp || gbar_a);
-  if (do_e) {
+  bool fused_done = false;
+  if (h->shared_axis && h->kernel_family == 1 && (do_e || do_a)) {
+    // both datasets on one axis: one pass evaluates exp(-k d^2) once for the two of them
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.S = h->e.S; a.nb_e = h->e.nb; a.nb_a = h->a.nb; a.bg = h->cfg.bg_temp;
+    pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
+    a.mom_stride = 1 + a.nb_e + a.nb_a + N * (pv ? 10 : 6);
+    CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
+    a.vax = h->e.vax.d();
+    a.yeff_e = h->e.yeff.d(); a.wgt_e = h->e.wgt.d(); a.basis_e = h->e.basis.d(); a.coeff_e = ce;
+    a.yeff_a = h->a.yeff.d(); a.wgt_a = h->a.wgt.d(); a.basis_a = h->a.basis.d(); a.coeff_a = ca;
+    a.vjp = vjp ? 1 : 0; a.gbar_e = vjp ? gbar_e : nullptr; a.gbar_a = vjp ? gbar_a : nullptr;
+    a.sl = sl; a.cc = L.cc.d(); a.mom = L.mom_e.d();
+    if (launch_moments_ea(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    h->launches++;
+    CK(cudaGetLastError());
+    ea.fused = 1; ea.has_e = 1; ea.has_a = 1; ea.nb_e = a.nb_e; ea.nb_a = a.nb_a;
+    ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride; ea.mom_e = L.mom_e.d();
+    if (!h->capturing) {
+      CK(cudaEventRecord(evs[2], L.st));
+      CK(cudaEventRecord(evs[3], L.st));
+    }
+    fused_done = true;
+  }
+  if (do_e && !fused_done) {
     ChanArgs a;
     memset(&a, 0, sizeof(a));
     a.B = B; a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp;
@@ -226,10 +253,10 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   }
   if (!h->capturing) CK(cudaEventRecord(evs[2], L.st));
   // under-filled launches (few chains): absorption runs next to emission on the aux stream
-  const bool fork = do_e && do_a && B * 8 < (int64_t)h->n_sm * 16;
+  const bool fork = !fused_done && do_e && do_a && B * 8 < (int64_t)h->n_sm * 16;
   cudaStream_t st_a = fork ? L.aux : L.st;
   if (fork) CK(cudaStreamWaitEvent(L.aux, L.ev_fork, 0));
-  if (do_a) {
+  if (do_a && !fused_done) {
     ChanArgs a;
     memset(&a, 0, sizeof(a));
     a.B = B; a.S = h->a.S; a.n_base = h->a.nb; a.bg = 0.0;
@@ -545,6 +572,10 @@ int chi_set_spectra(chi_handle* h, int n_sightlines, const chi_dataset* emission
     int rc = upload_dataset(h, h->a, absorption, n_sightlines, lconst.data(), "absorption");
     if (rc) return rc;
     h->map.wch2_a = channel_fwhm2(absorption->spectral);
+  }
+  h->shared_axis = false;
+  if (h->has_e && h->has_a && emission->n_channels == absorption->n_channels && !getenv("CHI_NO_FUSED")) {
+    h->shared_axis = memcmp(emission->spectral, absorption->spectral, emission->n_channels * sizeof(double)) == 0;
   }
   CK(h->lconst.ensure(n_sightlines * sizeof(double)));
   CK(cudaMemcpy(h->lconst.p, lconst.data(), n_sightlines * sizeof(double), cudaMemcpyHostToDevice));

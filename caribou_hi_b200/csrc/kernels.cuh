@@ -76,6 +76,7 @@ struct EpiArgs {
   int nb_e, nb_a;
   int chunks_e, chunks_a;
   int stride_e, stride_a;
+  int fused;  // 1: mom_e holds the fused emission+absorption record of moments_ea.cuh
   const double* __restrict__ theta;
   const double* __restrict__ mom_e;
   const double* __restrict__ mom_a;
@@ -112,12 +113,18 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
 
   // --- sums over channel chunks (fixed order: deterministic) ---
   double me[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ma[6] = {0, 0, 0, 0, 0, 0};
-  if (a.has_e) {
+  double mf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (a.fused) {
+    const int NF = a.pv ? 10 : 6;
+    const double* p = a.mom_e + (b * a.chunks_e) * a.stride_e + 1 + a.nb_e + a.nb_a + n * NF;
+    for (int c = 0; c < a.chunks_e; ++c, p += a.stride_e)
+      for (int j = 0; j < NF; ++j) mf[j] += p[j];
+  } else if (a.has_e) {
     const double* p = a.mom_e + (b * a.chunks_e) * a.stride_e + 1 + a.nb_e + n * NE;
     for (int c = 0; c < a.chunks_e; ++c, p += a.stride_e)
       for (int j = 0; j < NE; ++j) me[j] += p[j];
   }
-  if (a.has_a) {
+  if (a.has_a && !a.fused) {
     const double* p = a.mom_a + (b * a.chunks_a) * a.stride_a + 1 + a.nb_a + n * NA;
     for (int c = 0; c < a.chunks_a; ++c, p += a.stride_a)
       for (int j = 0; j < NA; ++j) ma[j] += p[j];
@@ -125,7 +132,16 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   if (n == 0 && j0 == 0) {
     // logp and baseline-coefficient gradients: one thread per draw
     double lp = 0.0;
-    if (a.has_e) {
+    if (a.fused) {
+      const double* p = a.mom_e + (b * a.chunks_e) * a.stride_e;
+      for (int c = 0; c < a.chunks_e; ++c) lp += p[c * a.stride_e];
+      for (int i = 0; i < a.nb_e + a.nb_a; ++i) {
+        double g = 0.0;
+        for (int c = 0; c < a.chunks_e; ++c) g += p[c * a.stride_e + 1 + i];
+        if (i < a.nb_e) { if (a.gcoeff_e) a.gcoeff_e[b * a.nb_e + i] = g; }
+        else if (a.gcoeff_a) a.gcoeff_a[b * a.nb_a + (i - a.nb_e)] = g;
+      }
+    } else if (a.has_e) {
       const double* p = a.mom_e + (b * a.chunks_e) * a.stride_e;
       for (int c = 0; c < a.chunks_e; ++c) lp += p[c * a.stride_e];
       if (a.gcoeff_e)
@@ -135,7 +151,7 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
           a.gcoeff_e[b * a.nb_e + i] = g;
         }
     }
-    if (a.has_a) {
+    if (a.has_a && !a.fused) {
       const double* p = a.mom_a + (b * a.chunks_a) * a.stride_a;
       for (int c = 0; c < a.chunks_a; ++c) lp += p[c * a.stride_a];
       if (a.gcoeff_a)
@@ -183,7 +199,24 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   };
 
   double cbar = 0.0;
-  if (a.has_e) {
+  if (a.fused) {
+    // shared axis: k and h are common to the two datasets, their adjoints arrive combined
+    ProfConst<D> pe = profile_consts<D>(ph.fwhm2, ph.fwhm_L, ph.tau_total, cfg.wch2_e, cfg.lorentzian != 0);
+    ProfConst<D> pa = profile_consts<D>(ph.fwhm2, ph.fwhm_L, D(ph.wt * ph.tau_total), cfg.wch2_a,
+                                        cfg.lorentzian != 0);
+    const double f = ph.ff.v;
+    cbar = 2.0 * pe.k.v * mf[2] + 2.0 * mf[9];
+    addc(-mf[3], pe.k);
+    addc(f * mf[0], pe.AG);
+    addc(mf[1], pa.AG);
+    if (a.pv) {
+      addc(f * mf[6], pe.AL);
+      addc(mf[7], pa.AL);
+      addc(-mf[8], pe.h);
+    }
+    addc(f * mf[4], ph.tspin);
+    addc(mf[5], ph.ff);
+  } else if (a.has_e) {
     ProfConst<D> pe = profile_consts<D>(ph.fwhm2, ph.fwhm_L, ph.tau_total, cfg.wch2_e, cfg.lorentzian != 0);
     const double f = ph.ff.v;
     cbar += f * (2.0 * pe.k.v * pe.AG.v * me[1] + 2.0 * pe.AL.v * me[7]);
@@ -196,7 +229,7 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
     addc(f * me[3], ph.tspin);
     addc(me[4], ph.ff);
   }
-  if (a.has_a) {
+  if (a.has_a && !a.fused) {
     ProfConst<D> pa = profile_consts<D>(ph.fwhm2, ph.fwhm_L, D(ph.wt * ph.tau_total), cfg.wch2_a,
                                         cfg.lorentzian != 0);
     cbar += 2.0 * pa.k.v * pa.AG.v * ma[1] + 2.0 * pa.AL.v * ma[5];

@@ -24,6 +24,8 @@ struct SpecArgs {
   double* __restrict__ mu;            // [B][S]
 };
 int launch_spectra(int N, bool pv, const SpecArgs& a, cudaStream_t st);
+struct FusedArgs;
+int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st);
 int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st, int family);
 int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st, int family);
 

@@ -1,0 +1,226 @@
+// Fused emission + absorption kernel for datasets that share one spectral axis.
+//
+// When both spectra are sampled on the same velocity grid, the convolved line width, k = 4ln2/W^2
+// and h = W^2/4 of a cloud are the same for the two datasets and so is exp(-k d^2): one pass over
+// the channels evaluates it once and feeds both the radiative transfer (emission) and the summed
+// optical depth (absorption), cutting the absorption side from ~25 to ~9 FP64 instructions per
+// (draw, cloud, channel).  The gradients with respect to the line centre and k
+// (and h) are accumulated through COMBINED moments
+//     M1c = sum (f AG_e g_e + AG_a g_a) E d,   M2c = sum (...) E d^2,   [Q2c, Q2dc likewise with AL, q^2]
+// so the fused record needs 6 (Gaussian) / 10 (pseudo-Voigt) sums per cloud instead of 5+3 / 8+6:
+//     M0e = sum g_e E, M0a = sum g_a E, M1c, M2c, aTs, af, [Q1e, Q1a, Q2c, Q2dc]
+// Record per (draw, chunk): [0] = sum -0.5 w r^2 of both datasets, [1..nb_e] and [1+nb_e..] the
+// baseline-coefficient gradients, then N x NF moments.  k_epilogue reads it with `fused = 1`.
+#pragma once
+#include "moments.cuh"
+
+namespace chi {
+
+struct FusedArgs {
+  int64_t B;
+  int S;
+  int nb_e, nb_a;
+  int n_chunks, chunk_len, mom_stride;
+  double bg;
+  const double* __restrict__ vax;
+  const double* __restrict__ yeff_e;
+  const double* __restrict__ wgt_e;
+  const double* __restrict__ basis_e;
+  const double* __restrict__ coeff_e;
+  const double* __restrict__ gbar_e;
+  const double* __restrict__ yeff_a;
+  const double* __restrict__ wgt_a;
+  const double* __restrict__ basis_a;
+  const double* __restrict__ coeff_a;
+  const double* __restrict__ gbar_a;
+  int vjp;                             // 1: cotangents gbar_* instead of residuals (null = zeros)
+  const int32_t* __restrict__ sl;
+  const double* __restrict__ cc;
+  double* __restrict__ mom;
+};
+
+template <bool PV> struct FusedLayout { static constexpr int NF = PV ? 10 : 6; };
+
+constexpr int ea_min_blocks(int N, bool pv) {
+  const int regs = 2 * ((pv ? 10 : 6) * N + (pv ? 4 : 3) * N) + 56;
+  return clamp_blocks((regs <= 128 ? 4 : (regs <= 168 ? 3 : 2)) + CHI_BLOCKS_BIAS) * 4 / CHI_WARPS_PER_BLOCK;
+}
+
+// shared per cloud (pairs are fetched together; the Gaussian case touches the first three / four):
+//   [c, -k] [-AG_e, -AG_a] [f, f*Ts] [Ts, h] [-AL_e, -AL_a]
+template <int N, bool PV>
+__global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(FusedArgs a) {
+  constexpr int NF = FusedLayout<PV>::NF;
+  __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][10];
+  __shared__ double s_gb[2 * CHI_MAX_BASELINE][CHI_BLOCK];
+  __shared__ double s_beta[CHI_WARPS_PER_BLOCK][2 * CHI_MAX_BASELINE];
+  __shared__ double s_T[64];
+  fill_exp_table(s_T);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
+  if (item >= a.B * a.n_chunks) return;
+  const int64_t b = item / a.n_chunks;
+  const int chunk = (int)(item - b * a.n_chunks);
+  const int nbe = a.nb_e, nba = a.nb_a, S = a.S;
+
+  if (lane < N) {
+    const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
+    const double f = p[CC_F], ts = p[CC_TS];
+    double* d = s_c[warp][lane];
+    d[0] = p[CC_C]; d[1] = -p[CC_KE]; d[2] = -p[CC_AGE]; d[3] = -p[CC_AGA]; d[4] = f; d[5] = f * ts;
+    d[6] = ts; d[7] = p[CC_HE]; d[8] = -p[CC_ALE]; d[9] = -p[CC_ALA];
+  }
+  if (lane < nbe) s_beta[warp][lane] = a.coeff_e ? a.coeff_e[b * nbe + lane] : 0.0;
+  if (lane < nba) s_beta[warp][CHI_MAX_BASELINE + lane] = a.coeff_a ? a.coeff_a[b * nba + lane] : 0.0;
+  for (int i = 1; i < nbe; ++i) s_gb[i][threadIdx.x] = 0.0;
+  for (int i = 1; i < nba; ++i) s_gb[CHI_MAX_BASELINE + i][threadIdx.x] = 0.0;
+  __syncwarp();
+  // the first baseline term of each dataset (degree 0) stays in registers
+  const double be0 = nbe > 0 ? s_beta[warp][0] : 0.0, ba0 = nba > 0 ? s_beta[warp][CHI_MAX_BASELINE] : 0.0;
+  double gbe0 = 0.0, gba0 = 0.0;
+
+  const int sl = a.sl ? a.sl[b] : 0;
+  const double* __restrict__ Ye = a.yeff_e + (int64_t)sl * S;
+  const double* __restrict__ We = a.wgt_e + (int64_t)sl * S;
+  const double* __restrict__ Ya = a.yeff_a + (int64_t)sl * S;
+  const double* __restrict__ Wa = a.wgt_a + (int64_t)sl * S;
+  const double* __restrict__ Ge = a.gbar_e ? a.gbar_e + b * S : nullptr;
+  const double* __restrict__ Ga = a.gbar_a ? a.gbar_a + b * S : nullptr;
+  const double* __restrict__ V = a.vax;
+
+  double acc[N][NF];
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+#pragma unroll
+    for (int j = 0; j < NF; ++j) acc[n][j] = 0.0;
+  double lp = 0.0;
+  const double bg = a.bg;
+  const double(*sc)[10] = s_c[warp];
+  const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
+
+  const int s_end = min(S, (chunk + 1) * a.chunk_len);
+  for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
+    const double v = V[s];
+    double base_e = 0.0, base_a = 0.0, pe0 = 0.0, pa0 = 0.0;
+    if (nbe > 0) { pe0 = a.basis_e[s]; base_e = be0 * pe0; }
+    if (nba > 0) { pa0 = a.basis_a[s]; base_a = ba0 * pa0; }
+    for (int i = 1; i < nbe; ++i) base_e = fma(s_beta[warp][i], a.basis_e[(int64_t)i * S + s], base_e);
+    for (int i = 1; i < nba; ++i)
+      base_a = fma(s_beta[warp][CHI_MAX_BASELINE + i], a.basis_a[(int64_t)i * S + s], base_a);
+
+    // ---- forward: one exp(-k d^2) per cloud feeds both datasets ----
+    double om[N], Pn[N], E[N], q[N];
+    double P = 1.0, T = 0.0, xs = 0.0;  // xs = -sum_n tau_a
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      double c0, nk, nAGe, nAGa, f, fTs;
+      lds2(&sc[n][0], c0, nk);
+      lds2(&sc[n][2], nAGe, nAGa);
+      lds2(&sc[n][4], f, fTs);
+      const double d = v - c0, d2 = d * d;
+      E[n] = chi_exp<false>(nk * d2, ek);
+      double x = nAGe * E[n];
+      xs = fma(nAGa, E[n], xs);
+      if (PV) {
+        double Ts_, h, nALe, nALa;
+        lds2(&sc[n][6], Ts_, h);
+        lds2(&sc[n][8], nALe, nALa);
+        q[n] = chi_rcp(d2 + h);
+        x = fma(nALe, q[n], x);
+        xs = fma(nALa, q[n], xs);
+      }
+      om[n] = 1.0 - chi_exp<true>(x, ek);
+      Pn[n] = P;
+      T = fma(fTs * om[n], P, T);
+      P *= fma(-f, om[n], 1.0);
+    }
+    const double mu_e = (bg * P + T) - bg + base_e;   // physics.py:362-365
+    const double ea = chi_exp<true>(xs, ek);
+    const double mu_a = (1.0 - ea) + base_a;          // absorption_model.py:91
+    double mbe, mba;
+    if (a.vjp) {
+      mbe = Ge ? Ge[s] : 0.0;
+      mba = Ga ? Ga[s] : 0.0;
+    } else {
+      const double re = Ye[s] - mu_e, ra = Ya[s] - mu_a;
+      mbe = We[s] * re;
+      mba = Wa[s] * ra;
+      lp = fma(-0.5 * mbe, re, lp);
+      lp = fma(-0.5 * mba, ra, lp);
+    }
+    gbe0 = fma(mbe, pe0, gbe0);
+    gba0 = fma(mba, pa0, gba0);
+    for (int i = 1; i < nbe; ++i)
+      s_gb[i][threadIdx.x] = fma(mbe, a.basis_e[(int64_t)i * S + s], s_gb[i][threadIdx.x]);
+    for (int i = 1; i < nba; ++i)
+      s_gb[CHI_MAX_BASELINE + i][threadIdx.x] =
+          fma(mba, a.basis_a[(int64_t)i * S + s], s_gb[CHI_MAX_BASELINE + i][threadIdx.x]);
+    const double ga = mba * ea;  // absorption taubar (same for every cloud)
+
+    // ---- reverse through the transfer; combined moments for the shared profile ----
+    double Q = bg;
+#pragma unroll
+    for (int n = N - 1; n >= 0; --n) {
+      double c0, nk, nAGe, nAGa, f, fTs, Ts, h;
+      lds2(&sc[n][0], c0, nk);
+      lds2(&sc[n][2], nAGe, nAGa);
+      lds2(&sc[n][4], f, fTs);
+      lds2(&sc[n][6], Ts, h);
+      const double Sn = Ts - Q;
+      const double x = om[n] * Pn[n];
+      const double mx = mbe * x;
+      acc[n][4] += mx;                                // aTs
+      acc[n][5] = fma(mx, Sn, acc[n][5]);             // af
+      const double ge = (mbe * Sn) * (Pn[n] - x);     // emission taubar / f
+      const double d = v - c0;
+      acc[n][0] = fma(ge, E[n], acc[n][0]);           // M0e
+      acc[n][1] = fma(ga, E[n], acc[n][1]);           // M0a
+      // (f AG_e ge + AG_a ga): the constants are stored negated
+      const double gc = -fma(f * nAGe, ge, nAGa * ga);
+      const double t = gc * E[n];
+      const double td = t * d;
+      acc[n][2] += td;                                // M1c
+      acc[n][3] = fma(td, d, acc[n][3]);              // M2c
+      if (PV) {
+        acc[n][6] = fma(ge, q[n], acc[n][6]);         // Q1e
+        acc[n][7] = fma(ga, q[n], acc[n][7]);         // Q1a
+        double nALe, nALa;
+        lds2(&sc[n][8], nALe, nALa);
+        const double gl = -fma(f * nALe, ge, nALa * ga);
+        const double u2 = gl * q[n] * q[n];
+        acc[n][8] += u2;                              // Q2c
+        acc[n][9] = fma(u2, d, acc[n][9]);            // Q2dc
+      }
+      Q = fma(fma(-f, om[n], 1.0), Q, fTs * om[n]);
+    }
+  }
+
+  double* out = a.mom + item * a.mom_stride;
+  lp = warp_sum(lp);
+  gbe0 = warp_sum(gbe0);
+  gba0 = warp_sum(gba0);
+  if (lane == 0) {
+    out[0] = lp;
+    if (nbe > 0) out[1] = gbe0;
+    if (nba > 0) out[1 + nbe] = gba0;
+  }
+  for (int i = 1; i < nbe; ++i) {
+    double g = warp_sum(s_gb[i][threadIdx.x]);
+    if (lane == 0) out[1 + i] = g;
+  }
+  for (int i = 1; i < nba; ++i) {
+    double g = warp_sum(s_gb[CHI_MAX_BASELINE + i][threadIdx.x]);
+    if (lane == 0) out[1 + nbe + i] = g;
+  }
+  double* om_ = out + 1 + nbe + nba;
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      double r = warp_sum(acc[n][j]);
+      if (lane == ((n * NF + j) & 31)) om_[n * NF + j] = r;
+    }
+}
+
+}  // namespace chi

@@ -56,7 +56,7 @@ def draw_free_oracle(spec, B, rng):
 
 
 def make_case(kind, n_clouds, S_e, S_a, B, seed, lorentzian=False, baseline_degree=0, weight=True,
-              half_width=60.0, **spec_kwargs):
+              half_width=60.0, shared_axis=False, **spec_kwargs):
     """A seeded test case: oracle spec, oracle data (truth at one prior draw + noise),
     B prior draws of the free RVs and baseline coefficients."""
     rng = np.random.default_rng(seed)
@@ -72,7 +72,10 @@ def make_case(kind, n_clouds, S_e, S_a, B, seed, lorentzian=False, baseline_degr
     if mr.has_emission(spec):
         axes["emission"] = (np.linspace(-half_width, half_width, S_e), 0.1)
     if mr.has_absorption(spec):
-        axes["absorption"] = (np.linspace(-half_width / 2, half_width / 2, S_a), 0.01)
+        if shared_axis:  # both spectra on one velocity grid: exercises the fused kernel
+            axes["absorption"] = (np.linspace(-half_width, half_width, S_e), 0.01)
+        else:
+            axes["absorption"] = (np.linspace(-half_width / 2, half_width / 2, S_a), 0.01)
     for key in axes:
         baseline[f"baseline_{key}_norm"] = 0.3 * rng.standard_normal(size=(B, baseline_degree + 1))
     # truth: forward model of a moderate, well-behaved draw + noise

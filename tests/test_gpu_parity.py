@@ -60,6 +60,53 @@ def test_cloud_counts(cuda_device, N):
     _check_case("emission_absorption_physical", N, 257, 131, 16, seed=100 + N, lorentzian=(N % 2 == 0))
 
 
+@pytest.mark.parametrize("kind", ["emission_absorption", "emission_absorption_physical"])
+@pytest.mark.parametrize("lorentzian", [False, True])
+@pytest.mark.parametrize("N", [1, 4, 8])
+def test_shared_axis_fused_kernel(cuda_device, kind, lorentzian, N):
+    """Emission and absorption on the same velocity grid take the fused kernel
+    (moments_ea.cuh: one exp(-k d^2) for both datasets, combined moments)."""
+    _check_case(kind, N, 333, 333, 24, seed=300 + N, lorentzian=lorentzian, baseline_degree=2, shared_axis=True)
+
+
+def test_shared_axis_small_batch_and_vjp(cuda_device):
+    """Fused kernel with channel chunking (small batch) and in VJP mode."""
+    import torch
+    from caribou_hi_b200 import Engine
+
+    _check_case("emission_absorption_physical", 5, 1500, 1500, 4, seed=77, lorentzian=True, shared_axis=True,
+                half_width=100.0)
+    rng = np.random.default_rng(8)
+    B, N, S = 6, 3, 200
+    v = np.linspace(-50, 50, S)
+    inp = {"velocity": rng.normal(0, 8, (B, N)), "fwhm2": rng.uniform(5, 200, (B, N)),
+           "fwhm_L": rng.uniform(0.0, 3.0, (B, N)), "tau_total": rng.uniform(0.05, 8, (B, N)),
+           "tspin": rng.uniform(30, 3000, (B, N)), "filling_factor": rng.uniform(0.1, 1.0, (B, N)),
+           "absorption_weight": rng.uniform(0.3, 1.2, (B, N))}
+    data = {"emission": mr.OracleData(v, rng.normal(5, 3, S), 0.3), "absorption": mr.OracleData(v, rng.normal(0.2, 0.1, S), 0.02)}
+    spec = mr.make_spec("emission_absorption", N)
+    eng = Engine("physics", N, lorentzian=True)
+    eng.set_spectra(emission=dict(spectral=v, brightness=data["emission"].brightness, noise=0.3),
+                    absorption=dict(spectral=v, brightness=data["absorption"].brightness, noise=0.02))
+    theta = eng.pack(inp)
+    for ge, ga in ((rng.standard_normal((B, S)), rng.standard_normal((B, S))), (None, rng.standard_normal((B, S))),
+                   (rng.standard_normal((B, S)), None)):
+        it = {k: torch.tensor(x, requires_grad=True) for k, x in inp.items()}
+        mu = mr.predict_from_inputs(spec, data, it)
+        tot = 0.0
+        if ge is not None:
+            tot = tot + (mu["emission"] * torch.tensor(ge)).sum()
+        if ga is not None:
+            tot = tot + (mu["absorption"] * torch.tensor(ga)).sum()
+        tot.backward()
+        vg, _, _ = eng.spectra_vjp(theta, ge, ga)
+        got = eng.unpack_grad(vg)
+        names = sorted(got)
+        ref = [it[k].grad.numpy() if it[k].grad is not None else np.zeros((B, N)) for k in names]
+        assert_close(np.concatenate([got[k] for k in names], axis=1), np.concatenate(ref, axis=1), what="fused vjp")
+    eng.close()
+
+
 def test_emission_absorption_fixed_weight(cuda_device):
     """prior_sigma_log10_NHI=None: absorption_weight is the constant 1
     (emission_absorption_model.py:46-47)."""
