@@ -47,52 +47,60 @@ def workload_name(draws):
 # clocks sampler (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML (nvidia_ml_py) from a thread while the
+    timed region runs; falls back to one `nvidia-smi` query when NVML is unavailable."""
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.perf_counter(), clk, reasons))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        mhz, mx, reasons = [], None, set()
-        for t, line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                clk, cmax = float(parts[0]), float(parts[1])
-            except ValueError:
-                continue
-            mx = cmax
-            if t0 <= t <= t1:
-                mhz.append(clk)
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                     parts[2:6]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx,
-                "samples": len(mhz), "reasons": sorted(reasons)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        inside = [(c, r) for (t, c, r) in self.samples if t0 <= t <= t1]
+        reasons = sorted({k for (_, r) in inside for k, bit in names.items() if r & bit})
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": mx,
+                "samples": len(inside), "reasons": reasons}
 
 
 # --------------------------------------------------------------------------------------
@@ -344,10 +352,16 @@ def run_b200(args):
 
     if rank == 0:
         peak = eng.microbench_fp64()
+        # configs[1] samples both spectra on one velocity grid, so the library takes its fused
+        # emission+absorption kernel: one launch covers B*N*S channel pairs, 32 + 12 canonical flops each
+        fused = float(stage[2]) < 0.05 * float(stage[1])
         t_em = float(stage[1]) * 1e-3
-        flops_em = draws * N * S_E * FLOPS_EM
+        flops_unit = FLOPS_EM + FLOPS_ABS if fused else FLOPS_EM
+        kernel_name = "k_moments_ea<4,false> (fused emission+absorption)" if fused else "k_moments_em<4,false>"
+        flops_em = draws * N * S_E * flops_unit
         achieved = flops_em / t_em / 1e12
-        bytes_em = draws * (N * 12 * 8 + (2 + 5 * N) * 8)  # cc read + moment record written per draw
+        rec = (3 + 6 * N) if fused else (2 + 5 * N)
+        bytes_em = draws * (N * 12 * 8 + rec * 8)  # cc read + moment record written per draw
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -369,11 +383,12 @@ def run_b200(args):
             "gpu_launches": launches,
             "stage_ms": {"cloud_map": float(stage[0]), "moments_emission": float(stage[1]),
                          "moments_absorption": float(stage[2]), "epilogue": float(stage[3])},
-            "roofline": {"kernel": "k_moments_em<4,false>", "bound": "fp64", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": kernel_name, "bound": "fp64", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "own DFMA microbenchmark on this GPU (chi_microbench_fp64); "
                                         "MEASURED_PEAKS.json has no CUDA-core FP64 figure",
-                         "flops_per_unit": FLOPS_EM, "units_per_launch": draws * N * S_E,
+                         "flops_per_unit": flops_unit, "units_per_launch": draws * N * S_E,
+                         "unit_of_launch": "draw*cloud*channel-pair" if fused else "draw*cloud*channel",
                          "traffic": None,
                          "hbm": {"achieved": bytes_em / t_em / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_em / t_em / 1e9 / hbm_peak,
