@@ -286,10 +286,12 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   const int K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
   if (B * N * K <= (int64_t)h->n_sm * 1024) {
     unsigned grid = (unsigned)((B * N * K + 127) / 128);
-    MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true><<<grid, 128, 0, L.st>>>(h->map, ea)));
+    if (model) { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, true><<<grid, 128, 0, L.st>>>(h->map, ea))); }
+    else { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, false><<<grid, 128, 0, L.st>>>(h->map, ea))); }
   } else {
     unsigned grid = (unsigned)((B * N + 127) / 128);
-    MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false><<<grid, 128, 0, L.st>>>(h->map, ea)));
+    if (model) { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, true><<<grid, 128, 0, L.st>>>(h->map, ea))); }
+    else { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, false><<<grid, 128, 0, L.st>>>(h->map, ea))); }
   }
   if (model) {
     k_add_prior<<<(unsigned)((B + 127) / 128), 128, 0, L.st>>>(B, N, L.prior.d(), logp);

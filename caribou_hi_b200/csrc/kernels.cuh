@@ -98,7 +98,8 @@ struct EpiArgs {
 // used for large batches).  SPLIT = true: one thread per (draw, cloud, direction) carries a
 // single tangent -- ~2x the arithmetic but a ~5x shorter dependent chain, which is what a
 // small batch (a few dozen chains) is bound by.
-template <int MODEL, bool SPLIT>
+// PRIOR: unconstrained-space model logp (a.u set): prior densities, Jacobians, transform chain rule.
+template <int MODEL, bool SPLIT, bool PRIOR>
 __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   constexpr int K = (MODEL == CHI_MODEL_PHYSICS) ? 7 : CHI_NSLOT;
   constexpr int KD = SPLIT ? 1 : K;   // tangent directions per thread
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
           a.gcoeff_a[b * a.nb_a + i] = g;
         }
     }
-    if (a.u) {
+    if (PRIOR) {
       // Normal(0, sigma_i) priors of the baseline coefficients (bayes_spec add_baseline_priors)
       for (int i = 0; i < a.nb_e; ++i) {
         const double c = a.coeff_e ? a.coeff_e[b * a.nb_e + i] : 0.0, s = a.bsig_e[i];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
     }
     if (a.logp) a.logp[b] = lp + (a.lconst ? a.lconst[a.sl ? a.sl[b] : 0] : 0.0);
   }
-  if (!a.grad && !a.u) return;
+  if (!a.grad && !PRIOR) return;
 
   // --- Jacobian of the per-cloud map by forward-mode duals ---
   typedef Dual<KD> D;
@@ -201,18 +202,22 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   double cbar = 0.0;
   if (a.fused) {
     // shared axis: k and h are common to the two datasets, their adjoints arrive combined
-    ProfConst<D> pe = profile_consts<D>(ph.fwhm2, ph.fwhm_L, ph.tau_total, cfg.wch2_e, cfg.lorentzian != 0);
-    ProfConst<D> pa = profile_consts<D>(ph.fwhm2, ph.fwhm_L, D(ph.wt * ph.tau_total), cfg.wch2_a,
-                                        cfg.lorentzian != 0);
     const double f = ph.ff.v;
-    cbar = 2.0 * pe.k.v * mf[2] + 2.0 * mf[9];
-    addc(-mf[3], pe.k);
-    addc(f * mf[0], pe.AG);
-    addc(mf[1], pa.AG);
-    if (a.pv) {
-      addc(f * mf[6], pe.AL);
-      addc(mf[7], pa.AL);
-      addc(-mf[8], pe.h);
+    {
+      ProfConst<D> pe = profile_consts<D>(ph.fwhm2, ph.fwhm_L, ph.tau_total, cfg.wch2_e, cfg.lorentzian != 0);
+      cbar = 2.0 * pe.k.v * mf[2] + 2.0 * mf[9];
+      addc(-mf[3], pe.k);
+      addc(f * mf[0], pe.AG);
+      if (a.pv) {
+        addc(f * mf[6], pe.AL);
+        addc(-mf[8], pe.h);
+      }
+    }
+    {
+      ProfConst<D> pa = profile_consts<D>(ph.fwhm2, ph.fwhm_L, D(ph.wt * ph.tau_total), cfg.wch2_a,
+                                          cfg.lorentzian != 0);
+      addc(mf[1], pa.AG);
+      if (a.pv) addc(mf[7], pa.AL);
     }
     addc(f * mf[4], ph.tspin);
     addc(mf[5], ph.ff);
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   }
   addc(cbar, ph.velocity);
 
-  if (a.u) {
+  if (PRIOR) {
     // priors of this cloud's free RVs at their constrained values (Dual: the coupled Normal's
     // mean depends on tkin / fwhm2_thermal), then the chain rule through the transforms
     const double* up = a.u + (b * CHI_NSLOT) * a.N + n;

@@ -1,19 +1,9 @@
 // k_moments_abs<N, PV> instantiations (N = 1..8, Gaussian / pseudo-Voigt).
-// -DCHI_WINDOWED additionally builds the experimental windowed family (moments_win.cuh).
 #include "launch.cuh"
-#ifdef CHI_WINDOWED
-#include "moments_win.cuh"
-#endif
 
 namespace chi {
 template <int N, bool PV>
 static void run(const ChanArgs& a, cudaStream_t st, int family) {
-#ifdef CHI_WINDOWED
-  if (family == 2) {
-    k_moments_abs2<N, PV, 2><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
-    return;
-  }
-#endif
   k_moments_abs<N, PV><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
 }
 

@@ -240,7 +240,8 @@ constexpr int ab_min_blocks(int N, bool pv) {
 // k_moments_em
 //   physics.py:294-309 (profile), emission_model.py:148 (tau), physics.py:345-365
 //   (radiative transfer), pm.Normal logp, and the adjoint of all of it.
-//   shared per cloud: c, -k, -AG, -AL, h, f, Ts, f*Ts
+//   shared per cloud, fetched in pairs (the Gaussian case touches the first three):
+//   [c, -k] [-AG, f] [f*Ts, Ts] [-AL, h]
 // ---------------------------------------------------------------------------
 template <int N, bool PV>
 __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(ChanArgs a) {
@@ -262,8 +263,8 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
     const double f = p[CC_F], ts = p[CC_TS];
     double* d = s_c[warp][lane];
-    d[0] = p[CC_C]; d[1] = -p[CC_KE]; d[2] = -p[CC_AGE]; d[3] = -p[CC_ALE]; d[4] = p[CC_HE];
-    d[5] = f; d[6] = ts; d[7] = f * ts;
+    d[0] = p[CC_C]; d[1] = -p[CC_KE]; d[2] = -p[CC_AGE]; d[3] = f; d[4] = f * ts; d[5] = ts;
+    d[6] = -p[CC_ALE]; d[7] = p[CC_HE];
   }
   if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
   for (int i = CHI_BASE_REG; i < nb; ++i) s_gb[i - CHI_BASE_REG][threadIdx.x] = 0.0;
@@ -301,15 +302,16 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     double P = 1.0, T = 0.0;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
-      double c0, nk, nAG, nAL, h, f, Ts, fTs;
+      double c0, nk, nAG, f, fTs, Ts;
       lds2(&sc[n][0], c0, nk);
-      lds2(&sc[n][2], nAG, nAL);
-      lds2(&sc[n][4], h, f);
-      lds2(&sc[n][6], Ts, fTs);
+      lds2(&sc[n][2], nAG, f);
+      lds2(&sc[n][4], fTs, Ts);
       const double d = v - c0, d2 = d * d;
       E[n] = chi_exp<false>(nk * d2, ek);
       double x = nAG * E[n];                    // -tau
       if (PV) {
+        double nAL, h;
+        lds2(&sc[n][6], nAL, h);
         q[n] = chi_rcp(d2 + h);
         x = fma(nAL, q[n], x);
       }
@@ -337,10 +339,10 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     double Q = bg;
 #pragma unroll
     for (int n = N - 1; n >= 0; --n) {
-      double c0, nk, h, f, Ts, fTs;
+      double c0, nk, nAG, f, fTs, Ts;
       lds2(&sc[n][0], c0, nk);
-      lds2(&sc[n][4], h, f);
-      lds2(&sc[n][6], Ts, fTs);
+      lds2(&sc[n][2], nAG, f);
+      lds2(&sc[n][4], fTs, Ts);
       const double Sn = Ts - Q;                 // Ts_n - Q_n
       const double x = om[n] * Pn[n];
       const double mx = mubar * x;
