@@ -187,7 +187,6 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   const double* u = nullptr;
   if (model) {
     CK(L.xcon.ensure((size_t)B * CHI_NSLOT * N * sizeof(double)));
-    CK(L.prior.ensure((size_t)B * N * sizeof(double)));
     u = theta;
   }
   int rc = launch_cloud_map(h, L, B, theta, model ? L.xcon.d() : nullptr);
@@ -202,7 +201,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   ea.theta = theta; ea.sl = sl; ea.logp = logp; ea.grad = grad; ea.gcoeff_e = gce; ea.gcoeff_a = gca;
   ea.lconst = vjp ? nullptr : h->lconst.d();
   if (model) {
-    ea.u = u; ea.prior_part = L.prior.d(); ea.coeff_e = ce; ea.coeff_a = ca;
+    ea.u = u; ea.coeff_e = ce; ea.coeff_a = ca;
     memcpy(ea.bsig_e, h->bsig_e, sizeof(ea.bsig_e));
     memcpy(ea.bsig_a, h->bsig_a, sizeof(ea.bsig_a));
   }
@@ -286,17 +285,22 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   const int K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
   if (B * N * K <= (int64_t)h->n_sm * 1024) {
     unsigned grid = (unsigned)((B * N * K + 127) / 128);
-    if (model) { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, true><<<grid, 128, 0, L.st>>>(h->map, ea))); }
+    if (model) {  // whole draws per block
+      const int per = N * K, bd = (128 / per) * per;
+      const unsigned gp = (unsigned)((B + bd / per - 1) / (bd / per));
+      MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, true><<<gp, bd, 0, L.st>>>(h->map, ea)));
+    }
     else { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, false><<<grid, 128, 0, L.st>>>(h->map, ea))); }
   } else {
     unsigned grid = (unsigned)((B * N + 127) / 128);
-    if (model) { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, true><<<grid, 128, 0, L.st>>>(h->map, ea))); }
+    if (model) {  // whole draws per block
+      const int bd = (128 / N) * N;
+      const unsigned gp = (unsigned)((B + bd / N - 1) / (bd / N));
+      MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, true><<<gp, bd, 0, L.st>>>(h->map, ea)));
+    }
     else { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, false><<<grid, 128, 0, L.st>>>(h->map, ea))); }
   }
-  if (model) {
-    k_add_prior<<<(unsigned)((B + 127) / 128), 128, 0, L.st>>>(B, N, L.prior.d(), logp);
-    h->launches++;
-  }
+
   h->launches++;
   CK(cudaGetLastError());
   if (!h->capturing) CK(cudaEventRecord(evs[4], L.st));
@@ -1238,20 +1242,21 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   // one leapfrog step (half kick + drift, batched logp+grad, half kick + tree bookkeeping) as a
   // CUDA graph: ~8 dependent launches per step would otherwise be pure launch latency for a few
   // dozen chains
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
-  h->capturing = true;
-  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  k_nuts_leap_a<<<grid, 64, 0, st>>>(s);
-  rc = evaluate();
-  k_nuts_leap_b<<<grid, 64, 0, st>>>(s);
-  cudaError_t cap_err = cudaStreamEndCapture(st, &graph);
-  h->capturing = false;
-  if (rc) return rc;
-  CK(cap_err);
-  CK(cudaGraphInstantiate(&gexec, graph, 0));
-  size_t n_nodes = 0;
-  CK(cudaGraphGetNodes(graph, nullptr, &n_nodes));
+  cudaGraph_t graph[2] = {nullptr, nullptr};
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  size_t n_nodes[2] = {0, 0};
+  for (int g = 0; g < 2; ++g) {  // g = 0: first leaf of a doubling (no pending half step), 1: the others
+    h->capturing = true;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    k_nuts_leap<<<grid, 64, 0, st>>>(s, g, 1);
+    rc = evaluate();
+    cudaError_t cap_err = cudaStreamEndCapture(st, &graph[g]);
+    h->capturing = false;
+    if (rc) return rc;
+    CK(cap_err);
+    CK(cudaGraphInstantiate(&gexec[g], graph[g], 0));
+    CK(cudaGraphGetNodes(graph[g], nullptr, &n_nodes[g]));
+  }
   int* h_flags = nullptr;
   CK(cudaMallocHost(&h_flags, 2 * sizeof(int)));
   const int total = n_tune + cfg->n_draws;
@@ -1264,16 +1269,17 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
       h->launches++;
       const int leaves = 1 << depth;
       for (int leaf = 0; leaf < leaves; ++leaf) {
-        CK(cudaGraphLaunch(gexec, st));
-        h->launches += (int64_t)n_nodes;
+        CK(cudaGraphLaunch(gexec[leaf ? 1 : 0], st));
+        h->launches += (int64_t)n_nodes[leaf ? 1 : 0];
         if (depth >= 4 && (leaf & 7) == 7 && leaf + 1 < leaves) {  // every chain's sub-tree stopped early?
           CK(cudaMemcpyAsync(h_flags + 1, s.n_stopped, sizeof(int), cudaMemcpyDeviceToHost, st));
           CK(cudaStreamSynchronize(st));
           if (h_flags[1] >= B) break;
         }
       }
+      k_nuts_leap<<<grid, 64, 0, st>>>(s, 1, 0);  // second half of the last leaf
       k_nuts_end_subtree<<<grid, 64, 0, st>>>(s, max_depth);
-      h->launches++;
+      h->launches += 2;
       CK(cudaMemcpyAsync(h_flags, s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       if (h_flags[0] <= 0) break;
@@ -1293,8 +1299,10 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     CK(cudaGetLastError());
   }
   cudaFreeHost(h_flags);
-  cudaGraphExecDestroy(gexec);
-  cudaGraphDestroy(graph);
+  for (int g = 0; g < 2; ++g) {
+    cudaGraphExecDestroy(gexec[g]);
+    cudaGraphDestroy(graph[g]);
+  }
   // draws back to the host in the layout of the API blocks
   CK(cudaStreamSynchronize(st));
   std::vector<double> tmp((size_t)n_keep * B * D);

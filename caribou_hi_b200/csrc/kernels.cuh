@@ -88,7 +88,6 @@ struct EpiArgs {
   double* __restrict__ gcoeff_a;
   // unconstrained-space model logp (priors + Jacobians), null/0 otherwise
   const double* __restrict__ u;        // [B][NSLOT][N] unconstrained values (theta = constrained)
-  double* __restrict__ prior_part;     // [B][N] per-cloud prior + Jacobian, summed by k_add_prior
   const double* __restrict__ coeff_e;  // [B][nb_e] baseline coefficients (their Normal priors)
   const double* __restrict__ coeff_a;
   double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];  // prior widths of the coefficients
@@ -104,13 +103,28 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   constexpr int K = (MODEL == CHI_MODEL_PHYSICS) ? 7 : CHI_NSLOT;
   constexpr int KD = SPLIT ? 1 : K;   // tangent directions per thread
   constexpr int NJ = K / KD;          // threads per (draw, cloud)
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.B * a.N * NJ) return;
-  const int j0 = SPLIT ? (int)(t % NJ) : 0;  // first direction of this thread
-  const int64_t bn = SPLIT ? t / NJ : t;
-  const int64_t b = bn / a.N;
-  const int n = (int)(bn - b * a.N);
+  int64_t b;
+  int n, j0;  // cloud, first tangent direction of this thread
+  bool valid = true;
+  if (PRIOR) {
+    // whole draws per block (blockDim is a multiple of N * NJ): the per-cloud prior terms are
+    // summed through shared memory in cloud order, so every thread must reach the barrier
+    const int per = a.N * NJ, dl = threadIdx.x / per, r = threadIdx.x - dl * per;
+    b = (int64_t)blockIdx.x * (blockDim.x / per) + dl;
+    n = r / NJ;
+    j0 = r - n * NJ;
+    valid = b < a.B;
+    if (!valid) { b = 0; n = 0; j0 = 0; }
+  } else {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.B * a.N * NJ) return;
+    j0 = SPLIT ? (int)(t % NJ) : 0;
+    const int64_t bn = SPLIT ? t / NJ : t;
+    b = bn / a.N;
+    n = (int)(bn - b * a.N);
+  }
   const int NE = a.pv ? 8 : 5, NA = a.pv ? 6 : 3;
+  double lp_draw = 0.0;  // likelihood (+ baseline priors) of the draw, held by its first thread
 
   // --- sums over channel chunks (fixed order: deterministic) ---
   double me[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ma[6] = {0, 0, 0, 0, 0, 0};
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
     for (int c = 0; c < a.chunks_a; ++c, p += a.stride_a)
       for (int j = 0; j < NA; ++j) ma[j] += p[j];
   }
-  if (n == 0 && j0 == 0) {
+  if (n == 0 && j0 == 0 && valid) {
     // logp and baseline-coefficient gradients: one thread per draw
     double lp = 0.0;
     if (a.fused) {
@@ -175,7 +189,8 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
         if (a.gcoeff_a) a.gcoeff_a[b * a.nb_a + i] -= c / (s * s);
       }
     }
-    if (a.logp) a.logp[b] = lp + (a.lconst ? a.lconst[a.sl ? a.sl[b] : 0] : 0.0);
+    lp_draw = lp + (a.lconst ? a.lconst[a.sl ? a.sl[b] : 0] : 0.0);
+    if (!PRIOR && a.logp) a.logp[b] = lp_draw;
   }
   if (!a.grad && !PRIOR) return;
 
@@ -262,7 +277,14 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
       lp = lp + w * slot_density<D>(cfg, dist, th[s], thermal);
       logj += w * slot_backward(dist, up[(int64_t)s * a.N]).logj;
     }
-    if (j0 == 0) a.prior_part[b * a.N + n] = lp.v + logj;
+    __shared__ double s_prior[128];
+    s_prior[threadIdx.x] = (valid && j0 == 0) ? lp.v + logj : 0.0;
+    __syncthreads();
+    if (valid && n == 0 && j0 == 0 && a.logp) {
+      double tot = lp_draw;
+      for (int i = 0; i < a.N; ++i) tot += s_prior[threadIdx.x + i * NJ];
+      a.logp[b] = tot;
+    }
 #pragma unroll
     for (int i = 0; i < KD; ++i) {
       const int s = j0 + i;
@@ -272,22 +294,13 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
       g[i] = (g[i] + lp.d[i]) * tr.dxdu + w * tr.dlogj;
     }
   }
-  if (!a.grad) return;
+  if (!a.grad || !valid) return;
 
   double* go = a.grad + (b * CHI_NSLOT) * a.N + n;
 #pragma unroll
   for (int i = 0; i < KD; ++i) go[(int64_t)(j0 + i) * a.N] = g[i];
   if (j0 == 0)
     for (int s = K; s < CHI_NSLOT; ++s) go[(int64_t)s * a.N] = 0.0;  // slots the model kind does not use
-}
-
-// adds the per-cloud prior + Jacobian terms to logp in cloud order (deterministic)
-__global__ void k_add_prior(int64_t B, int N, const double* __restrict__ prior_part, double* __restrict__ logp) {
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  double s = 0.0;
-  for (int n = 0; n < N; ++n) s += prior_part[b * N + n];
-  logp[b] += s;
 }
 
 // unconstrained <-> constrained values of the free RVs (direction = +1: u -> x, -1: x -> u)

@@ -183,9 +183,7 @@ __global__ void k_nuts_begin_subtree(NutsState s) {
 }
 
 // ---- leapfrog, first half: half kick + drift; the new position becomes the evaluation point ---
-__global__ void k_nuts_leap_a(NutsState s) {
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= s.B || s.sub_stop[b]) return;
+__device__ __forceinline__ void nuts_leap_a(const NutsState& s, int64_t b) {
   const int64_t o = b * s.D;
   const double h = s.dir[b] * s.eps[b];
   double x[CHI_NSLOT * CHI_MAX_CLOUDS + 2 * CHI_MAX_BASELINE];
@@ -202,9 +200,7 @@ __global__ void k_nuts_leap_a(NutsState s) {
 
 // ---- leapfrog, second half + sub-tree bookkeeping of the chain's next leaf -------------------
 // (the leaf index lives on the device so that one captured CUDA graph serves every leapfrog step)
-__global__ void k_nuts_leap_b(NutsState s) {
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= s.B || s.sub_stop[b]) return;
+__device__ __forceinline__ void nuts_leap_b(const NutsState& s, int64_t b) {
   const int leaf = s.leaf[b]++;
   const int64_t o = b * s.D;
   const double h = s.dir[b] * s.eps[b];
@@ -268,6 +264,16 @@ __global__ void k_nuts_leap_b(NutsState s) {
     s.sub_stop[b] = turning ? 2 : 3;  // 2: sub-tree turned, 3: diverged
     atomicAdd(s.n_stopped, 1);
   }
+}
+
+// One kernel per leapfrog boundary: finish the leaf whose logp/gradient just arrived (do_b) and,
+// unless the chain's sub-tree stopped, start the next one (do_a).  The first launch of a
+// doubling has do_b = 0, the last one do_a = 0.
+__global__ void k_nuts_leap(NutsState s, int do_b, int do_a) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B || s.sub_stop[b]) return;
+  if (do_b) nuts_leap_b(s, b);
+  if (do_a && !s.sub_stop[b]) nuts_leap_a(s, b);
 }
 
 // ---- end of a doubling: merge the sub-tree into the tree ------------------------------------
