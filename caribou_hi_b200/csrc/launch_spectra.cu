@@ -12,17 +12,17 @@ template <int N, bool PV, bool EMISSION>
 __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
   __shared__ __align__(16) double s_c[N][8];
   __shared__ double s_beta[CHI_MAX_BASELINE];
-  __shared__ double s_T[64];
+  __shared__ double s_T[CHI_EXP_TABLE];
   const int64_t b = blockIdx.x;
   if (threadIdx.x < N) {
     const double* p = a.cc + (b * N + threadIdx.x) * CHI_CC_STRIDE;
     double* d = s_c[threadIdx.x];
     d[0] = p[CC_C];
     if (EMISSION) {
-      d[1] = -p[CC_KE]; d[2] = -p[CC_AGE]; d[3] = -p[CC_ALE]; d[4] = p[CC_HE];
+      d[1] = -CHI_LOG2E * p[CC_KE]; d[2] = -CHI_LOG2E * p[CC_AGE]; d[3] = -CHI_LOG2E * p[CC_ALE]; d[4] = p[CC_HE];
       d[5] = p[CC_F]; d[6] = p[CC_TS]; d[7] = p[CC_F] * p[CC_TS];
     } else {
-      d[1] = -p[CC_KA]; d[2] = -p[CC_AGA]; d[3] = -p[CC_ALA]; d[4] = p[CC_HA];
+      d[1] = -CHI_LOG2E * p[CC_KA]; d[2] = -CHI_LOG2E * p[CC_AGA]; d[3] = -CHI_LOG2E * p[CC_ALA]; d[4] = p[CC_HA];
       d[5] = d[6] = d[7] = 0.0;
     }
   }
@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
       lds2(&s_c[n][0], c0, nk);
       lds2(&s_c[n][2], nAG, nAL);
       const double d = v - c0, d2 = d * d;
-      E[n] = chi_exp<false>(nk * d2, ek);
-      x[n] = nAG * E[n];  // -tau
+      E[n] = chi_exp2<false>(nk * d2, ek);
+      x[n] = nAG * E[n];  // -tau log2(e)
       if (PV) x[n] = fma(nAL, chi_rcp(d2 + s_c[n][4]), x[n]);
     }
     double r;
@@ -51,16 +51,16 @@ __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
       double P = 1.0, T = 0.0;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        const double om = 1.0 - chi_exp<true>(x[n], ek);
-        T = fma(s_c[n][7] * om, P, T);
-        P *= fma(-s_c[n][5], om, 1.0);
+        const double u = (1.0 - chi_exp2<true>(x[n], ek)) * P;
+        T = fma(s_c[n][7], u, T);
+        P = fma(-s_c[n][5], u, P);
       }
       r = (a.bg * P + T) - a.bg + base;
     } else {
       double xs = 0.0;
 #pragma unroll
       for (int n = 0; n < N; ++n) xs += x[n];
-      r = (1.0 - chi_exp<true>(xs, ek)) + base;
+      r = (1.0 - chi_exp2<true>(xs, ek)) + base;
     }
     out[s] = r;
   }

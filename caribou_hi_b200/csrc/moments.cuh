@@ -82,86 +82,79 @@ __device__ __forceinline__ double chi_exp(double x, const ExpK& c) {
 }
 __device__ __forceinline__ double chi_exp(double x) { return chi_exp<true>(x, load_expk()); }
 
-// Table-driven variant used by the hot kernels: exp(x) = 2^m * T[j] * exp(r) with
-// n = rint(x * 64/ln2) = 64 m + j, |r| <= ln2/128, T[j] = 2^(j/64) in shared memory and
-// exp(r) - 1 = r + r^2 g(r), g of degree 3 (fit error 5e-18).  10 FP64-pipe instructions and a
-// dependent chain of 9 instead of 16 and 15: the pipe is the bound of these kernels and the
-// chain length sets how much parallelism is needed to fill it.  Result within ~1 ulp.
-__constant__ double c_expt[8] = {
-    92.33248261689366,        // 0  64/ln2
-    6755399441055744.0,       // 1  1.5 * 2^52
-    -0.010830424667801708,    // 2  -(ln2/64) hi (29 significant bits: n * hi is exact)
-    -2.8447437476627285e-11,  // 3  -(ln2/64) lo
-    0.008333339386755335,     // 4  g3
-    0.041666709040625166,     // 5  g2
-    0.1666666666666436,       // 6  g1
-    0.4999999999998384};      // 7  g0
-__constant__ double c_exp_table[64] = {
-    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
-    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
-    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
-    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
-    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
-    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
-    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
-    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
-    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
-    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
-    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
-    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
-    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
-    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
-    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
-    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+// Table-driven base-2 variant used by the hot kernels.  The argument is y = x log2(e): the
+// per-cloud constants (-k, -A_G, -A_L) are pre-multiplied by log2(e) when they are staged in
+// shared memory, so the conversion costs nothing per channel.
+//   t = y + 1.5*2^42 rounds y to a multiple of 2^-10: lo32(t) = n = 1024 m + j,
+//   r = y - n/1024 (exact), |r| <= 2^-11,
+//   2^y = 2^m * T[j] * (1 + r q(r)),  q a quadratic fitted to (2^r - 1)/r (fit error 9.5e-17),
+//   T[j] = 2^(j/1024) in shared memory (8 KB per block, filled from g_exp2_table).
+// 7 FP64-pipe instructions and a dependent chain of 6; result within ~1 ulp.
+//   * y < -1022 returns a value below 2^-1042 (hi word zeroed; the low word is left alone, one
+//     select instead of two), i.e. zero for every use on this path;
+//   * OVERFLOW: y >= 1024 and +inf give +inf; NaNs propagate through r.
+__device__ const double g_exp2_table[1024] = {
+#include "exp2_table.inc"
+};
+__constant__ double c_expt[4] = {
+    6597069766656.0,        // 0  1.5 * 2^42
+    0x1.62e42fefa39efp-1,   // 1  q0 = ln2
+    0x1.ebfbe039d53f1p-3,   // 2  q1
+    0x1.c6b08da6e74bcp-5};  // 3  q2
+#define CHI_LOG2E 1.4426950408889634074
+#define CHI_LN2 0.69314718055994530942
+#define CHI_EXP_TABLE 1024
 
 struct ExpT {
-  double k[8];
-  const double* T;  // shared-memory copy of c_exp_table
+  double k[4];
+  unsigned T;  // shared-memory address of the table
 };
 __device__ __forceinline__ ExpT load_expt(const double* shared_table) {
   ExpT e;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) e.k[i] = c_expt[i];
-  e.T = shared_table;
+  for (int i = 0; i < 4; ++i) e.k[i] = c_expt[i];
+  e.T = (unsigned)__cvta_generic_to_shared(shared_table);
   return e;
 }
 // every thread of the block must call this before any early exit (block barrier inside)
 __device__ __forceinline__ void fill_exp_table(double* shared_table) {
-  if (threadIdx.x < 64) shared_table[threadIdx.x] = c_exp_table[threadIdx.x];
+  for (int i = threadIdx.x; i < CHI_EXP_TABLE; i += blockDim.x) shared_table[i] = g_exp2_table[i];
   __syncthreads();
 }
 
+// 2^y
 template <bool OVERFLOW = true>
-__device__ __forceinline__ double chi_exp(double x, const ExpT& c) {
-  const int hi = __double2hiint(x);
-  const double t = fma(x, c.k[0], c.k[1]);
-  const double nf = t - c.k[1];
-  double r = fma(nf, c.k[2], x);
-  r = fma(nf, c.k[3], r);
+__device__ __forceinline__ double chi_exp2(double y, const ExpT& c) {
+  const int hi = __double2hiint(y);
+  const double t = y + c.k[0];
+  const double nf = t - c.k[0];
+  const double r = y - nf;
   const int n = __double2loint(t);
-  const double Tj = c.T[n & 63];
-  double q = fma(c.k[4], r, c.k[5]);
-  q = fma(q, r, c.k[6]);
-  q = fma(q, r, c.k[7]);
-  const double e = fma(r * r, q, r);  // exp(r) - 1
-  const double p = fma(Tj, e, Tj);
-  const double res = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
-  const bool underflow = (unsigned)(hi - 0xC0862001) <= (0xFFF00000u - 0xC0862001u);
-  double out = underflow ? 0.0 : res;
+  unsigned addr;
+  asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(n & (CHI_EXP_TABLE - 1)), "r"(c.T));
+  double Tj;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(Tj) : "r"(addr));
+  double q = fma(c.k[3], r, c.k[2]);
+  q = fma(q, r, c.k[1]);
+  const double Tr = Tj * r;
+  const double p = fma(Tr, q, Tj);
+  int ph;
+  asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(ph) : "r"(n >> 10), "r"(__double2hiint(p)));
+  // -1022 = 0xC08FF00000000000; negative doubles order like unsigned ints on the high word; the
+  // range stops at -inf (0xFFF00000) so that NaNs still propagate through r and p
+  const bool underflow = (unsigned)(hi - 0xC08FF001) <= (0xFFF00000u - 0xC08FF001u);
+  ph = underflow ? 0 : ph;
+  double out = __hiloint2double(ph, __double2loint(p));
   if (OVERFLOW) {
-    const bool overflow = (unsigned)(hi - 0x40862801) <= (0x7FF00000u - 0x40862801u);
+    // y >= 1024 (0x4090000000000000) up to and including +inf gives +inf
+    const bool overflow = (unsigned)(hi - 0x40900000) <= (0x7FF00000u - 0x40900000u);
     out = overflow ? __hiloint2double(0x7FF00000, 0) : out;
   }
   return out;
 }
 
-#ifndef CHI_EXP_POLY
-typedef ExpT ExpCtx;   // hot kernels: table-driven exp
+typedef ExpT ExpCtx;
 #define CHI_LOAD_EXPCTX(tab) load_expt(tab)
-#else
-typedef ExpK ExpCtx;   // -DCHI_EXP_POLY: pure-polynomial exp (A/B builds)
-#define CHI_LOAD_EXPCTX(tab) load_expk()
-#endif
 
 // 1/x for normal x > 0 (x = d^2 + W^2/4 of the Lorentzian): MUFU.RCP64H seed + two
 // Newton steps, ~1 ulp, no slow path.
@@ -240,8 +233,9 @@ constexpr int ab_min_blocks(int N, bool pv) {
 // k_moments_em
 //   physics.py:294-309 (profile), emission_model.py:148 (tau), physics.py:345-365
 //   (radiative transfer), pm.Normal logp, and the adjoint of all of it.
-//   shared per cloud, fetched in pairs (the Gaussian case touches the first three):
-//   [c, -k] [-AG, f] [f*Ts, Ts] [-AL, h]
+//   shared per cloud, fetched in pairs (the Gaussian case touches the first three forward and
+//   the first and third in reverse); k' A' = k A log2(e) feed chi_exp2:
+//   [c, -k'] [-AG', f*Ts] [f, Ts] [-AL', h]
 // ---------------------------------------------------------------------------
 template <int N, bool PV>
 __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(ChanArgs a) {
@@ -249,7 +243,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][8];
   __shared__ double s_gb[CHI_MAX_BASELINE - CHI_BASE_REG][CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
-  __shared__ double s_T[64];
+  __shared__ double s_T[CHI_EXP_TABLE];
   fill_exp_table(s_T);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,8 +257,8 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
     const double f = p[CC_F], ts = p[CC_TS];
     double* d = s_c[warp][lane];
-    d[0] = p[CC_C]; d[1] = -p[CC_KE]; d[2] = -p[CC_AGE]; d[3] = f; d[4] = f * ts; d[5] = ts;
-    d[6] = -p[CC_ALE]; d[7] = p[CC_HE];
+    d[0] = p[CC_C]; d[1] = -CHI_LOG2E * p[CC_KE]; d[2] = -CHI_LOG2E * p[CC_AGE]; d[3] = f * ts;
+    d[4] = f; d[5] = ts; d[6] = -CHI_LOG2E * p[CC_ALE]; d[7] = p[CC_HE];
   }
   if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
   for (int i = CHI_BASE_REG; i < nb; ++i) s_gb[i - CHI_BASE_REG][threadIdx.x] = 0.0;
@@ -304,21 +298,22 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     for (int n = 0; n < N; ++n) {
       double c0, nk, nAG, f, fTs, Ts;
       lds2(&sc[n][0], c0, nk);
-      lds2(&sc[n][2], nAG, f);
-      lds2(&sc[n][4], fTs, Ts);
+      lds2(&sc[n][2], nAG, fTs);
+      lds2(&sc[n][4], f, Ts);
       const double d = v - c0, d2 = d * d;
-      E[n] = chi_exp<false>(nk * d2, ek);
-      double x = nAG * E[n];                    // -tau
+      E[n] = chi_exp2<false>(nk * d2, ek);
+      double x = nAG * E[n];                    // -tau log2(e)
       if (PV) {
         double nAL, h;
         lds2(&sc[n][6], nAL, h);
         q[n] = chi_rcp(d2 + h);
         x = fma(nAL, q[n], x);
       }
-      om[n] = 1.0 - chi_exp(x, ek);               // 1 - e^-tau
+      om[n] = 1.0 - chi_exp2(x, ek);            // 1 - e^-tau
       Pn[n] = P;
-      T = fma(fTs * om[n], P, T);               // f Ts (1-e) x attenuation in front
-      P *= fma(-f, om[n], 1.0);                 // 1 - f + f e
+      const double u = om[n] * P;
+      T = fma(fTs, u, T);                       // f Ts (1-e) x attenuation in front
+      P = fma(-f, u, P);                        // P (1 - f + f e)
     }
     const double mu = (bg * P + T) - bg + base;  // ON - OFF, physics.py:362-365
     double mubar;
@@ -327,7 +322,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     } else {
       const double r = Y[s] - mu;
       mubar = Wt[s] * r;                        // d logp / d mu
-      lp = fma(-0.5 * mubar, r, lp);
+      lp = fma(mubar, r, lp);                   // -0.5 applied once at the end
     }
     if (nb > 0) gb0 = fma(mubar, p0, gb0);
     if (nb > 1) gb1 = fma(mubar, p1, gb1);
@@ -339,10 +334,9 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     double Q = bg;
 #pragma unroll
     for (int n = N - 1; n >= 0; --n) {
-      double c0, nk, nAG, f, fTs, Ts;
+      double c0, nk, f, Ts;
       lds2(&sc[n][0], c0, nk);
-      lds2(&sc[n][2], nAG, f);
-      lds2(&sc[n][4], fTs, Ts);
+      lds2(&sc[n][4], f, Ts);
       const double Sn = Ts - Q;                 // Ts_n - Q_n
       const double x = om[n] * Pn[n];
       const double mx = mubar * x;
@@ -362,12 +356,12 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
         acc[n][6] += u2;
         acc[n][7] = fma(u2, d, acc[n][7]);
       }
-      Q = fma(fma(-f, om[n], 1.0), Q, fTs * om[n]);
+      Q = fma(om[n], f * Sn, Q);                // (1 - f om) Q + f Ts om
     }
   }
 
   double* out = a.mom + item * a.mom_stride;
-  lp = warp_sum(lp);
+  lp = -0.5 * warp_sum(lp);
   gb0 = warp_sum(gb0);
   gb1 = warp_sum(gb1);
   if (lane == 0) {
@@ -392,7 +386,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
 // ---------------------------------------------------------------------------
 // k_moments_abs: absorption spectrum 1 - exp(-sum_n tau)
 //   absorption_model.py:88-91, emission_absorption_model.py:84-99 + physical equivalents
-//   shared per cloud: c, -k, -AG, -AL, h
+//   shared per cloud: c, -k', -AG', -AL', h   (' = times log2(e), for chi_exp2)
 // ---------------------------------------------------------------------------
 template <int N, bool PV>
 __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs(ChanArgs a) {
@@ -400,7 +394,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][6];
   __shared__ double s_gb[CHI_MAX_BASELINE - CHI_BASE_REG][CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
-  __shared__ double s_T[64];
+  __shared__ double s_T[CHI_EXP_TABLE];
   fill_exp_table(s_T);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -413,7 +407,8 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
   if (lane < N) {
     const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
     double* d = s_c[warp][lane];
-    d[0] = p[CC_C]; d[1] = -p[CC_KA]; d[2] = -p[CC_AGA]; d[3] = -p[CC_ALA]; d[4] = p[CC_HA];
+    d[0] = p[CC_C]; d[1] = -CHI_LOG2E * p[CC_KA]; d[2] = -CHI_LOG2E * p[CC_AGA];
+    d[3] = -CHI_LOG2E * p[CC_ALA]; d[4] = p[CC_HA];
     d[5] = 0.0;
   }
   if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
@@ -455,14 +450,14 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
       lds2(&sc[n][2], nAG, nAL);
       d[n] = v - c0;
       const double d2 = d[n] * d[n];
-      E[n] = chi_exp<false>(nk * d2, ek);
+      E[n] = chi_exp2<false>(nk * d2, ek);
       xs = fma(nAG, E[n], xs);
       if (PV) {
         q[n] = chi_rcp(d2 + sc[n][4]);
         xs = fma(nAL, q[n], xs);
       }
     }
-    const double ea = chi_exp(xs, ek);
+    const double ea = chi_exp2(xs, ek);
     const double mu = (1.0 - ea) + base;
     double mubar;
     if (G) {
@@ -470,7 +465,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
     } else {
       const double r = Y[s] - mu;
       mubar = Wt[s] * r;
-      lp = fma(-0.5 * mubar, r, lp);
+      lp = fma(mubar, r, lp);
     }
     if (nb > 0) gb0 = fma(mubar, p0, gb0);
     if (nb > 1) gb1 = fma(mubar, p1, gb1);
@@ -497,7 +492,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
   }
 
   double* out = a.mom + item * a.mom_stride;
-  lp = warp_sum(lp);
+  lp = -0.5 * warp_sum(lp);
   gb0 = warp_sum(gb0);
   gb1 = warp_sum(gb1);
   if (lane == 0) {

@@ -46,15 +46,16 @@ constexpr int ea_min_blocks(int N, bool pv) {
   return clamp_blocks((regs <= 128 ? 4 : (regs <= 168 ? 3 : 2)) + CHI_BLOCKS_BIAS) * 4 / CHI_WARPS_PER_BLOCK;
 }
 
-// shared per cloud (pairs are fetched together; the Gaussian case touches the first three / four):
-//   [c, -k] [-AG_e, -AG_a] [f, f*Ts] [Ts, h] [-AL_e, -AL_a]
+// shared per cloud, fetched in pairs; ' = times log2(e) (arguments of chi_exp2).  The Gaussian case
+// reads A B C forward and A C D in reverse:
+//   A [c, -k']  B [-AG_e', f*Ts]  C [f, -AG_a']  D [Ts, -f AG_e']  E [-AL_e', -AL_a']  F [h, -f AL_e']
 template <int N, bool PV>
 __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(FusedArgs a) {
   constexpr int NF = FusedLayout<PV>::NF;
-  __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][10];
+  __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][12];
   __shared__ double s_gb[2 * CHI_MAX_BASELINE][CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][2 * CHI_MAX_BASELINE];
-  __shared__ double s_T[64];
+  __shared__ double s_T[CHI_EXP_TABLE];
   fill_exp_table(s_T);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,8 +69,10 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
     const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
     const double f = p[CC_F], ts = p[CC_TS];
     double* d = s_c[warp][lane];
-    d[0] = p[CC_C]; d[1] = -p[CC_KE]; d[2] = -p[CC_AGE]; d[3] = -p[CC_AGA]; d[4] = f; d[5] = f * ts;
-    d[6] = ts; d[7] = p[CC_HE]; d[8] = -p[CC_ALE]; d[9] = -p[CC_ALA];
+    const double age = -CHI_LOG2E * p[CC_AGE], ale = -CHI_LOG2E * p[CC_ALE];
+    d[0] = p[CC_C]; d[1] = -CHI_LOG2E * p[CC_KE]; d[2] = age; d[3] = f * ts; d[4] = f;
+    d[5] = -CHI_LOG2E * p[CC_AGA]; d[6] = ts; d[7] = f * age; d[8] = ale; d[9] = -CHI_LOG2E * p[CC_ALA];
+    d[10] = p[CC_HE]; d[11] = f * ale;
   }
   if (lane < nbe) s_beta[warp][lane] = a.coeff_e ? a.coeff_e[b * nbe + lane] : 0.0;
   if (lane < nba) s_beta[warp][CHI_MAX_BASELINE + lane] = a.coeff_a ? a.coeff_a[b * nba + lane] : 0.0;
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
     for (int j = 0; j < NF; ++j) acc[n][j] = 0.0;
   double lp = 0.0;
   const double bg = a.bg;
-  const double(*sc)[10] = s_c[warp];
+  const double(*sc)[12] = s_c[warp];
   const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
@@ -116,27 +119,28 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
     for (int n = 0; n < N; ++n) {
       double c0, nk, nAGe, nAGa, f, fTs;
       lds2(&sc[n][0], c0, nk);
-      lds2(&sc[n][2], nAGe, nAGa);
-      lds2(&sc[n][4], f, fTs);
+      lds2(&sc[n][2], nAGe, fTs);
+      lds2(&sc[n][4], f, nAGa);
       const double d = v - c0, d2 = d * d;
-      E[n] = chi_exp<false>(nk * d2, ek);
+      E[n] = chi_exp2<false>(nk * d2, ek);
       double x = nAGe * E[n];
       xs = fma(nAGa, E[n], xs);
       if (PV) {
-        double Ts_, h, nALe, nALa;
-        lds2(&sc[n][6], Ts_, h);
+        double h, fALe, nALe, nALa;
         lds2(&sc[n][8], nALe, nALa);
+        lds2(&sc[n][10], h, fALe);
         q[n] = chi_rcp(d2 + h);
         x = fma(nALe, q[n], x);
         xs = fma(nALa, q[n], xs);
       }
-      om[n] = 1.0 - chi_exp<true>(x, ek);
+      om[n] = 1.0 - chi_exp2<true>(x, ek);
       Pn[n] = P;
-      T = fma(fTs * om[n], P, T);
-      P *= fma(-f, om[n], 1.0);
+      const double u = om[n] * P;
+      T = fma(fTs, u, T);
+      P = fma(-f, u, P);
     }
     const double mu_e = (bg * P + T) - bg + base_e;   // physics.py:362-365
-    const double ea = chi_exp<true>(xs, ek);
+    const double ea = chi_exp2<true>(xs, ek);
     const double mu_a = (1.0 - ea) + base_a;          // absorption_model.py:91
     double mbe, mba;
     if (a.vjp) {
@@ -146,8 +150,8 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
       const double re = Ye[s] - mu_e, ra = Ya[s] - mu_a;
       mbe = We[s] * re;
       mba = Wa[s] * ra;
-      lp = fma(-0.5 * mbe, re, lp);
-      lp = fma(-0.5 * mba, ra, lp);
+      lp = fma(mbe, re, lp);                          // -0.5 applied once at the end
+      lp = fma(mba, ra, lp);
     }
     gbe0 = fma(mbe, pe0, gbe0);
     gba0 = fma(mba, pa0, gba0);
@@ -162,11 +166,10 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
     double Q = bg;
 #pragma unroll
     for (int n = N - 1; n >= 0; --n) {
-      double c0, nk, nAGe, nAGa, f, fTs, Ts, h;
+      double c0, nk, f, nAGa, Ts, fAGe;
       lds2(&sc[n][0], c0, nk);
-      lds2(&sc[n][2], nAGe, nAGa);
-      lds2(&sc[n][4], f, fTs);
-      lds2(&sc[n][6], Ts, h);
+      lds2(&sc[n][4], f, nAGa);
+      lds2(&sc[n][6], Ts, fAGe);
       const double Sn = Ts - Q;
       const double x = om[n] * Pn[n];
       const double mx = mbe * x;
@@ -176,8 +179,8 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
       const double d = v - c0;
       acc[n][0] = fma(ge, E[n], acc[n][0]);           // M0e
       acc[n][1] = fma(ga, E[n], acc[n][1]);           // M0a
-      // (f AG_e ge + AG_a ga): the constants are stored negated
-      const double gc = -fma(f * nAGe, ge, nAGa * ga);
+      // (f AG_e ge + AG_a ga) log2(e): the constants are stored negated and scaled
+      const double gc = -fma(fAGe, ge, nAGa * ga);
       const double t = gc * E[n];
       const double td = t * d;
       acc[n][2] += td;                                // M1c
@@ -185,19 +188,20 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
       if (PV) {
         acc[n][6] = fma(ge, q[n], acc[n][6]);         // Q1e
         acc[n][7] = fma(ga, q[n], acc[n][7]);         // Q1a
-        double nALe, nALa;
+        double nALe, nALa, h, fALe;
         lds2(&sc[n][8], nALe, nALa);
-        const double gl = -fma(f * nALe, ge, nALa * ga);
+        lds2(&sc[n][10], h, fALe);
+        const double gl = -fma(fALe, ge, nALa * ga);
         const double u2 = gl * q[n] * q[n];
         acc[n][8] += u2;                              // Q2c
         acc[n][9] = fma(u2, d, acc[n][9]);            // Q2dc
       }
-      Q = fma(fma(-f, om[n], 1.0), Q, fTs * om[n]);
+      Q = fma(om[n], f * Sn, Q);                      // (1 - f om) Q + f Ts om
     }
   }
 
   double* out = a.mom + item * a.mom_stride;
-  lp = warp_sum(lp);
+  lp = -0.5 * warp_sum(lp);
   gbe0 = warp_sum(gbe0);
   gba0 = warp_sum(gba0);
   if (lane == 0) {
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
 #pragma unroll
     for (int j = 0; j < NF; ++j) {
       double r = warp_sum(acc[n][j]);
+      if (j == 2 || j == 3 || j == 8 || j == 9) r *= CHI_LN2;  // combined moments carry log2(e)
       if (lane == ((n * NF + j) & 31)) om_[n * NF + j] = r;
     }
 }
