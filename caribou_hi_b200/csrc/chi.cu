@@ -48,10 +48,9 @@ struct Buf {
 
 struct DevDataset {
   int S = 0, nb = 0;
-  int dir = 0;  // +1/-1 strictly ascending/descending axis, 0 otherwise
   bool has_offset = false;
-  Buf vax, yeff, wgt, basis, offset;
-  void release() { vax.release(); yeff.release(); wgt.release(); basis.release(); offset.release(); }
+  Buf vax, chan, basis, offset;  // chan: packed v / p_0 / y / w planes (ChanArgs::chan)
+  void release() { vax.release(); chan.release(); basis.release(); offset.release(); }
 };
 
 // One pipeline lane: a stream plus the device workspace a batch needs.  Lane 0 uses the
@@ -94,13 +93,12 @@ struct chi_handle {
   // further staging of the host entry points (single-lane paths)
   Buf w_gbe, w_gba, w_mue, w_mua, w_misc[8];
   bool shared_axis = false;  // both datasets on the same spectral axis: fused kernel
+  Buf chan;                  // its packed per-channel data [n_sl][S][8]
   bool priors_set = false;
   bool capturing = false;  // inside a stream capture: no timing events
   double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];
   int64_t call_first_stage = 0;  // stage_calls at the start of the current model-level call
   int64_t launches = 0;
-  int kernel_family = 1;  // 1: moments.cuh (default), 2: moments_win.cuh (env CHI_KERNEL=2)
-  int cpt = 2;            // channels per thread of family 2
   std::string err;
 };
 
@@ -210,7 +208,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   const bool do_e = h->has_e && (!vjp || gbar_e);
   const bool do_a = h->has_a && (!vjp || gbar_a);
   bool fused_done = false;
-  if (h->shared_axis && h->kernel_family == 1 && (do_e || do_a)) {
+  if (h->shared_axis && (do_e || do_a)) {
     // both datasets on one axis: one pass evaluates exp(-k d^2) once for the two of them
     FusedArgs a;
     memset(&a, 0, sizeof(a));
@@ -218,9 +216,9 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = 1 + a.nb_e + a.nb_a + N * (pv ? 10 : 6);
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
-    a.vax = h->e.vax.d();
-    a.yeff_e = h->e.yeff.d(); a.wgt_e = h->e.wgt.d(); a.basis_e = h->e.basis.d(); a.coeff_e = ce;
-    a.yeff_a = h->a.yeff.d(); a.wgt_a = h->a.wgt.d(); a.basis_a = h->a.basis.d(); a.coeff_a = ca;
+    a.chan = h->chan.d();
+    a.basis_e = h->e.basis.d(); a.coeff_e = ce;
+    a.basis_a = h->a.basis.d(); a.coeff_a = ca;
     a.vjp = vjp ? 1 : 0; a.gbar_e = vjp ? gbar_e : nullptr; a.gbar_a = vjp ? gbar_a : nullptr;
     a.sl = sl; a.cc = L.cc.d(); a.mom = L.mom_e.d();
     if (launch_moments_ea(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
@@ -240,11 +238,10 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     a.B = B; a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp;
     pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = em_record(h);
-    a.axis_dir = h->e.dir;
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
-    a.vax = h->e.vax.d(); a.yeff = h->e.yeff.d(); a.wgt = h->e.wgt.d(); a.basis = h->e.basis.d();
+    a.chan = h->e.chan.d(); a.basis = h->e.basis.d();
     a.coeff = ce; a.sl = sl; a.gbar = vjp ? gbar_e : nullptr; a.cc = L.cc.d(); a.mom = L.mom_e.d();
-    if (launch_moments_em(N, pv, a, L.st, h->kernel_family)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    if (launch_moments_em(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
     ea.has_e = 1; ea.nb_e = a.n_base; ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride;
@@ -261,11 +258,10 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     a.B = B; a.S = h->a.S; a.n_base = h->a.nb; a.bg = 0.0;
     pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = ab_record(h);
-    a.axis_dir = h->a.dir;
     CK(L.mom_a.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
-    a.vax = h->a.vax.d(); a.yeff = h->a.yeff.d(); a.wgt = h->a.wgt.d(); a.basis = h->a.basis.d();
+    a.chan = h->a.chan.d(); a.basis = h->a.basis.d();
     a.coeff = ca; a.sl = sl; a.gbar = vjp ? gbar_a : nullptr; a.cc = L.cc.d(); a.mom = L.mom_a.d();
-    if (launch_moments_abs(N, pv, a, st_a, h->kernel_family)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    if (launch_moments_abs(N, pv, a, st_a)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
     h->launches++;
     CK(cudaGetLastError());
     ea.has_a = 1; ea.nb_a = a.n_base; ea.chunks_a = a.n_chunks; ea.stride_a = a.mom_stride;
@@ -365,36 +361,29 @@ int upload_dataset(chi_handle* h, DevDataset& d, const chi_dataset* src, int n_s
   d.S = S;
   d.nb = src->n_baseline;
   d.has_offset = src->offset != nullptr;
-  {
-    bool up = true, down = true;
-    for (int s = 1; s < S; ++s) {
-      up = up && src->spectral[s] > src->spectral[s - 1];
-      down = down && src->spectral[s] < src->spectral[s - 1];
-    }
-    d.dir = up ? 1 : (down ? -1 : 0);
-    if (getenv("CHI_NOWIN")) d.dir = 0;  // experiment knob: disable the active-window skipping
-  }
-  std::vector<double> yeff((size_t)n_sl * S), wgt((size_t)n_sl * S);
+  const size_t groups = ((size_t)S + 31) / 32;
+  std::vector<double> chan((size_t)n_sl * groups * 128, 0.0);  // [sightline][group][v, p_0, y, w][32]
   const double half_log_2pi = 0.5 * log(2.0 * M_PI);
   for (int i = 0; i < n_sl; ++i) {
     double lc = 0.0;
     for (int s = 0; s < S; ++s) {
       const double sig = src->noise[(size_t)i * S + s];
       if (!(sig > 0.0)) return fail(h, CHI_EINVAL, std::string(name) + ": noise must be > 0");
-      yeff[(size_t)i * S + s] = src->brightness[(size_t)i * S + s] - (src->offset ? src->offset[s] : 0.0);
-      wgt[(size_t)i * S + s] = 1.0 / (sig * sig);
+      double* c = &chan[((size_t)i * groups + s / 32) * 128 + s % 32];
+      c[0] = src->spectral[s];
+      c[32] = src->n_baseline > 0 ? src->basis[s] : 0.0;
+      c[64] = src->brightness[(size_t)i * S + s] - (src->offset ? src->offset[s] : 0.0);
+      c[96] = 1.0 / (sig * sig);
       lc += -log(sig) - half_log_2pi;  // pm.Normal logp normalisation
     }
     lconst_host[i] += lc;
   }
   CK(d.vax.ensure(S * sizeof(double)));
-  CK(d.yeff.ensure(yeff.size() * sizeof(double)));
-  CK(d.wgt.ensure(wgt.size() * sizeof(double)));
+  CK(d.chan.ensure(chan.size() * sizeof(double)));
   CK(d.basis.ensure(std::max<size_t>(1, (size_t)d.nb * S) * sizeof(double)));
   CK(d.offset.ensure(S * sizeof(double)));
   CK(cudaMemcpy(d.vax.p, src->spectral, S * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d.yeff.p, yeff.data(), yeff.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d.wgt.p, wgt.data(), wgt.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d.chan.p, chan.data(), chan.size() * sizeof(double), cudaMemcpyHostToDevice));
   if (d.nb > 0) CK(cudaMemcpy(d.basis.p, src->basis, (size_t)d.nb * S * sizeof(double), cudaMemcpyHostToDevice));
   if (src->offset) CK(cudaMemcpy(d.offset.p, src->offset, S * sizeof(double), cudaMemcpyHostToDevice));
   return CHI_OK;
@@ -473,7 +462,6 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
   h->cfg = *cfg;
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
-  if (const char* e = getenv("CHI_KERNEL")) h->kernel_family = atoi(e) == 2 ? 2 : 1;
   const int m = cfg->model;
   h->has_e = (m == CHI_MODEL_PHYSICS) ? cfg->has_emission != 0 : kind_has_emission(m);
   h->has_a = (m == CHI_MODEL_PHYSICS) ? cfg->has_absorption != 0 : kind_has_absorption(m);
@@ -515,7 +503,7 @@ void chi_destroy(chi_handle* h) {
   cudaSetDevice(h->device);
   for (Lane& L : h->lanes)
     if (L.st) cudaStreamSynchronize(L.st);
-  h->e.release(); h->a.release(); h->lconst.release();
+  h->e.release(); h->a.release(); h->lconst.release(); h->chan.release();
   for (Lane& L : h->lanes) L.release();
   Buf* bufs[] = {&h->w_gbe, &h->w_gba, &h->w_mue, &h->w_mua};
   for (Buf* b : bufs) b->release();
@@ -582,6 +570,28 @@ int chi_set_spectra(chi_handle* h, int n_sightlines, const chi_dataset* emission
   h->shared_axis = false;
   if (h->has_e && h->has_a && emission->n_channels == absorption->n_channels && !getenv("CHI_NO_FUSED")) {
     h->shared_axis = memcmp(emission->spectral, absorption->spectral, emission->n_channels * sizeof(double)) == 0;
+  }
+  if (h->shared_axis) {
+    // packed channel data of the fused kernel, [sightline][group of 32 channels][plane][32]:
+    // planes v, p_e0, p_a0, -, y_e, w_e, y_a, w_a
+    const int S = emission->n_channels;
+    const size_t groups = ((size_t)S + 31) / 32;
+    std::vector<double> chan((size_t)n_sightlines * groups * 256, 0.0);
+    for (int i = 0; i < n_sightlines; ++i)
+      for (int s = 0; s < S; ++s) {
+        double* c = &chan[((size_t)i * groups + s / 32) * 256 + s % 32];
+        const size_t k = (size_t)i * S + s;
+        const double sig_e = emission->noise[k], sig_a = absorption->noise[k];
+        c[0] = emission->spectral[s];
+        c[32] = emission->n_baseline > 0 ? emission->basis[s] : 0.0;
+        c[64] = absorption->n_baseline > 0 ? absorption->basis[s] : 0.0;
+        c[128] = emission->brightness[k] - (emission->offset ? emission->offset[s] : 0.0);
+        c[160] = 1.0 / (sig_e * sig_e);
+        c[192] = absorption->brightness[k] - (absorption->offset ? absorption->offset[s] : 0.0);
+        c[224] = 1.0 / (sig_a * sig_a);
+      }
+    CK(h->chan.ensure(chan.size() * sizeof(double)));
+    CK(cudaMemcpy(h->chan.p, chan.data(), chan.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   CK(h->lconst.ensure(n_sightlines * sizeof(double)));
   CK(cudaMemcpy(h->lconst.p, lconst.data(), n_sightlines * sizeof(double), cudaMemcpyHostToDevice));

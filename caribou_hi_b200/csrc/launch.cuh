@@ -1,6 +1,5 @@
-// Launchers of the two hot kernels, compiled in their own translation units
-// (launch_em.cu / launch_abs.cu) so that the 8 x 2 template instantiations of each build in
-// parallel.  Return 0, or -1 for an unsupported cloud count.
+// Launchers of the hot kernels, compiled in their own translation units (launch_*.cu) so that
+// the 8 x 2 x 2 template instantiations of each build in parallel.  Return 0, or -1 for an unsupported cloud count.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -26,8 +25,8 @@ struct SpecArgs {
 int launch_spectra(int N, bool pv, const SpecArgs& a, cudaStream_t st);
 struct FusedArgs;
 int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st);
-int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st, int family);
-int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st, int family);
+int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st);
+int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st);
 
 inline unsigned warp_grid(const ChanArgs& a) {
   int64_t items = a.B * a.n_chunks;

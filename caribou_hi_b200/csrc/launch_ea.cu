@@ -1,16 +1,26 @@
-// k_moments_ea<N, PV> instantiations: fused emission+absorption for a shared spectral axis.
+// k_moments_ea<N, PV, SB> instantiations: fused emission+absorption for a shared spectral axis.
+// Built twice (launch_ea.cu: CHI_EA_SB=1, launch_ea_gb.cu: CHI_EA_SB=0) so the two halves compile
+// in parallel.
 #include "launch.cuh"
 #include "moments_ea.cuh"
+
+#ifndef CHI_EA_SB
+#define CHI_EA_SB 1
+#endif
 
 namespace chi {
 template <int N, bool PV>
 static void run(const FusedArgs& a, cudaStream_t st) {
   const int64_t items = a.B * a.n_chunks;
   const unsigned grid = (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
-  k_moments_ea<N, PV><<<grid, CHI_BLOCK, 0, st>>>(a);
+  k_moments_ea<N, PV, CHI_EA_SB != 0><<<grid, CHI_BLOCK, 0, st>>>(a);
 }
 
-int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
+#if CHI_EA_SB
+int launch_moments_ea_sb(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
+#else
+int launch_moments_ea_gb(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
+#endif
   switch (N * 2 + (pv ? 1 : 0)) {
 #define CASE(n)                           \
   case (n)*2: run<n, false>(a, st); return 0; \
@@ -20,4 +30,11 @@ int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
   }
   return -1;
 }
+
+#if CHI_EA_SB
+int launch_moments_ea_gb(int N, bool pv, const FusedArgs& a, cudaStream_t st);
+int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
+  return (a.nb_e <= 1 && a.nb_a <= 1) ? launch_moments_ea_sb(N, pv, a, st) : launch_moments_ea_gb(N, pv, a, st);
+}
+#endif
 }  // namespace chi

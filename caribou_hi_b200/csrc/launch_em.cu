@@ -1,20 +1,36 @@
-// k_moments_em<N, PV> instantiations (N = 1..8, Gaussian / pseudo-Voigt).
+// k_moments_em<N, PV, SB> instantiations (N = 1..8, Gaussian / pseudo-Voigt).  Built twice
+// (launch_em.cu: CHI_SB=1, launch_em_gb.cu: CHI_SB=0) so the two halves compile in parallel.
 #include "launch.cuh"
+
+#ifndef CHI_SB
+#define CHI_SB 1
+#endif
 
 namespace chi {
 template <int N, bool PV>
-static void run(const ChanArgs& a, cudaStream_t st, int family) {
-  k_moments_em<N, PV><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
+static void run(const ChanArgs& a, cudaStream_t st) {
+  k_moments_em<N, PV, CHI_SB != 0><<<warp_grid(a), CHI_BLOCK, 0, st>>>(a);
 }
 
-int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st, int family) {
+#if CHI_SB
+static int launch_sb(int N, bool pv, const ChanArgs& a, cudaStream_t st) {
+#else
+int launch_moments_em_gb(int N, bool pv, const ChanArgs& a, cudaStream_t st) {
+#endif
   switch (N * 2 + (pv ? 1 : 0)) {
-#define CASE(n)                                \
-  case (n)*2: run<n, false>(a, st, family); return 0; \
-  case (n)*2 + 1: run<n, true>(a, st, family); return 0;
+#define CASE(n)                        \
+  case (n)*2: run<n, false>(a, st); return 0; \
+  case (n)*2 + 1: run<n, true>(a, st); return 0;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
   }
   return -1;
 }
+
+#if CHI_SB
+int launch_moments_em_gb(int N, bool pv, const ChanArgs& a, cudaStream_t st);
+int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st) {
+  return a.n_base <= 1 ? launch_sb(N, pv, a, st) : launch_moments_em_gb(N, pv, a, st);
+}
+#endif
 }  // namespace chi

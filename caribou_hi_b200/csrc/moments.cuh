@@ -191,11 +191,11 @@ struct ChanArgs {
   int n_chunks;     // channel chunks per draw
   int chunk_len;    // channels per chunk (multiple of 32)
   int mom_stride;   // doubles per (draw, chunk) record
-  int axis_dir;     // +1 / -1: spectral axis strictly ascending / descending, 0: neither
   double bg;
-  const double* __restrict__ vax;     // [S]
-  const double* __restrict__ yeff;    // [n_sl][S]   brightness - baseline offset
-  const double* __restrict__ wgt;     // [n_sl][S]   1/noise^2
+  // packed channel data [n_sl][ceil(S/32)][4][32]: per group of 32 channels the planes v, p_0
+  // (first baseline basis column or 0), y (brightness - baseline offset), w (1/noise^2): one
+  // address per warp iteration, immediate plane offsets, coalesced 256-byte requests
+  const double* __restrict__ chan;
   const double* __restrict__ basis;   // [n_base][S]
   const double* __restrict__ coeff;   // [B][n_base] or null
   const int32_t* __restrict__ sl;     // [B] or null
@@ -237,11 +237,13 @@ constexpr int ab_min_blocks(int N, bool pv) {
 //   the first and third in reverse); k' A' = k A log2(e) feed chi_exp2:
 //   [c, -k'] [-AG', f*Ts] [f, Ts] [-AL', h]
 // ---------------------------------------------------------------------------
-template <int N, bool PV>
+// SB ("simple baseline") instantiations serve n_base <= 1 -- the reference's default
+// baseline_degree = 0 -- and carry no baseline loops.
+template <int N, bool PV, bool SB>
 __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(ChanArgs a) {
   constexpr int NE = EmLayout<PV>::NE;
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][8];
-  __shared__ double s_gb[CHI_MAX_BASELINE - CHI_BASE_REG][CHI_BLOCK];
+  __shared__ double s_gb[SB ? 1 : CHI_MAX_BASELINE - CHI_BASE_REG][SB ? 1 : CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
   __shared__ double s_T[CHI_EXP_TABLE];
   fill_exp_table(s_T);
@@ -261,17 +263,15 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     d[4] = f; d[5] = ts; d[6] = -CHI_LOG2E * p[CC_ALE]; d[7] = p[CC_HE];
   }
   if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
-  for (int i = CHI_BASE_REG; i < nb; ++i) s_gb[i - CHI_BASE_REG][threadIdx.x] = 0.0;
+  if (!SB)
+    for (int i = CHI_BASE_REG; i < nb; ++i) s_gb[i - CHI_BASE_REG][threadIdx.x] = 0.0;
   __syncwarp();
-  const double beta0 = nb > 0 ? s_beta[warp][0] : 0.0, beta1 = nb > 1 ? s_beta[warp][1] : 0.0;
-  const double* __restrict__ bas0 = a.basis;
+  const double beta0 = nb > 0 ? s_beta[warp][0] : 0.0, beta1 = (!SB && nb > 1) ? s_beta[warp][1] : 0.0;
   const double* __restrict__ bas1 = a.basis + S;
 
   const int sl = a.sl ? a.sl[b] : 0;
-  const double* __restrict__ Y = a.yeff + (int64_t)sl * S;
-  const double* __restrict__ Wt = a.wgt + (int64_t)sl * S;
+  const double* __restrict__ ch = a.chan + (int64_t)sl * ((S + 31) >> 5) * 128 + lane;
   const double* __restrict__ G = a.gbar ? a.gbar + b * S : nullptr;
-  const double* __restrict__ V = a.vax;
 
   double acc[N][NE];
 #pragma unroll
@@ -285,11 +285,13 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
   for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
-    const double v = V[s];
-    double p0 = 0.0, p1 = 0.0, base = 0.0;
-    if (nb > 0) { p0 = bas0[s]; base = beta0 * p0; }
-    if (nb > 1) { p1 = bas1[s]; base = fma(beta1, p1, base); }
-    for (int i = CHI_BASE_REG; i < nb; ++i) base = fma(s_beta[warp][i], a.basis[(int64_t)i * S + s], base);
+    const double* __restrict__ cs = ch + (int64_t)(s >> 5) * 128;  // lane offset is in ch
+    const double v = __ldg(cs), p0 = __ldg(cs + 32);
+    double p1 = 0.0, base = beta0 * p0;  // p_0 is 0 without a baseline
+    if (!SB) {
+      if (nb > 1) { p1 = bas1[s]; base = fma(beta1, p1, base); }
+      for (int i = CHI_BASE_REG; i < nb; ++i) base = fma(s_beta[warp][i], a.basis[(int64_t)i * S + s], base);
+    }
 
     // ---- forward, nearest cloud first ----
     double om[N], Pn[N], E[N], q[N];
@@ -320,15 +322,17 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     if (G) {
       mubar = G[s];
     } else {
-      const double r = Y[s] - mu;
-      mubar = Wt[s] * r;                        // d logp / d mu
+      const double r = __ldg(cs + 64) - mu;
+      mubar = __ldg(cs + 96) * r;               // d logp / d mu
       lp = fma(mubar, r, lp);                   // -0.5 applied once at the end
     }
-    if (nb > 0) gb0 = fma(mubar, p0, gb0);
-    if (nb > 1) gb1 = fma(mubar, p1, gb1);
-    for (int i = CHI_BASE_REG; i < nb; ++i)
-      s_gb[i - CHI_BASE_REG][threadIdx.x] =
-          fma(mubar, a.basis[(int64_t)i * S + s], s_gb[i - CHI_BASE_REG][threadIdx.x]);
+    gb0 = fma(mubar, p0, gb0);
+    if (!SB) {
+      if (nb > 1) gb1 = fma(mubar, p1, gb1);
+      for (int i = CHI_BASE_REG; i < nb; ++i)
+        s_gb[i - CHI_BASE_REG][threadIdx.x] =
+            fma(mubar, a.basis[(int64_t)i * S + s], s_gb[i - CHI_BASE_REG][threadIdx.x]);
+    }
 
     // ---- reverse, farthest cloud first; Q = brightness arriving behind cloud n ----
     double Q = bg;
@@ -369,10 +373,11 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     if (nb > 0) out[1] = gb0;
     if (nb > 1) out[2] = gb1;
   }
-  for (int i = CHI_BASE_REG; i < nb; ++i) {
-    double g = warp_sum(s_gb[i - CHI_BASE_REG][threadIdx.x]);
-    if (lane == 0) out[1 + i] = g;
-  }
+  if (!SB)
+    for (int i = CHI_BASE_REG; i < nb; ++i) {
+      double g = warp_sum(s_gb[i - CHI_BASE_REG][threadIdx.x]);
+      if (lane == 0) out[1 + i] = g;
+    }
   double* om_ = out + 1 + nb;
 #pragma unroll
   for (int n = 0; n < N; ++n)
@@ -388,11 +393,11 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
 //   absorption_model.py:88-91, emission_absorption_model.py:84-99 + physical equivalents
 //   shared per cloud: c, -k', -AG', -AL', h   (' = times log2(e), for chi_exp2)
 // ---------------------------------------------------------------------------
-template <int N, bool PV>
+template <int N, bool PV, bool SB>
 __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs(ChanArgs a) {
   constexpr int NA = AbLayout<PV>::NA;
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][6];
-  __shared__ double s_gb[CHI_MAX_BASELINE - CHI_BASE_REG][CHI_BLOCK];
+  __shared__ double s_gb[SB ? 1 : CHI_MAX_BASELINE - CHI_BASE_REG][SB ? 1 : CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
   __shared__ double s_T[CHI_EXP_TABLE];
   fill_exp_table(s_T);
@@ -412,17 +417,15 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
     d[5] = 0.0;
   }
   if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
-  for (int i = CHI_BASE_REG; i < nb; ++i) s_gb[i - CHI_BASE_REG][threadIdx.x] = 0.0;
+  if (!SB)
+    for (int i = CHI_BASE_REG; i < nb; ++i) s_gb[i - CHI_BASE_REG][threadIdx.x] = 0.0;
   __syncwarp();
-  const double beta0 = nb > 0 ? s_beta[warp][0] : 0.0, beta1 = nb > 1 ? s_beta[warp][1] : 0.0;
-  const double* __restrict__ bas0 = a.basis;
+  const double beta0 = nb > 0 ? s_beta[warp][0] : 0.0, beta1 = (!SB && nb > 1) ? s_beta[warp][1] : 0.0;
   const double* __restrict__ bas1 = a.basis + S;
 
   const int sl = a.sl ? a.sl[b] : 0;
-  const double* __restrict__ Y = a.yeff + (int64_t)sl * S;
-  const double* __restrict__ Wt = a.wgt + (int64_t)sl * S;
+  const double* __restrict__ ch = a.chan + (int64_t)sl * ((S + 31) >> 5) * 128 + lane;
   const double* __restrict__ G = a.gbar ? a.gbar + b * S : nullptr;
-  const double* __restrict__ V = a.vax;
 
   double acc[N][NA];
 #pragma unroll
@@ -435,11 +438,13 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
   for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
-    const double v = V[s];
-    double p0 = 0.0, p1 = 0.0, base = 0.0;
-    if (nb > 0) { p0 = bas0[s]; base = beta0 * p0; }
-    if (nb > 1) { p1 = bas1[s]; base = fma(beta1, p1, base); }
-    for (int i = CHI_BASE_REG; i < nb; ++i) base = fma(s_beta[warp][i], a.basis[(int64_t)i * S + s], base);
+    const double* __restrict__ cs = ch + (int64_t)(s >> 5) * 128;  // lane offset is in ch
+    const double v = __ldg(cs), p0 = __ldg(cs + 32);
+    double p1 = 0.0, base = beta0 * p0;  // p_0 is 0 without a baseline
+    if (!SB) {
+      if (nb > 1) { p1 = bas1[s]; base = fma(beta1, p1, base); }
+      for (int i = CHI_BASE_REG; i < nb; ++i) base = fma(s_beta[warp][i], a.basis[(int64_t)i * S + s], base);
+    }
 
     double E[N], d[N], q[N];
     double xs = 0.0;  // -sum_n tau_n
@@ -463,15 +468,17 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
     if (G) {
       mubar = G[s];
     } else {
-      const double r = Y[s] - mu;
-      mubar = Wt[s] * r;
+      const double r = __ldg(cs + 64) - mu;
+      mubar = __ldg(cs + 96) * r;
       lp = fma(mubar, r, lp);
     }
-    if (nb > 0) gb0 = fma(mubar, p0, gb0);
-    if (nb > 1) gb1 = fma(mubar, p1, gb1);
-    for (int i = CHI_BASE_REG; i < nb; ++i)
-      s_gb[i - CHI_BASE_REG][threadIdx.x] =
-          fma(mubar, a.basis[(int64_t)i * S + s], s_gb[i - CHI_BASE_REG][threadIdx.x]);
+    gb0 = fma(mubar, p0, gb0);
+    if (!SB) {
+      if (nb > 1) gb1 = fma(mubar, p1, gb1);
+      for (int i = CHI_BASE_REG; i < nb; ++i)
+        s_gb[i - CHI_BASE_REG][threadIdx.x] =
+            fma(mubar, a.basis[(int64_t)i * S + s], s_gb[i - CHI_BASE_REG][threadIdx.x]);
+    }
 
     const double g = mubar * ea;  // taubar, identical for every cloud
 #pragma unroll
@@ -500,10 +507,11 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
     if (nb > 0) out[1] = gb0;
     if (nb > 1) out[2] = gb1;
   }
-  for (int i = CHI_BASE_REG; i < nb; ++i) {
-    double g = warp_sum(s_gb[i - CHI_BASE_REG][threadIdx.x]);
-    if (lane == 0) out[1 + i] = g;
-  }
+  if (!SB)
+    for (int i = CHI_BASE_REG; i < nb; ++i) {
+      double g = warp_sum(s_gb[i - CHI_BASE_REG][threadIdx.x]);
+      if (lane == 0) out[1 + i] = g;
+    }
   double* om_ = out + 1 + nb;
 #pragma unroll
   for (int n = 0; n < N; ++n)

@@ -9,6 +9,13 @@
 //     M1c = sum (f AG_e g_e + AG_a g_a) E d,   M2c = sum (...) E d^2,   [Q2c, Q2dc likewise with AL, q^2]
 // so the fused record needs 6 (Gaussian) / 10 (pseudo-Voigt) sums per cloud instead of 5+3 / 8+6:
 //     M0e = sum g_e E, M0a = sum g_a E, M1c, M2c, aTs, af, [Q1e, Q1a, Q2c, Q2dc]
+// The per-channel data of the two datasets is read from one packed array (FusedArgs::chan): per
+// group of 32 channels eight planes of 32 doubles -- v, p_e0, p_a0, -, y_e, w_e, y_a, w_a; p_x0 =
+// first baseline basis column or 0 -- so that a warp's iteration has one address, every plane
+// is an immediate offset from it and each load stays a coalesced 256-byte request (an
+// array-of-structs layout costs 16 L1 wavefronts per load and saturates the LSU data pipe).  SB ("simple
+// baseline") instantiations serve n_baseline <= 1 on both datasets -- the reference's default
+// baseline_degree = 0 -- and carry no shared-memory baseline loops at all.
 // Record per (draw, chunk): [0] = sum -0.5 w r^2 of both datasets, [1..nb_e] and [1+nb_e..] the
 // baseline-coefficient gradients, then N x NF moments.  k_epilogue reads it with `fused = 1`.
 #pragma once
@@ -22,14 +29,10 @@ struct FusedArgs {
   int nb_e, nb_a;
   int n_chunks, chunk_len, mom_stride;
   double bg;
-  const double* __restrict__ vax;
-  const double* __restrict__ yeff_e;
-  const double* __restrict__ wgt_e;
+  const double* __restrict__ chan;     // [n_sl][ceil(S/32)][8][32] packed channel data (see above)
   const double* __restrict__ basis_e;
   const double* __restrict__ coeff_e;
   const double* __restrict__ gbar_e;
-  const double* __restrict__ yeff_a;
-  const double* __restrict__ wgt_a;
   const double* __restrict__ basis_a;
   const double* __restrict__ coeff_a;
   const double* __restrict__ gbar_a;
@@ -49,11 +52,17 @@ constexpr int ea_min_blocks(int N, bool pv) {
 // shared per cloud, fetched in pairs; ' = times log2(e) (arguments of chi_exp2).  The Gaussian case
 // reads A B C forward and A C D in reverse:
 //   A [c, -k']  B [-AG_e', f*Ts]  C [f, -AG_a']  D [Ts, -f AG_e']  E [-AL_e', -AL_a']  F [h, -f AL_e']
-template <int N, bool PV>
+__device__ __forceinline__ void ldg2(const double* p, double& x, double& y) {
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+  x = t.x;
+  y = t.y;
+}
+
+template <int N, bool PV, bool SB>
 __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(FusedArgs a) {
   constexpr int NF = FusedLayout<PV>::NF;
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][12];
-  __shared__ double s_gb[2 * CHI_MAX_BASELINE][CHI_BLOCK];
+  __shared__ double s_gb[SB ? 1 : 2 * CHI_MAX_BASELINE][SB ? 1 : CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][2 * CHI_MAX_BASELINE];
   __shared__ double s_T[CHI_EXP_TABLE];
   fill_exp_table(s_T);
@@ -76,21 +85,19 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
   }
   if (lane < nbe) s_beta[warp][lane] = a.coeff_e ? a.coeff_e[b * nbe + lane] : 0.0;
   if (lane < nba) s_beta[warp][CHI_MAX_BASELINE + lane] = a.coeff_a ? a.coeff_a[b * nba + lane] : 0.0;
-  for (int i = 1; i < nbe; ++i) s_gb[i][threadIdx.x] = 0.0;
-  for (int i = 1; i < nba; ++i) s_gb[CHI_MAX_BASELINE + i][threadIdx.x] = 0.0;
+  if (!SB) {
+    for (int i = 1; i < nbe; ++i) s_gb[i][threadIdx.x] = 0.0;
+    for (int i = 1; i < nba; ++i) s_gb[CHI_MAX_BASELINE + i][threadIdx.x] = 0.0;
+  }
   __syncwarp();
   // the first baseline term of each dataset (degree 0) stays in registers
   const double be0 = nbe > 0 ? s_beta[warp][0] : 0.0, ba0 = nba > 0 ? s_beta[warp][CHI_MAX_BASELINE] : 0.0;
   double gbe0 = 0.0, gba0 = 0.0;
 
   const int sl = a.sl ? a.sl[b] : 0;
-  const double* __restrict__ Ye = a.yeff_e + (int64_t)sl * S;
-  const double* __restrict__ We = a.wgt_e + (int64_t)sl * S;
-  const double* __restrict__ Ya = a.yeff_a + (int64_t)sl * S;
-  const double* __restrict__ Wa = a.wgt_a + (int64_t)sl * S;
+  const double* __restrict__ ch = a.chan + (int64_t)sl * ((S + 31) >> 5) * 256 + lane;
   const double* __restrict__ Ge = a.gbar_e ? a.gbar_e + b * S : nullptr;
   const double* __restrict__ Ga = a.gbar_a ? a.gbar_a + b * S : nullptr;
-  const double* __restrict__ V = a.vax;
 
   double acc[N][NF];
 #pragma unroll
@@ -104,13 +111,14 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
   for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
-    const double v = V[s];
-    double base_e = 0.0, base_a = 0.0, pe0 = 0.0, pa0 = 0.0;
-    if (nbe > 0) { pe0 = a.basis_e[s]; base_e = be0 * pe0; }
-    if (nba > 0) { pa0 = a.basis_a[s]; base_a = ba0 * pa0; }
-    for (int i = 1; i < nbe; ++i) base_e = fma(s_beta[warp][i], a.basis_e[(int64_t)i * S + s], base_e);
-    for (int i = 1; i < nba; ++i)
-      base_a = fma(s_beta[warp][CHI_MAX_BASELINE + i], a.basis_a[(int64_t)i * S + s], base_a);
+    const double* __restrict__ cs = ch + (int64_t)(s >> 5) * 256;  // lane offset is in ch
+    const double v = __ldg(cs), pe0 = __ldg(cs + 32), pa0 = __ldg(cs + 64);
+    double base_e = be0 * pe0, base_a = ba0 * pa0;  // p_x0 is 0 without a baseline
+    if (!SB) {
+      for (int i = 1; i < nbe; ++i) base_e = fma(s_beta[warp][i], a.basis_e[(int64_t)i * S + s], base_e);
+      for (int i = 1; i < nba; ++i)
+        base_a = fma(s_beta[warp][CHI_MAX_BASELINE + i], a.basis_a[(int64_t)i * S + s], base_a);
+    }
 
     // ---- forward: one exp(-k d^2) per cloud feeds both datasets ----
     double om[N], Pn[N], E[N], q[N];
@@ -147,19 +155,21 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
       mbe = Ge ? Ge[s] : 0.0;
       mba = Ga ? Ga[s] : 0.0;
     } else {
-      const double re = Ye[s] - mu_e, ra = Ya[s] - mu_a;
-      mbe = We[s] * re;
-      mba = Wa[s] * ra;
+      const double re = __ldg(cs + 128) - mu_e, ra = __ldg(cs + 192) - mu_a;
+      mbe = __ldg(cs + 160) * re;
+      mba = __ldg(cs + 224) * ra;
       lp = fma(mbe, re, lp);                          // -0.5 applied once at the end
       lp = fma(mba, ra, lp);
     }
     gbe0 = fma(mbe, pe0, gbe0);
     gba0 = fma(mba, pa0, gba0);
-    for (int i = 1; i < nbe; ++i)
-      s_gb[i][threadIdx.x] = fma(mbe, a.basis_e[(int64_t)i * S + s], s_gb[i][threadIdx.x]);
-    for (int i = 1; i < nba; ++i)
-      s_gb[CHI_MAX_BASELINE + i][threadIdx.x] =
-          fma(mba, a.basis_a[(int64_t)i * S + s], s_gb[CHI_MAX_BASELINE + i][threadIdx.x]);
+    if (!SB) {
+      for (int i = 1; i < nbe; ++i)
+        s_gb[i][threadIdx.x] = fma(mbe, a.basis_e[(int64_t)i * S + s], s_gb[i][threadIdx.x]);
+      for (int i = 1; i < nba; ++i)
+        s_gb[CHI_MAX_BASELINE + i][threadIdx.x] =
+            fma(mba, a.basis_a[(int64_t)i * S + s], s_gb[CHI_MAX_BASELINE + i][threadIdx.x]);
+    }
     const double ga = mba * ea;  // absorption taubar (same for every cloud)
 
     // ---- reverse through the transfer; combined moments for the shared profile ----
@@ -209,13 +219,15 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
     if (nbe > 0) out[1] = gbe0;
     if (nba > 0) out[1 + nbe] = gba0;
   }
-  for (int i = 1; i < nbe; ++i) {
-    double g = warp_sum(s_gb[i][threadIdx.x]);
-    if (lane == 0) out[1 + i] = g;
-  }
-  for (int i = 1; i < nba; ++i) {
-    double g = warp_sum(s_gb[CHI_MAX_BASELINE + i][threadIdx.x]);
-    if (lane == 0) out[1 + nbe + i] = g;
+  if (!SB) {
+    for (int i = 1; i < nbe; ++i) {
+      double g = warp_sum(s_gb[i][threadIdx.x]);
+      if (lane == 0) out[1 + i] = g;
+    }
+    for (int i = 1; i < nba; ++i) {
+      double g = warp_sum(s_gb[CHI_MAX_BASELINE + i][threadIdx.x]);
+      if (lane == 0) out[1 + nbe + i] = g;
+    }
   }
   double* om_ = out + 1 + nbe + nba;
 #pragma unroll
