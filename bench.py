@@ -46,6 +46,9 @@ def workload_name(draws):
 # --------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------
+NCU_DRAM_BYTES_PER_DRAW = 8087296.0 / 20000.0  # k_moments_ea<4,0,1>, profiles/r1c_ncu_full_summary.txt
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML (nvidia_ml_py) from a thread while the
     timed region runs; falls back to one `nvidia-smi` query when NVML is unavailable."""
@@ -414,7 +417,11 @@ def run_b200(args):
                                         "MEASURED_PEAKS.json has no CUDA-core FP64 figure",
                          "flops_per_unit": flops_unit, "units_per_launch": draws * N * S_E,
                          "unit_of_launch": "draw*cloud*channel-pair" if fused else "draw*cloud*channel",
-                         "traffic": None,
+                         # dram__bytes_read+write of this kernel from the ncu --set full capture in
+                         # profiles/ (20000 draws per launch: 8.09 MB read, writes absorbed by L2),
+                         # scaled to this launch's draws
+                         "traffic": (NCU_DRAM_BYTES_PER_DRAW * draws) if fused else None,
+                         "traffic_source": "profiles/r1c_ncu_full_summary.txt" if fused else None,
                          "hbm": {"achieved": bytes_em / t_em / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_em / t_em / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},

@@ -14,7 +14,7 @@ with open(os.path.join(out, f"{tag}_ncu_full_summary.txt"), "w") as f:
     f.write(f"# ncu --set full --clock-control none, summary of {os.path.basename(rep)}\n")
     f.write("# command: python tools/profile_target.py (configs[1] shape, 20000 draws, one launch per kernel)\n")
     f.write(run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep]))
-    for k in ("k_moments_em", "k_moments_abs"):
+    for k in ("k_moments_ea", "k_moments_em", "k_moments_abs"):
         f.write("\n# dynamic opcode mix and hottest stall lines (ncu source page)\n")
         f.write(run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_hist.py"), rep, k]))
 
