@@ -134,7 +134,8 @@ struct CloudPhys {
   T velocity, fwhm2, fwhm_L, tau_total, tspin, ff, wt;
   // extras (dead code unless chi_deterministics asks for them)
   T tkin, log10_NHI, log10_nHI, log10_depth, fwhm2_thermal, fwhm2_nonthermal;
-  bool has_tspin, has_ff, has_wt, has_thermal;
+  T log10_n_alpha, depth, TB_fwhm, thermal_fraction;
+  bool has_tspin, has_ff, has_wt, has_thermal, has_TB, has_fraction;
 };
 
 // hi_physical_model.py:153-197
@@ -144,6 +145,7 @@ CHI_HD void physical_chain(const MapCfg& c, const T& nth_fwhm_1pc, const T& log1
   o.fwhm2_nonthermal = o.fwhm2 - o.fwhm2_thermal;
   // physics.calc_depth_nonthermal (physics.py:188) on sqrt(fwhm2_nonthermal)
   T depth = m_powc(m_sqrt(o.fwhm2_nonthermal) / nth_fwhm_1pc, c.inv_power);
+  o.depth = depth;
   o.log10_depth = m_log10(depth);
   o.log10_nHI = o.log10_NHI - o.log10_depth - CHI_PC_CM_LOG10;  // physics.py:225
   o.tspin = spin_temp(o.tkin, m_exp10(o.log10_nHI), m_exp10(log10_n_alpha));
@@ -157,7 +159,7 @@ CHI_HD void physical_chain(const MapCfg& c, const T& nth_fwhm_1pc, const T& log1
 template <int MODEL, class T, bool WANT_ALL = false>
 CHI_HD CloudPhys<T> cloud_phys(const MapCfg& c, const T* th) {
   CloudPhys<T> o;
-  o.has_tspin = o.has_ff = o.has_wt = o.has_thermal = false;
+  o.has_tspin = o.has_ff = o.has_wt = o.has_thermal = o.has_TB = o.has_fraction = false;
   o.ff = T(1.0);
   o.wt = T(1.0);
   o.tspin = T(0.0);
@@ -176,6 +178,7 @@ CHI_HD CloudPhys<T> cloud_phys(const MapCfg& c, const T* th) {
     o.fwhm2 = c.prior_fwhm2 * th[CHI_FR_FWHM2_NORM];
     o.velocity = c.pv0 + c.pv1 * th[CHI_FR_VELOCITY_NORM];
     T log10_n_alpha = c.pa0 + c.pa1 * th[CHI_FR_LOG10_N_ALPHA_NORM];
+    if constexpr (WANT_ALL) o.log10_n_alpha = log10_n_alpha;
     o.fwhm_L = c.lorentzian ? T(c.prior_fwhm_L * th[CHI_FR_FWHM_L_NORM]) : T(0.0);
     constexpr bool physical = (MODEL >= CHI_MODEL_ABSORPTION_PHYSICAL);
     if constexpr (!physical) o.log10_nHI = c.pn0 + c.pn1 * th[CHI_FR_LOG10_NHI_NORM];
@@ -191,6 +194,10 @@ CHI_HD CloudPhys<T> cloud_phys(const MapCfg& c, const T* th) {
     } else if constexpr (MODEL == CHI_MODEL_EMISSION || MODEL == CHI_MODEL_EMISSION_ABSORPTION) {
       // emission_model.py:60-132
       T TB_fwhm = c.prior_amp * th[CHI_FR_AMPLITUDE_NORM];
+      if constexpr (WANT_ALL) {
+        o.TB_fwhm = TB_fwhm;
+        o.has_TB = true;
+      }
       T root = m_sqrt(o.fwhm2);
       T tkin_min = TB_fwhm / root;
       T tkin_max = o.fwhm2 / (CHI_THERMAL_CONST * CHI_THERMAL_CONST);
@@ -223,6 +230,10 @@ CHI_HD CloudPhys<T> cloud_phys(const MapCfg& c, const T* th) {
       T frac_min = (CHI_THERMAL_CONST * CHI_THERMAL_CONST) * tkin_min / o.fwhm2;
       T frac = m_select(m_value(frac_min) > 1.0, T(1.0),
                         T(th[CHI_FR_THERMAL] * (1.0 - frac_min) + frac_min));
+      if constexpr (WANT_ALL) {
+        o.thermal_fraction = frac;
+        o.has_fraction = true;
+      }
       o.fwhm2_thermal = o.fwhm2 * frac;
       o.tkin = o.fwhm2_thermal / (CHI_THERMAL_CONST * CHI_THERMAL_CONST);
       T ff_min = tkin_min / o.tkin;

@@ -520,6 +520,10 @@ __global__ void __launch_bounds__(128) k_deterministics(MapCfg cfg, int64_t B, i
       o[CHI_DET_LOG10_NHI] = ph.log10_NHI;
       o[CHI_DET_LOG10_DEPTH] = ph.log10_depth;
     }
+    o[CHI_DET_LOG10_N_ALPHA] = ph.log10_n_alpha;
+    if (ph.has_TB) o[CHI_DET_TB_FWHM] = ph.TB_fwhm;
+    if (ph.has_fraction) o[CHI_DET_FWHM2_THERMAL_FRACTION] = ph.thermal_fraction;
+    if (ph.has_thermal) o[CHI_DET_DEPTH] = ph.depth;  // hi_physical_model.py:163
     o[CHI_DET_LOG10_PTH] = log10(ph.tkin) + ph.log10_nHI;  // hi_model.py:143, hi_physical_model.py:202
     if (ph.has_thermal) {
       o[CHI_DET_FWHM2_THERMAL] = ph.fwhm2_thermal;

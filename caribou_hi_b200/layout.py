@@ -68,6 +68,10 @@ DET_NAMES = [
     "log10_Pth",
     "log10_Pnth",
     "log10_Ptot",
+    "log10_n_alpha",
+    "depth",
+    "TB_fwhm",
+    "fwhm2_thermal_fraction",
 ]
 
 

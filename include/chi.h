@@ -100,7 +100,7 @@ enum {
 
 /* Per-cloud derived quantities written by chi_deterministics (the reference's
  * pm.Deterministic nodes), det[B][CHI_NDET][N]. NaN where a model lacks one. */
-#define CHI_NDET 16
+#define CHI_NDET 20
 enum {
   CHI_DET_VELOCITY = 0,
   CHI_DET_FWHM2 = 1,
@@ -117,7 +117,11 @@ enum {
   CHI_DET_FWHM2_NONTHERMAL = 12,
   CHI_DET_LOG10_PTH = 13,
   CHI_DET_LOG10_PNTH = 14,
-  CHI_DET_LOG10_PTOT = 15
+  CHI_DET_LOG10_PTOT = 15,
+  CHI_DET_LOG10_N_ALPHA = 16,
+  CHI_DET_DEPTH = 17,                 /* pc; physical models (hi_physical_model.py:163) */
+  CHI_DET_TB_FWHM = 18,               /* emission models (emission_model.py:66) */
+  CHI_DET_FWHM2_THERMAL_FRACTION = 19 /* emission physical models (emission_physical_model.py:81) */
 };
 
 typedef struct chi_config {

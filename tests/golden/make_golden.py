@@ -1,8 +1,8 @@
 """Generates tests/golden/*.npz: seeded inputs and the CPU oracle's outputs (logp, gradients
 by torch autograd, predicted spectra, deterministics) for every model class x {Gaussian,
-pseudo-Voigt}.  The reference itself (PyTensor/PyMC) cannot be imported in this image, so
-these vectors pin the ORACLE (guarding it against drift) and give the GPU tests fixed
-cases; they are not outputs of the reference program ("parity unpinned", oracle/__init__.py).
+pseudo-Voigt}.  These vectors guard the ORACLE against drift and give the GPU tests further
+fixed cases; the vectors produced by the reference's own source are the `ref_*` files made by
+make_golden_ref.py.
 
     python tests/golden/make_golden.py
 """
