@@ -192,12 +192,15 @@ def time_c_oracle(sample_draws, steps, warmup, min_seconds=0.0):
     det = mr.cloud_inputs(spec, free)
     det = {k: np.ascontiguousarray(np.broadcast_to(det[k], free["fwhm2_norm"].shape)) for k in c_oracle.INPUTS}
     cores = 1
+    # every host thread this process may use, stated explicitly: torchrun exports
+    # OMP_NUM_THREADS=1 to its workers, which would time a single-threaded baseline
+    n_thr = len(os.sched_getaffinity(0))
     for _ in range(warmup):
-        cores = c_oracle.logp_grad(data, det, spec["bg_temp"])[2]
+        cores = c_oracle.logp_grad(data, det, spec["bg_temp"], n_threads=n_thr)[2]
     t0 = time.perf_counter()
     done = 0
     while done < steps or (time.perf_counter() - t0) < min_seconds:
-        c_oracle.logp_grad(data, det, spec["bg_temp"])
+        c_oracle.logp_grad(data, det, spec["bg_temp"], n_threads=n_thr)
         done += 1
     dt = time.perf_counter() - t0
     units = sample_draws * N_CLOUDS * (S_E + S_A)
@@ -295,15 +298,32 @@ def run_b200(args):
     gathered = torch.empty((world, 1 + 10 * N), dtype=torch.float64, device=dev) if world > 1 else None
     torch.cuda.synchronize()
 
+    # the exchange of step i runs on its own stream next to the kernels of step i+1
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_done = [torch.cuda.Event() for _ in range(N_SETS)]   # kernels of buffer set k finished
+    ev_read = [torch.cuda.Event() for _ in range(N_SETS)]   # exchange has read buffer set k
+    read_pending = [False] * N_SETS
+
     def step(i, exchange=True):
         k = i % N_SETS
+        if read_pending[k]:
+            stream.wait_event(ev_read[k])  # do not overwrite outputs the exchange still reads
+            read_pending[k] = False
         eng.logp_grad_dev(draws, th_d[k], lp_d[k], gr_d[k], coeff_e=ce_d, coeff_a=ca_d, gcoeff_e=gce_d, gcoeff_a=gca_d)
         if world > 1 and exchange:
             # the only collective of the path: gather per-shard logp and gradient sums
-            with torch.cuda.stream(stream):
+            ev_done[k].record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_done[k])
                 summary = torch.cat([torch.nan_to_num(lp_d[k]).sum().reshape(1),
                                      torch.nan_to_num(gr_d[k]).sum(dim=0).reshape(-1)])
                 dist.all_gather_into_tensor(gathered, summary)
+                ev_read[k].record(side)
+            read_pending[k] = True
+
+    def join_side():
+        if side is not None:
+            stream.wait_stream(side)  # the timed region ends after the last exchange
 
     def barrier():
         eng.synchronize()
@@ -326,6 +346,7 @@ def run_b200(args):
     e0.record(stream)
     for i in range(args.steps):
         step(i)
+    join_side()
     e1.record(stream)
     barrier()
     t_end = time.perf_counter()
@@ -403,7 +424,7 @@ def run_b200(args):
             "config": {"workload": workload_name(draws), "units_per_step_per_gpu": units_step,
                        "l2": f"inputs/outputs rotated over {N_SETS} buffer sets ({N_SETS * 65} MB > 126 MB L2)",
                        "parallelism": f"draws sharded over {world} GPU(s), one process per GPU"
-                                      + ("; per-step NCCL all_gather of per-shard logp/grad sums" if world > 1 else "")},
+                                      + ("; per-step NCCL all_gather of per-shard logp/grad sums on a side stream, overlapping the next step" if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": world * units_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,
