@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("CHI_LIB") or os.path.join(_HERE, "libchi.so")
 CHI_VERSION = 100
 CHI_NSLOT = 10
 CHI_NDET = 20
-CHI_MAX_CLOUDS = 8
+CHI_MAX_CLOUDS = 16
 CHI_MAX_BASELINE = 8
 
 MODEL_PHYSICS = 0

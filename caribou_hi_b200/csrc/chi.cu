@@ -137,8 +137,13 @@ bool kind_has_absorption(int m) {
          m == CHI_MODEL_ABSORPTION_PHYSICAL || m == CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL;
 }
 
-int em_record(const chi_handle* h) { return 1 + h->e.nb + h->cfg.n_clouds * (h->cfg.lorentzian ? 8 : 5); }
-int ab_record(const chi_handle* h) { return 1 + h->a.nb + h->cfg.n_clouds * (h->cfg.lorentzian ? 6 : 3); }
+// moment records are sized for the (possibly padded) instantiation that runs
+int em_record(const chi_handle* h) {
+  return 1 + h->e.nb + padded_clouds(h->cfg.n_clouds) * (h->cfg.lorentzian ? 8 : 5);
+}
+int ab_record(const chi_handle* h) {
+  return 1 + h->a.nb + padded_clouds(h->cfg.n_clouds) * (h->cfg.lorentzian ? 6 : 3);
+}
 
 // channel chunking: enough warps to fill the machine when B is small
 void pick_chunks(const chi_handle* h, int64_t B, int S, int* n_chunks, int* chunk_len) {
@@ -214,7 +219,8 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     memset(&a, 0, sizeof(a));
     a.B = B; a.S = h->e.S; a.nb_e = h->e.nb; a.nb_a = h->a.nb; a.bg = h->cfg.bg_temp;
     pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
-    a.mom_stride = 1 + a.nb_e + a.nb_a + N * (pv ? 10 : 6);
+    a.n_real = N;
+    a.mom_stride = 1 + a.nb_e + a.nb_a + padded_clouds(N) * (pv ? 10 : 6);
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.chan = h->chan.d();
     a.basis_e = h->e.basis.d(); a.coeff_e = ce;
@@ -235,7 +241,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   if (do_e && !fused_done) {
     ChanArgs a;
     memset(&a, 0, sizeof(a));
-    a.B = B; a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp;
+    a.B = B; a.S = h->e.S; a.n_base = h->e.nb; a.n_real = N; a.bg = h->cfg.bg_temp;
     pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = em_record(h);
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
@@ -255,7 +261,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   if (do_a && !fused_done) {
     ChanArgs a;
     memset(&a, 0, sizeof(a));
-    a.B = B; a.S = h->a.S; a.n_base = h->a.nb; a.bg = 0.0;
+    a.B = B; a.S = h->a.S; a.n_base = h->a.nb; a.n_real = N; a.bg = 0.0;
     pick_chunks(h, B, a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = ab_record(h);
     CK(L.mom_a.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
@@ -279,7 +285,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   // small batches are bound by the dependent chain of the per-cloud map: split the tangent
   // directions over threads; large batches take the fused form (half the arithmetic)
   const int K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
-  if (B * N * K <= (int64_t)h->n_sm * 1024) {
+  if (B * N * K <= (int64_t)h->n_sm * 1024 && N * K <= 128) {
     unsigned grid = (unsigned)((B * N * K + 127) / 128);
     if (model) {  // whole draws per block
       const int per = N * K, bd = (128 / per) * per;

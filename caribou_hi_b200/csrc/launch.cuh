@@ -28,6 +28,9 @@ int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st);
 int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st);
 int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st);
 
+// cloud count of the instantiation that serves a model with N clouds
+inline int padded_clouds(int N) { return N <= 8 ? N : (N <= 12 ? 12 : 16); }
+
 inline unsigned warp_grid(const ChanArgs& a) {
   int64_t items = a.B * a.n_chunks;
   return (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);

@@ -21,11 +21,15 @@ int launch_moments_ea_sb(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
 #else
 int launch_moments_ea_gb(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
 #endif
+  N = padded_clouds(N);
   switch (N * 2 + (pv ? 1 : 0)) {
 #define CASE(n)                           \
   case (n)*2: run<n, false>(a, st); return 0; \
   case (n)*2 + 1: run<n, true>(a, st); return 0;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#if !CHI_EA_SB
+    CASE(12) CASE(16)  // N = 9..16 run padded on these (general-baseline half only)
+#endif
 #undef CASE
   }
   return -1;
@@ -34,7 +38,7 @@ int launch_moments_ea_gb(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
 #if CHI_EA_SB
 int launch_moments_ea_gb(int N, bool pv, const FusedArgs& a, cudaStream_t st);
 int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
-  return (a.nb_e <= 1 && a.nb_a <= 1) ? launch_moments_ea_sb(N, pv, a, st) : launch_moments_ea_gb(N, pv, a, st);
+  return (a.nb_e <= 1 && a.nb_a <= 1 && N <= 8) ? launch_moments_ea_sb(N, pv, a, st) : launch_moments_ea_gb(N, pv, a, st);
 }
 #endif
 }  // namespace chi

@@ -14,8 +14,12 @@ __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
   __shared__ double s_beta[CHI_MAX_BASELINE];
   __shared__ double s_T[CHI_EXP_TABLE];
   const int64_t b = blockIdx.x;
-  if (threadIdx.x < N) {
-    const double* p = a.cc + (b * N + threadIdx.x) * CHI_CC_STRIDE;
+  if (threadIdx.x >= a.N && threadIdx.x < N) {  // null cloud of a padded instantiation
+    double* d = s_c[threadIdx.x];
+    d[0] = 0.0; d[1] = -1.0; d[2] = 0.0; d[3] = 0.0; d[4] = 1.0; d[5] = d[6] = d[7] = 0.0;
+  }
+  if (threadIdx.x < a.N) {
+    const double* p = a.cc + (b * a.N + threadIdx.x) * CHI_CC_STRIDE;
     double* d = s_c[threadIdx.x];
     d[0] = p[CC_C];
     if (EMISSION) {
@@ -73,11 +77,12 @@ static void run(const SpecArgs& a, cudaStream_t st) {
 }
 
 int launch_spectra(int N, bool pv, const SpecArgs& a, cudaStream_t st) {
+  N = padded_clouds(N);
   switch (N * 2 + (pv ? 1 : 0)) {
 #define CASE(n)                           \
   case (n)*2: run<n, false>(a, st); return 0; \
   case (n)*2 + 1: run<n, true>(a, st); return 0;
-    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(12) CASE(16)
 #undef CASE
   }
   return -1;

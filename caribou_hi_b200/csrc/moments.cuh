@@ -188,6 +188,8 @@ struct ChanArgs {
   int64_t B;
   int S;            // channels of this dataset
   int n_base;       // baseline terms
+  int n_real;       // clouds of the model; the template N may be larger (N > 8 runs on the 12- and
+                    // 16-cloud instantiations, padded with null clouds: tau = 0, f = 0)
   int n_chunks;     // channel chunks per draw
   int chunk_len;    // channels per chunk (multiple of 32)
   int mom_stride;   // doubles per (draw, chunk) record
@@ -255,12 +257,15 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
   const int chunk = (int)(item - b * a.n_chunks);
   const int nb = a.n_base, S = a.S;
 
-  if (lane < N) {
-    const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
+  if (lane < a.n_real) {
+    const double* p = a.cc + (b * a.n_real + lane) * CHI_CC_STRIDE;
     const double f = p[CC_F], ts = p[CC_TS];
     double* d = s_c[warp][lane];
     d[0] = p[CC_C]; d[1] = -CHI_LOG2E * p[CC_KE]; d[2] = -CHI_LOG2E * p[CC_AGE]; d[3] = f * ts;
     d[4] = f; d[5] = ts; d[6] = -CHI_LOG2E * p[CC_ALE]; d[7] = p[CC_HE];
+  } else if (lane < N) {  // null cloud
+    double* d = s_c[warp][lane];
+    d[0] = 0.0; d[1] = -1.0; d[2] = 0.0; d[3] = 0.0; d[4] = 0.0; d[5] = 0.0; d[6] = 0.0; d[7] = 1.0;
   }
   if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
   if (!SB)
@@ -409,12 +414,15 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
   const int chunk = (int)(item - b * a.n_chunks);
   const int nb = a.n_base, S = a.S;
 
-  if (lane < N) {
-    const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
+  if (lane < a.n_real) {
+    const double* p = a.cc + (b * a.n_real + lane) * CHI_CC_STRIDE;
     double* d = s_c[warp][lane];
     d[0] = p[CC_C]; d[1] = -CHI_LOG2E * p[CC_KA]; d[2] = -CHI_LOG2E * p[CC_AGA];
     d[3] = -CHI_LOG2E * p[CC_ALA]; d[4] = p[CC_HA];
     d[5] = 0.0;
+  } else if (lane < N) {  // null cloud
+    double* d = s_c[warp][lane];
+    d[0] = 0.0; d[1] = -1.0; d[2] = 0.0; d[3] = 0.0; d[4] = 1.0; d[5] = 0.0;
   }
   if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
   if (!SB)

@@ -27,6 +27,7 @@ struct FusedArgs {
   int64_t B;
   int S;
   int nb_e, nb_a;
+  int n_real;                          // clouds of the model (<= template N, see ChanArgs::n_real)
   int n_chunks, chunk_len, mom_stride;
   double bg;
   const double* __restrict__ chan;     // [n_sl][ceil(S/32)][8][32] packed channel data (see above)
@@ -74,8 +75,13 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
   const int chunk = (int)(item - b * a.n_chunks);
   const int nbe = a.nb_e, nba = a.nb_a, S = a.S;
 
-  if (lane < N) {
-    const double* p = a.cc + (b * N + lane) * CHI_CC_STRIDE;
+  if (lane >= a.n_real && lane < N) {  // null cloud
+    double* d = s_c[warp][lane];
+    for (int i = 0; i < 12; ++i) d[i] = 0.0;
+    d[1] = -1.0; d[10] = 1.0;
+  }
+  if (lane < a.n_real) {
+    const double* p = a.cc + (b * a.n_real + lane) * CHI_CC_STRIDE;
     const double f = p[CC_F], ts = p[CC_TS];
     double* d = s_c[warp][lane];
     const double age = -CHI_LOG2E * p[CC_AGE], ale = -CHI_LOG2E * p[CC_ALE];

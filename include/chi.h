@@ -146,7 +146,7 @@ typedef struct chi_config {
                                    prior_ff_NHI, by model kind */
 } chi_config;
 
-#define CHI_MAX_CLOUDS 8
+#define CHI_MAX_CLOUDS 16
 #define CHI_MAX_BASELINE 8
 
 /* One dataset ("emission" or "absorption") of a bayes_spec SpecData dict, for

@@ -55,9 +55,20 @@ def test_logp_grad_spectra_all_models(cuda_device, kind, lorentzian):
     assert n_ok >= 32  # most prior draws must be finite, otherwise the test is vacuous
 
 
-@pytest.mark.parametrize("N", [1, 2, 4, 5, 8])
+@pytest.mark.parametrize("N", [1, 2, 4, 5, 8, 9, 12, 13, 16])
 def test_cloud_counts(cuda_device, N):
+    """N > 8 runs on the 12- / 16-cloud instantiations padded with null clouds."""
     _check_case("emission_absorption_physical", N, 257, 131, 16, seed=100 + N, lorentzian=(N % 2 == 0))
+
+
+@pytest.mark.parametrize("kind,N,shared", [("emission_absorption", 11, True), ("emission", 10, False),
+                                           ("absorption_physical", 14, False), ("emission_absorption_physical", 16, True)])
+def test_many_clouds_other_paths(cuda_device, kind, N, shared):
+    """Padded cloud slots on the fused kernel, the single-dataset kernels and the model-level
+    (prior) epilogue."""
+    from oracle import priors_ref as pr
+
+    _check_case(kind, N, 200, 200, 12, seed=300 + N, lorentzian=(N % 2 == 1), shared_axis=shared)
 
 
 @pytest.mark.parametrize("kind", ["emission_absorption", "emission_absorption_physical"])
@@ -290,7 +301,7 @@ def test_error_behaviour(cuda_device):
     from caribou_hi_b200._lib import ChiError
 
     with pytest.raises(ChiError):
-        Engine("emission", 9)  # > CHI_MAX_CLOUDS
+        Engine("emission", 17)  # > CHI_MAX_CLOUDS
     eng = Engine("emission", 2)
     with pytest.raises(ChiError):  # spectra not set
         eng.logp_grad(np.zeros((1, 10, 2)))
