@@ -117,6 +117,8 @@ SYMBOLS = {
     "chi_radiative_transfer_vjp": (C.c_int, [_H, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp]),
     "chi_logp_grad": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp]),
     "chi_logp_grad_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 8),
+    "chi_logp_grad_rows": (C.c_int, [_H, C.c_int64, C.c_int32, _ip, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp]),
+    "chi_logp_grad_rows_dev": (C.c_int, [_H, C.c_int64, C.c_int32, _ip] + [C.c_void_p] * 8),
     "chi_spectra": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
     "chi_spectra_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 5),
     "chi_spectra_vjp": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

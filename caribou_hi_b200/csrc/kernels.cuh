@@ -28,8 +28,17 @@ namespace chi {
 // `constrained` != null: theta holds UNCONSTRAINED values (PyMC's value variables); they are
 // mapped back through the default transforms first and the constrained values are kept for
 // the epilogue.
+// Layout of the caller's theta / grad blocks: [B][n_rows][N]; row[s] is the row that holds slot
+// s, -1 = the caller does not carry that slot (reads as 0, its gradient is dropped).  The slot
+// layout [B][CHI_NSLOT][N] is the identity map; the packed form carries only the free RVs a
+// model kind has (chi_logp_grad_rows: fewer bytes over PCIe).
+struct RowMap {
+  int n_rows;
+  signed char row[CHI_NSLOT];
+};
+
 template <int MODEL>
-__global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, int64_t B, int N,
+__global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, RowMap rm, int64_t B, int N,
                                                    const double* __restrict__ theta,
                                                    double* __restrict__ cc,
                                                    double* __restrict__ constrained) {
@@ -38,9 +47,9 @@ __global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, int64_t B, int N,
   int64_t b = t / N;
   int n = (int)(t - b * N);
   double th[CHI_NSLOT];
-  const double* tp = theta + (b * CHI_NSLOT) * N + n;
+  const double* tp = theta + (b * rm.n_rows) * N + n;
 #pragma unroll
-  for (int s = 0; s < CHI_NSLOT; ++s) th[s] = tp[(int64_t)s * N];
+  for (int s = 0; s < CHI_NSLOT; ++s) th[s] = rm.row[s] >= 0 ? tp[(int64_t)rm.row[s] * N] : 0.0;
   if (constrained) {
     double* xp = constrained + (b * CHI_NSLOT) * N + n;
 #pragma unroll
@@ -71,6 +80,7 @@ __global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, int64_t B, int N,
 struct EpiArgs {
   int64_t B;
   int N;
+  RowMap rm;  // layout of theta and grad (identity in model mode)
   int pv;
   int has_e, has_a;
   int nb_e, nb_a;
@@ -197,10 +207,10 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   // --- Jacobian of the per-cloud map by forward-mode duals ---
   typedef Dual<KD> D;
   D th[CHI_NSLOT];
-  const double* tp = a.theta + (b * CHI_NSLOT) * a.N + n;
+  const double* tp = a.theta + (b * a.rm.n_rows) * a.N + n;
 #pragma unroll
   for (int s = 0; s < CHI_NSLOT; ++s) {
-    th[s] = D(tp[(int64_t)s * a.N]);
+    th[s] = D(a.rm.row[s] >= 0 ? tp[(int64_t)a.rm.row[s] * a.N] : 0.0);
 #pragma unroll
     for (int i = 0; i < KD; ++i) th[s].d[i] = (s == j0 + i) ? 1.0 : 0.0;
   }
@@ -296,11 +306,13 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
   }
   if (!a.grad || !valid) return;
 
-  double* go = a.grad + (b * CHI_NSLOT) * a.N + n;
+  double* go = a.grad + (b * a.rm.n_rows) * a.N + n;
 #pragma unroll
-  for (int i = 0; i < KD; ++i) go[(int64_t)(j0 + i) * a.N] = g[i];
+  for (int i = 0; i < KD; ++i)
+    if (a.rm.row[j0 + i] >= 0) go[(int64_t)a.rm.row[j0 + i] * a.N] = g[i];
   if (j0 == 0)
-    for (int s = K; s < CHI_NSLOT; ++s) go[(int64_t)s * a.N] = 0.0;  // slots the model kind does not use
+    for (int s = K; s < CHI_NSLOT; ++s)  // slots the model kind does not use
+      if (a.rm.row[s] >= 0) go[(int64_t)a.rm.row[s] * a.N] = 0.0;
 }
 
 // unconstrained <-> constrained values of the free RVs (direction = +1: u -> x, -1: x -> u)

@@ -248,6 +248,67 @@ class Engine:
         )
         return logp, grad, gce, gca
 
+    # ---- packed rows: only the free RVs the model kind has ---------------------
+    @property
+    def row_slots(self):
+        """Slots of the model kind's free RVs in ascending order: the rows of the packed
+        blocks ``[B, len(row_slots), N]`` taken by :meth:`logp_grad_rows`."""
+        return np.array(sorted(self.slots.values()), dtype=np.int32)
+
+    def pack_rows(self, rvs, B=None):
+        """Like :meth:`pack` but ``[B, n_rows, N]`` with only the rows in :attr:`row_slots`."""
+        return np.ascontiguousarray(self.pack(rvs, B)[:, self.row_slots, :])
+
+    def unpack_rows(self, rows):
+        """``rows [B, n_rows, N]`` (values or gradients) -> dict keyed by RV name; per-draw scalar
+        RVs are summed over clouds."""
+        scal = layout.scalar_rvs(self.kind)
+        index = {int(s): r for r, s in enumerate(self.row_slots)}
+        out = {}
+        for name, slot in self.slots.items():
+            g = rows[:, index[slot], :]
+            out[name] = g.sum(axis=1, keepdims=True) if name in scal else g
+        return out
+
+    def logp_grad_rows(self, rows, coeff_e=None, coeff_a=None, sightline=None, want_grad=True, out=None):
+        """:meth:`logp_grad` on packed blocks (C ABI ``chi_logp_grad_rows``): ``rows`` and the
+        returned gradient are ``[B, len(row_slots), N]`` -- 10-40 % fewer bytes over PCIe."""
+        N = self.n_clouds
+        slots = self.row_slots
+        rows = _f64(rows)
+        if rows.ndim != 3 or rows.shape[1:] != (slots.size, N):
+            raise ValueError(f"rows: expected [B, {slots.size}, {N}], got {rows.shape}")
+        B = rows.shape[0]
+        ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
+        ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
+        sl = None
+        if sightline is not None:
+            sl = np.ascontiguousarray(sightline, dtype=np.int32)
+            if sl.shape != (B,):
+                raise ValueError("sightline: expected [B]")
+        out = out or {}
+        logp = out.get("logp")
+        if logp is None:
+            logp = np.empty(B, dtype=np.float64)
+        grad = gce = gca = None
+        if want_grad:
+            grad = out.get("grad")
+            if grad is None:
+                grad = np.empty((B, slots.size, N), dtype=np.float64)
+            if self.nb_e:
+                gce = out.get("gcoeff_e")
+                gce = np.empty((B, self.nb_e), dtype=np.float64) if gce is None else gce
+            if self.nb_a:
+                gca = out.get("gcoeff_a")
+                gca = np.empty((B, self.nb_a), dtype=np.float64) if gca is None else gca
+        self._check(
+            self._lib.chi_logp_grad_rows(
+                self._h, B, int(slots.size), _lib.as_ip(slots), _lib.as_dp(rows), _lib.as_dp(ce), _lib.as_dp(ca),
+                _lib.as_ip(sl), _lib.as_dp(logp), _lib.as_dp(grad), _lib.as_dp(gce), _lib.as_dp(gca),
+            )
+        )
+        return logp, grad, gce, gca
+
     def spectra(self, theta, coeff_e=None, coeff_a=None):
         """Predicted spectra ``(mu_e [B, S_e] | None, mu_a [B, S_a] | None)``."""
         N = self.n_clouds
@@ -402,6 +463,16 @@ class Engine:
         self._check(
             self._lib.chi_logp_grad_dev(self._h, int(B), p(theta), p(coeff_e), p(coeff_a), p(sightline),
                                         p(logp), p(grad), p(gcoeff_e), p(gcoeff_a))
+        )
+
+    def logp_grad_rows_dev(self, B, rows, logp, grad=None, coeff_e=None, coeff_a=None, sightline=None,
+                           gcoeff_e=None, gcoeff_a=None):
+        """:meth:`logp_grad_dev` on packed device blocks ``[B, len(row_slots), N]``."""
+        p = self._ptr
+        slots = self.row_slots
+        self._check(
+            self._lib.chi_logp_grad_rows_dev(self._h, int(B), int(slots.size), _lib.as_ip(slots), p(rows), p(coeff_e),
+                                             p(coeff_a), p(sightline), p(logp), p(grad), p(gcoeff_e), p(gcoeff_a))
         )
 
     def spectra_dev(self, B, theta, mu_e=None, mu_a=None, coeff_e=None, coeff_a=None):

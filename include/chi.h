@@ -249,6 +249,21 @@ int chi_logp_grad_dev(chi_handle* h, int64_t B, const double* theta, const doubl
                       const double* coeff_a, const int32_t* sightline, double* logp_out,
                       double* grad_out, double* gcoeff_e, double* gcoeff_a);
 
+/* Packed form of chi_logp_grad[_dev]: the caller's blocks carry only the rows it needs,
+ * rows[B][n_rows][N] with row r holding slot slot_of_row[r] (distinct slots; a slot that is not
+ * listed reads as 0 and its gradient is dropped), grad_rows[B][n_rows][N] likewise.  A model kind
+ * has 6-9 free RVs per cloud, so listing exactly those (Engine.row_slots in the Python host
+ * side) moves 10-40 % fewer bytes over PCIe than the CHI_NSLOT-row block.  Replaces the same
+ * reference call as chi_logp_grad (PyMC's logp_dlogp_function over the free RVs). */
+int chi_logp_grad_rows(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* slot_of_row,
+                       const double* rows, const double* coeff_e, const double* coeff_a,
+                       const int32_t* sightline, double* logp_out, double* grad_rows_out,
+                       double* gcoeff_e_out, double* gcoeff_a_out);
+int chi_logp_grad_rows_dev(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* slot_of_row,
+                           const double* rows, const double* coeff_e, const double* coeff_a,
+                           const int32_t* sightline, double* logp_out, double* grad_rows_out,
+                           double* gcoeff_e_out, double* gcoeff_a_out);
+
 /* Predicted spectra mu_e[B][S_e], mu_a[B][S_a] (baseline included): the `mu` of
  * the pm.Normal nodes, i.e. what sample_posterior_predictive evaluates per draw.
  * Either output may be NULL. */
