@@ -918,10 +918,22 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
     if (pieces > 0 && B >= 8192) sub = std::min<int64_t>(cap, std::max<int64_t>(4096, (B + pieces - 1) / pieces));
     for (int64_t b0 = 0; b0 < B; b0 += sub) sizes.push_back(std::min(sub, B - b0));
   } else {
-    const int den[9] = {24, 12, 8, 6, 6, 6, 8, 12, 24};
+    std::vector<double> den = {24, 12, 8, 6, 6, 6, 8, 12, 24};
+    if (const char* e = getenv("CHI_PIPE_RAMP")) {  // tuning knob: comma-separated denominators
+      den.clear();
+      for (const char* c = e; *c;) {
+        char* end = nullptr;
+        const double v = strtod(c, &end);
+        if (end == c) break;
+        if (v >= 1.0) den.push_back(v);
+        c = (*end == ',') ? end + 1 : end;
+      }
+      if (den.empty()) den.push_back(1.0);
+    }
+    const int nd = (int)den.size();
     int64_t left = B;
-    for (int i = 0; i < 9 && left > 0; ++i) {
-      int64_t want = (i == 8) ? left : std::min<int64_t>(left, ((B / den[i]) + 255) / 256 * 256);
+    for (int i = 0; i < nd && left > 0; ++i) {
+      int64_t want = (i == nd - 1) ? left : std::min<int64_t>(left, ((int64_t)(B / den[i]) + 255) / 256 * 256);
       while (want > 0) {  // honour the workspace cap
         const int64_t nb = std::min(want, cap);
         sizes.push_back(nb);

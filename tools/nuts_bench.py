@@ -28,5 +28,9 @@ def run(cls, N, S_e, S_a, chains, tune, draws, **priors):
           f"divergent {stats['diverging'].mean():.3f}, launches {model.engine.launch_count()-l0}", flush=True)
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # many chains in lock step: python tools/nuts_bench.py <chains> [tune draws]
+        c = int(sys.argv[1]); t = int(sys.argv[2]) if len(sys.argv) > 2 else 200; d = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+        run(EmissionAbsorptionModel, 2, 334, 166, c, t, d)
+        sys.exit(0)
     run(EmissionAbsorptionModel, 2, 334, 166, 8, 500, 500)
     run(EmissionAbsorptionPhysicalModel, 8, 2048, 2048, 64, 200, 200, prior_fwhm_L=1.0)
