@@ -439,3 +439,49 @@ def test_packed_rows_entry_points(cuda_device):
             eng._check(eng._lib.chi_logp_grad_rows(eng._h, 1, 2, np.array([1, 1], dtype=np.int32).ctypes.data_as(
                 __import__("ctypes").POINTER(__import__("ctypes").c_int32)), None, None, None, None, None, None, None, None))
         eng.close()
+
+
+@pytest.mark.parametrize("kind", ["emission", "emission_absorption", "emission_physical",
+                                  "emission_absorption_physical", "absorption", "absorption_physical"])
+def test_branch_edges_of_the_parameter_maps(cuda_device, kind):
+    """The switch / clip branches of add_priors (emission_model.py:82-132,
+    emission_physical_model.py:81-129), the Tk < 300 K switch of the spin temperature
+    (physics.py:95-101), optically thick clouds with f = 1, and fwhm_L = 0 under the
+    pseudo-Voigt profile: both sides of every branch must occur in the batch and match."""
+    B, N = 768, 3
+    spec, data, free, baseline = make_case(kind, N, 96, 64, B, seed=909, lorentzian=True)
+    rng = np.random.default_rng(910)
+    amp = [k for k in free if k in ("TB_fwhm_norm", "ff_NHI_norm", "tau_total_norm", "NHI_fwhm2_thermal_norm")][0]
+    free[amp] = free[amp] * 10 ** rng.uniform(-3, 3, size=(B, 1))          # sweeps tkin_min/ff_min/frac_min past 1
+    free["fwhm2_norm"] = free["fwhm2_norm"] * 10 ** rng.uniform(-2, 1, size=(B, 1))  # Tk on both sides of 300 K
+    for k in ("filling_factor_norm", "tkin_factor_norm", "fwhm2_thermal_fraction_norm"):
+        if k in free:  # exact interval ends: ff = ff_min makes the clip at 0.9999 active
+            free[k][: B // 8] = 0.0
+            free[k][B // 8 : B // 4] = 1.0
+    free["fwhm_L_norm"][B // 2 :: 7] = 0.0                                   # eta = 0 under the PV profile
+    det = mr.cloud_inputs(spec, free)
+    tk = np.broadcast_to(det["tkin"], (B, N))
+    assert (tk < 300).any() and (tk > 300).any()
+    if "filling_factor" in det and mr.has_emission(spec):
+        ff = np.broadcast_to(det["filling_factor"], (B, N))
+        assert (ff == 1.0).any() and (ff < 1.0).any()                        # ff_min > 1 and ff_min <= 1
+    ref_lp, ref_g = oracle_logp_grad(spec, data, free, baseline)
+    eng = engine_for(spec, data, 0)
+    lp, grad, _, _ = eng.logp_grad(eng.pack(free), baseline.get("baseline_emission_norm"),
+                                   baseline.get("baseline_absorption_norm"))
+    assert np.array_equal(np.isfinite(lp), np.isfinite(ref_lp))
+    fin = np.isfinite(ref_lp)
+    assert fin.sum() > B // 4
+    assert_close(lp, ref_lp, what=f"{kind} logp", axis=None)
+    got = eng.unpack_grad(grad)
+    names = sorted(got)
+    # amplitudes swept over six decades make some draws so ill-conditioned that fp64 autograd itself
+    # is 6e-10 off the 60-digit value (tests/test_oracle_arbiter.py::test_extreme_draw, where the
+    # CUDA number is the closer one): 2e-9 here, 1e-10 everywhere else
+    assert_close(np.concatenate([got[n][fin] for n in names], axis=1),
+                 np.concatenate([ref_g[n][fin] for n in names], axis=1), rtol=2e-9, what=f"{kind} grad")
+    d_dev = eng.deterministics(eng.pack(free))
+    for k in ("tkin", "tspin", "filling_factor", "tau_total"):
+        if k in det and k in d_dev:
+            assert_close(d_dev[k][fin], np.broadcast_to(det[k], (B, N))[fin], rtol=1e-12, what=k)
+    eng.close()
