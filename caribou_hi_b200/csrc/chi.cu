@@ -243,6 +243,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     a.B = B; a.S = h->e.S; a.nb_e = h->e.nb; a.nb_a = h->a.nb; a.bg = h->cfg.bg_temp;
     pick_chunks(h, std::max<int64_t>(B, h->call_draws), a.S, &a.n_chunks, &a.chunk_len);
     a.n_real = N;
+    a.staged = (h->n_sl > 1 && !getenv("CHI_NO_STAGED")) ? 1 : 0;
     a.mom_stride = 1 + a.nb_e + a.nb_a + padded_clouds(N) * (pv ? 10 : 6);
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.chan = h->chan.d();

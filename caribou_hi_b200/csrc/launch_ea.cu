@@ -37,7 +37,10 @@ int launch_moments_ea_gb(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
 
 #if CHI_EA_SB
 int launch_moments_ea_gb(int N, bool pv, const FusedArgs& a, cudaStream_t st);
+int launch_moments_ea_staged(int N, bool pv, const FusedArgs& a, cudaStream_t st);
 int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st) {
+  // per-draw sightlines (survey mode): no L1 reuse of the channel data -> staged pipeline
+  if (a.sl && a.staged && a.nb_e <= 1 && a.nb_a <= 1 && N <= 8) return launch_moments_ea_staged(N, pv, a, st);
   return (a.nb_e <= 1 && a.nb_a <= 1 && N <= 8) ? launch_moments_ea_sb(N, pv, a, st) : launch_moments_ea_gb(N, pv, a, st);
 }
 #endif

@@ -28,6 +28,7 @@ struct FusedArgs {
   int S;
   int nb_e, nb_a;
   int n_real;                          // clouds of the model (<= template N, see ChanArgs::n_real)
+  int staged;                          // 1: more than one sightline is loaded (survey mode)
   int n_chunks, chunk_len, mom_stride;
   double bg;
   const double* __restrict__ chan;     // [n_sl][ceil(S/32)][8][32] packed channel data (see above)
@@ -53,22 +54,64 @@ constexpr int ea_min_blocks(int N, bool pv) {
 // shared per cloud, fetched in pairs; ' = times log2(e) (arguments of chi_exp2).  The Gaussian case
 // reads A B C forward and A C D in reverse:
 //   A [c, -k']  B [-AG_e', f*Ts]  C [f, -AG_a']  D [Ts, -f AG_e']  E [-AL_e', -AL_a']  F [h, -f AL_e']
+// --- bulk async copy (TMA, 1-D) + mbarrier helpers of the STAGED channel pipeline -----------
+__device__ __forceinline__ void mbar_init(unsigned bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+// one lane: expect 2048 bytes on `bar`, then copy one packed channel group global -> shared
+__device__ __forceinline__ void tma_fetch(const double* src, unsigned dst, unsigned bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 2048;" ::"r"(bar) : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 2048, [%2];" ::"r"(dst),
+      "l"(src), "r"(bar)
+      : "memory");
+}
+// all lanes: wait for the phase with the given parity; a protocol error traps instead of hanging
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
 __device__ __forceinline__ void ldg2(const double* p, double& x, double& y) {
   const double2 t = __ldg(reinterpret_cast<const double2*>(p));
   x = t.x;
   y = t.y;
 }
 
-template <int N, bool PV, bool SB>
+// STAGED (survey mode, one spectrum pair per sightline): warps of a block read different
+// sightlines, so the channel data has no L1 reuse and every iteration's loads would be L2 / HBM
+// latency on the critical path.  Each warp then streams its sightline through a double buffer in
+// shared memory: one lane issues a 2 KB bulk async copy (cp.async.bulk, completion on an
+// mbarrier) for the NEXT channel group while the current one is consumed -- no registers are held
+// across the load latency.  (With one shared spectrum the L1-cached loads are faster: the bulk
+// copies bypass L1 and would re-read every group from L2 for every warp.)
+template <int N, bool PV, bool SB, bool STAGED = false>
 __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(FusedArgs a) {
   constexpr int NF = FusedLayout<PV>::NF;
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][12];
   __shared__ double s_gb[SB ? 1 : 2 * CHI_MAX_BASELINE][SB ? 1 : CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][2 * CHI_MAX_BASELINE];
   __shared__ double s_T[CHI_EXP_TABLE];
-  fill_exp_table(s_T);
-
+  __shared__ __align__(128) double s_stage[STAGED ? CHI_WARPS_PER_BLOCK : 1][2][STAGED ? 256 : 2];
+  __shared__ __align__(8) unsigned long long s_bar[STAGED ? CHI_WARPS_PER_BLOCK : 1][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (STAGED && lane == 0) {
+    mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[warp][0]));
+    mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[warp][1]));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fill_exp_table(s_T);  // contains the block barrier
+
   const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
   if (item >= a.B * a.n_chunks) return;
   const int64_t b = item / a.n_chunks;
@@ -116,9 +159,30 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
   const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
-  for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
+  const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&s_stage[STAGED ? warp : 0][0][0]);
+  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&s_bar[STAGED ? warp : 0][0]);
+  int it = 0;
+  if (STAGED && lane == 0 && chunk * a.chunk_len < s_end)
+    tma_fetch(ch - lane + (int64_t)((chunk * a.chunk_len) >> 5) * 256, stage_addr, bar_addr);
+  // STAGED: the whole warp runs every group (lanes past a ragged end carry zero weight) because
+  // all lanes take part in the buffer hand-over
+  for (int s = chunk * a.chunk_len + lane; (STAGED ? s - lane : s) < s_end; s += 32) {
     const double* __restrict__ cs = ch + (int64_t)(s >> 5) * 256;  // lane offset is in ch
-    const double v = __ldg(cs), pe0 = __ldg(cs + 32), pa0 = __ldg(cs + 64);
+    const int sx = STAGED ? min(s, s_end - 1) : s;
+    const double* __restrict__ sg = cs;
+    double v, pe0, pa0;
+    if (STAGED) {
+      const int buf = it & 1;
+      __syncwarp();  // every lane is done reading the other buffer
+      if (lane == 0 && s - lane + 32 < s_end)
+        tma_fetch(cs - lane + 256, stage_addr + (buf ^ 1) * 2048, bar_addr + (buf ^ 1) * 8);
+      mbar_wait(bar_addr + buf * 8, (it >> 1) & 1);
+      sg = &s_stage[warp][buf][lane];
+      ++it;
+      v = sg[0]; pe0 = sg[32]; pa0 = sg[64];
+    } else {
+      v = __ldg(cs); pe0 = __ldg(cs + 32); pa0 = __ldg(cs + 64);
+    }
     double base_e = be0 * pe0, base_a = ba0 * pa0;  // p_x0 is 0 without a baseline
     if (!SB) {
       for (int i = 1; i < nbe; ++i) base_e = fma(s_beta[warp][i], a.basis_e[(int64_t)i * S + s], base_e);
@@ -158,15 +222,23 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
     const double mu_a = (1.0 - ea) + base_a;          // absorption_model.py:91
     double mbe, mba;
     if (a.vjp) {
-      mbe = Ge ? Ge[s] : 0.0;
-      mba = Ga ? Ga[s] : 0.0;
+      mbe = Ge ? Ge[sx] : 0.0;
+      mba = Ga ? Ga[sx] : 0.0;
     } else {
-      const double re = __ldg(cs + 128) - mu_e, ra = __ldg(cs + 192) - mu_a;
-      mbe = __ldg(cs + 160) * re;
-      mba = __ldg(cs + 224) * ra;
+      double ye, we, ya, wa;
+      if (STAGED) {
+        ye = sg[128]; we = sg[160]; ya = sg[192]; wa = sg[224];
+      } else {
+        ye = __ldg(cs + 128); we = __ldg(cs + 160); ya = __ldg(cs + 192); wa = __ldg(cs + 224);
+      }
+      const double re = ye - mu_e, ra = ya - mu_a;
+      mbe = we * re;
+      mba = wa * ra;
+      if (STAGED && s >= s_end) { mbe = 0.0; mba = 0.0; }  // padded lanes of a ragged end
       lp = fma(mbe, re, lp);                          // -0.5 applied once at the end
       lp = fma(mba, ra, lp);
     }
+    if (STAGED && s >= s_end) { mbe = 0.0; mba = 0.0; }
     gbe0 = fma(mbe, pe0, gbe0);
     gba0 = fma(mba, pa0, gba0);
     if (!SB) {

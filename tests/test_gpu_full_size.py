@@ -147,3 +147,62 @@ def test_absorption_clouds_commute_at_full_size(cuda_device):
     fin = np.isfinite(lp)
     assert_close(grad_p.reshape(B_FULL, -1)[fin], grad[:, :, order].reshape(B_FULL, -1)[fin], rtol=1e-11, what="cloud order grad")
     eng.close()
+
+
+def test_config4_survey_full_size(cuda_device):
+    """BASELINE configs[3]: 10^4 sightlines x 5 clouds x 1000 channels (EmissionAbsorptionPhysical,
+    one spectrum pair per sightline, a few chains per sightline).  Properties: a draw's result
+    depends on its own sightline only (single-sightline engines reproduce sampled rows bit for
+    bit), and sharding by sightline (caribou_hi_b200.sharding) returns the same rows."""
+    import time
+
+    from caribou_hi_b200 import Engine, sharding
+
+    kind, N, S, n_sl, per = "emission_absorption_physical", 5, 1000, 10_000, 2
+    rng = np.random.default_rng(8)
+    v = np.linspace(-100.0, 100.0, S)
+    g = lambda c, w: np.exp(-4 * np.log(2) * (v[None, :] - c[:, None]) ** 2 / w[:, None] ** 2)  # noqa: E731
+    c1, c2 = rng.normal(0, 20, n_sl), rng.normal(0, 20, n_sl)
+    w1, w2 = rng.uniform(5, 25, n_sl), rng.uniform(5, 25, n_sl)
+    ye = 30 * g(c1, w1) + 10 * g(c2, w2) + 0.1 * rng.standard_normal((n_sl, S))
+    ya = 1 - np.exp(-(0.7 * g(c1, 0.8 * w1) + 0.2 * g(c2, 0.8 * w2))) + 0.01 * rng.standard_normal((n_sl, S))
+    eng = Engine(kind, N, prior_amplitude=1e21)
+    eng.set_spectra(emission=dict(spectral=v, brightness=ye, noise=0.1), absorption=dict(spectral=v, brightness=ya, noise=0.01),
+                    n_sightlines=n_sl)
+    B = n_sl * per
+    theta = eng.pack(_draws(eng, kind, N, B, 9))
+    sl = np.repeat(np.arange(n_sl, dtype=np.int32), per)
+    lp, grad, _, _ = eng.logp_grad(theta, sightline=sl)
+    t0 = time.perf_counter()
+    lp2, grad2, _, _ = eng.logp_grad(theta, sightline=sl)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(lp, lp2, equal_nan=True) and np.array_equal(grad, grad2, equal_nan=True)
+    print(f"\\nsurvey sweep: {B} draws over {n_sl} sightlines in {dt * 1e3:.2f} ms host call "
+          f"({B * N * 2 * S / dt:.3e} units/s incl. copies)")
+    fin = np.isfinite(lp)
+    assert 0.4 < fin.mean() < 1.0
+
+    # a draw depends on its own sightline only
+    for i in rng.choice(n_sl, 5, replace=False):
+        one = Engine(kind, N, prior_amplitude=1e21)
+        one.set_spectra(emission=dict(spectral=v, brightness=ye[i], noise=0.1),
+                        absorption=dict(spectral=v, brightness=ya[i], noise=0.01))
+        rows = np.where(sl == i)[0]
+        big = np.concatenate([theta[rows]] * 4096)  # same large-call arithmetic as the survey sweep
+        lp1, g1, _, _ = one.logp_grad(big)
+        assert np.array_equal(lp1[: rows.size], lp[rows], equal_nan=True)
+        assert np.array_equal(g1[: rows.size], grad[rows], equal_nan=True)
+        one.close()
+
+    # sharding by sightline: each shard evaluates its own sightlines, rows are the same
+    for rank in range(4):
+        lo, hi = sharding.shard_bounds(n_sl, 4, rank)
+        sel = (sl >= lo) & (sl < hi)
+        part = Engine(kind, N, prior_amplitude=1e21)
+        part.set_spectra(emission=dict(spectral=v, brightness=ye[lo:hi], noise=0.1),
+                         absorption=dict(spectral=v, brightness=ya[lo:hi], noise=0.01), n_sightlines=hi - lo)
+        lp_s, g_s, _, _ = part.logp_grad(theta[sel], sightline=sl[sel] - lo)
+        assert np.array_equal(lp_s, lp[sel], equal_nan=True)
+        assert np.array_equal(g_s, grad[sel], equal_nan=True)
+        part.close()
+    eng.close()
