@@ -347,6 +347,20 @@ int run_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce,
   SpecArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.N = N; a.pv = h->cfg.lorentzian != 0; a.cc = h->lanes[0].cc.d();
+  if (mu_e && mu_a && h->has_e && h->has_a && h->shared_axis) {
+    // one pass for both spectra of a shared axis
+    a.S = h->e.S; a.bg = h->cfg.bg_temp; a.vax = h->e.vax.d(); a.emission = 1;
+    a.n_base = h->e.nb; a.basis = h->e.basis.d(); a.offset = h->e.has_offset ? h->e.offset.d() : nullptr;
+    a.coeff = ce; a.mu = mu_e;
+    a.n_base_a = h->a.nb; a.basis_a = h->a.basis.d(); a.offset_a = h->a.has_offset ? h->a.offset.d() : nullptr;
+    a.coeff_a = ca; a.mu_a = mu_a;
+    if (launch_spectra_ea(N, a.pv != 0, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->ev_pending = true;
+    return CHI_OK;
+  }
   if (mu_e && h->has_e) {
     a.S = h->e.S; a.n_base = h->e.nb; a.bg = h->cfg.bg_temp; a.vax = h->e.vax.d();
     a.basis = h->e.basis.d(); a.offset = h->e.has_offset ? h->e.offset.d() : nullptr;

@@ -21,8 +21,15 @@ struct SpecArgs {
   const double* __restrict__ coeff;   // [B][n_base] or null
   const double* __restrict__ cc;
   double* __restrict__ mu;            // [B][S]
+  // second dataset of the fused shared-axis kernel (launch_spectra_ea): absorption
+  int n_base_a;
+  const double* __restrict__ basis_a;
+  const double* __restrict__ offset_a;
+  const double* __restrict__ coeff_a;
+  double* __restrict__ mu_a;
 };
 int launch_spectra(int N, bool pv, const SpecArgs& a, cudaStream_t st);
+int launch_spectra_ea(int N, bool pv, const SpecArgs& a, cudaStream_t st);
 struct FusedArgs;
 int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st);
 int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st);
