@@ -266,6 +266,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     ChanArgs a;
     memset(&a, 0, sizeof(a));
     a.B = B; a.S = h->e.S; a.n_base = h->e.nb; a.n_real = N; a.bg = h->cfg.bg_temp;
+    a.staged = (h->n_sl > 1 && !getenv("CHI_NO_STAGED")) ? 1 : 0;
     pick_chunks(h, std::max<int64_t>(B, h->call_draws), a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = em_record(h);
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
@@ -286,6 +287,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     ChanArgs a;
     memset(&a, 0, sizeof(a));
     a.B = B; a.S = h->a.S; a.n_base = h->a.nb; a.n_real = N; a.bg = 0.0;
+    a.staged = (h->n_sl > 1 && !getenv("CHI_NO_STAGED")) ? 1 : 0;
     pick_chunks(h, std::max<int64_t>(B, h->call_draws), a.S, &a.n_chunks, &a.chunk_len);
     a.mom_stride = ab_record(h);
     CK(L.mom_a.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));

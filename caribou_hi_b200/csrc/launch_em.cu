@@ -33,7 +33,10 @@ int launch_moments_em_gb(int N, bool pv, const ChanArgs& a, cudaStream_t st) {
 
 #if CHI_SB
 int launch_moments_em_gb(int N, bool pv, const ChanArgs& a, cudaStream_t st);
+int launch_moments_em_staged(int N, bool pv, const ChanArgs& a, cudaStream_t st);
 int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st) {
+  // per-draw sightlines (survey mode): no L1 reuse of the channel data -> staged pipeline
+  if (a.sl && a.staged && a.n_base <= 1 && N <= 8) return launch_moments_em_staged(N, pv, a, st);
   return (a.n_base <= 1 && N <= 8) ? launch_sb(N, pv, a, st) : launch_moments_em_gb(N, pv, a, st);
 }
 #endif

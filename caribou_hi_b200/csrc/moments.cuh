@@ -181,6 +181,42 @@ __device__ __forceinline__ double warp_sum(double x) {
   return x;
 }
 
+// --- bulk async copy (TMA, 1-D) + mbarrier helpers of the STAGED channel pipeline -----------
+// STAGED instantiations (survey mode, one spectrum per sightline): warps of a block read different
+// sightlines, so the channel data has no L1 reuse and every iteration's loads would be L2 / HBM
+// latency on the critical path.  Each warp then streams its sightline through a double buffer in
+// shared memory: one lane issues a bulk async copy (cp.async.bulk, completion on an mbarrier) of
+// the NEXT channel group while the current one is consumed -- no registers are held across the
+// load latency.  (With one shared spectrum the L1-cached loads are faster: the bulk copies bypass
+// L1 and would re-read every group from L2 for every warp.)
+__device__ __forceinline__ void mbar_init(unsigned bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+// one lane: expect `bytes` on `bar`, then copy one packed channel group global -> shared
+template <int BYTES>
+__device__ __forceinline__ void tma_fetch(const double* src, unsigned dst, unsigned bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(BYTES) : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %3, [%2];" ::"r"(dst),
+      "l"(src), "r"(bar), "n"(BYTES)
+      : "memory");
+}
+// all lanes: wait for the phase with the given parity; a protocol error traps instead of hanging
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
 // ---------------------------------------------------------------------------
 // argument block of the channel kernels
 // ---------------------------------------------------------------------------
@@ -188,6 +224,7 @@ struct ChanArgs {
   int64_t B;
   int S;            // channels of this dataset
   int n_base;       // baseline terms
+  int staged;       // 1: more than one sightline is loaded (survey mode)
   int n_real;       // clouds of the model; the template N may be larger (N > 8 runs on the 12- and
                     // 16-cloud instantiations, padded with null clouds: tau = 0, f = 0)
   int n_chunks;     // channel chunks per draw
@@ -241,16 +278,23 @@ constexpr int ab_min_blocks(int N, bool pv) {
 // ---------------------------------------------------------------------------
 // SB ("simple baseline") instantiations serve n_base <= 1 -- the reference's default
 // baseline_degree = 0 -- and carry no baseline loops.
-template <int N, bool PV, bool SB>
+template <int N, bool PV, bool SB, bool STAGED = false>
 __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(ChanArgs a) {
   constexpr int NE = EmLayout<PV>::NE;
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][8];
   __shared__ double s_gb[SB ? 1 : CHI_MAX_BASELINE - CHI_BASE_REG][SB ? 1 : CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
   __shared__ double s_T[CHI_EXP_TABLE];
-  fill_exp_table(s_T);
-
+  __shared__ __align__(128) double s_stage[STAGED ? CHI_WARPS_PER_BLOCK : 1][2][STAGED ? 128 : 2];
+  __shared__ __align__(8) unsigned long long s_bar[STAGED ? CHI_WARPS_PER_BLOCK : 1][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (STAGED && lane == 0) {
+    mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[warp][0]));
+    mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[warp][1]));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fill_exp_table(s_T);  // contains the block barrier
+
   const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
   if (item >= a.B * a.n_chunks) return;
   const int64_t b = item / a.n_chunks;
@@ -289,9 +333,29 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
   const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
-  for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
+  const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&s_stage[STAGED ? warp : 0][0][0]);
+  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&s_bar[STAGED ? warp : 0][0]);
+  int it = 0;
+  if (STAGED && lane == 0 && chunk * a.chunk_len < s_end)
+    tma_fetch<1024>(ch - lane + (int64_t)((chunk * a.chunk_len) >> 5) * 128, stage_addr, bar_addr);
+  // STAGED: the whole warp runs every group (lanes past a ragged end carry zero weight)
+  for (int s = chunk * a.chunk_len + lane; (STAGED ? s - lane : s) < s_end; s += 32) {
     const double* __restrict__ cs = ch + (int64_t)(s >> 5) * 128;  // lane offset is in ch
-    const double v = __ldg(cs), p0 = __ldg(cs + 32);
+    const int sx = STAGED ? min(s, s_end - 1) : s;
+    const double* __restrict__ sg = cs;
+    double v, p0;
+    if (STAGED) {
+      const int buf = it & 1;
+      __syncwarp();  // every lane is done reading the other buffer
+      if (lane == 0 && s - lane + 32 < s_end)
+        tma_fetch<1024>(cs - lane + 128, stage_addr + (buf ^ 1) * 1024, bar_addr + (buf ^ 1) * 8);
+      mbar_wait(bar_addr + buf * 8, (it >> 1) & 1);
+      sg = &s_stage[warp][buf][lane];
+      ++it;
+      v = sg[0]; p0 = sg[32];
+    } else {
+      v = __ldg(cs); p0 = __ldg(cs + 32);
+    }
     double p1 = 0.0, base = beta0 * p0;  // p_0 is 0 without a baseline
     if (!SB) {
       if (nb > 1) { p1 = bas1[s]; base = fma(beta1, p1, base); }
@@ -325,12 +389,14 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
     const double mu = (bg * P + T) - bg + base;  // ON - OFF, physics.py:362-365
     double mubar;
     if (G) {
-      mubar = G[s];
+      mubar = G[sx];
     } else {
-      const double r = __ldg(cs + 64) - mu;
-      mubar = __ldg(cs + 96) * r;               // d logp / d mu
+      const double r = (STAGED ? sg[64] : __ldg(cs + 64)) - mu;
+      mubar = (STAGED ? sg[96] : __ldg(cs + 96)) * r;  // d logp / d mu
+      if (STAGED && s >= s_end) mubar = 0.0;    // padded lanes of a ragged end
       lp = fma(mubar, r, lp);                   // -0.5 applied once at the end
     }
+    if (STAGED && s >= s_end) mubar = 0.0;
     gb0 = fma(mubar, p0, gb0);
     if (!SB) {
       if (nb > 1) gb1 = fma(mubar, p1, gb1);
@@ -398,16 +464,23 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
 //   absorption_model.py:88-91, emission_absorption_model.py:84-99 + physical equivalents
 //   shared per cloud: c, -k', -AG', -AL', h   (' = times log2(e), for chi_exp2)
 // ---------------------------------------------------------------------------
-template <int N, bool PV, bool SB>
+template <int N, bool PV, bool SB, bool STAGED = false>
 __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs(ChanArgs a) {
   constexpr int NA = AbLayout<PV>::NA;
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][6];
   __shared__ double s_gb[SB ? 1 : CHI_MAX_BASELINE - CHI_BASE_REG][SB ? 1 : CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
   __shared__ double s_T[CHI_EXP_TABLE];
-  fill_exp_table(s_T);
-
+  __shared__ __align__(128) double s_stage[STAGED ? CHI_WARPS_PER_BLOCK : 1][2][STAGED ? 128 : 2];
+  __shared__ __align__(8) unsigned long long s_bar[STAGED ? CHI_WARPS_PER_BLOCK : 1][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (STAGED && lane == 0) {
+    mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[warp][0]));
+    mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[warp][1]));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fill_exp_table(s_T);  // contains the block barrier
+
   const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
   if (item >= a.B * a.n_chunks) return;
   const int64_t b = item / a.n_chunks;
@@ -445,9 +518,29 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
   const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
 
   const int s_end = min(S, (chunk + 1) * a.chunk_len);
-  for (int s = chunk * a.chunk_len + lane; s < s_end; s += 32) {
+  const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&s_stage[STAGED ? warp : 0][0][0]);
+  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&s_bar[STAGED ? warp : 0][0]);
+  int it = 0;
+  if (STAGED && lane == 0 && chunk * a.chunk_len < s_end)
+    tma_fetch<1024>(ch - lane + (int64_t)((chunk * a.chunk_len) >> 5) * 128, stage_addr, bar_addr);
+  // STAGED: the whole warp runs every group (lanes past a ragged end carry zero weight)
+  for (int s = chunk * a.chunk_len + lane; (STAGED ? s - lane : s) < s_end; s += 32) {
     const double* __restrict__ cs = ch + (int64_t)(s >> 5) * 128;  // lane offset is in ch
-    const double v = __ldg(cs), p0 = __ldg(cs + 32);
+    const int sx = STAGED ? min(s, s_end - 1) : s;
+    const double* __restrict__ sg = cs;
+    double v, p0;
+    if (STAGED) {
+      const int buf = it & 1;
+      __syncwarp();  // every lane is done reading the other buffer
+      if (lane == 0 && s - lane + 32 < s_end)
+        tma_fetch<1024>(cs - lane + 128, stage_addr + (buf ^ 1) * 1024, bar_addr + (buf ^ 1) * 8);
+      mbar_wait(bar_addr + buf * 8, (it >> 1) & 1);
+      sg = &s_stage[warp][buf][lane];
+      ++it;
+      v = sg[0]; p0 = sg[32];
+    } else {
+      v = __ldg(cs); p0 = __ldg(cs + 32);
+    }
     double p1 = 0.0, base = beta0 * p0;  // p_0 is 0 without a baseline
     if (!SB) {
       if (nb > 1) { p1 = bas1[s]; base = fma(beta1, p1, base); }
@@ -474,12 +567,14 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
     const double mu = (1.0 - ea) + base;
     double mubar;
     if (G) {
-      mubar = G[s];
+      mubar = G[sx];
     } else {
-      const double r = __ldg(cs + 64) - mu;
-      mubar = __ldg(cs + 96) * r;
+      const double r = (STAGED ? sg[64] : __ldg(cs + 64)) - mu;
+      mubar = (STAGED ? sg[96] : __ldg(cs + 96)) * r;
+      if (STAGED && s >= s_end) mubar = 0.0;    // padded lanes of a ragged end
       lp = fma(mubar, r, lp);
     }
+    if (STAGED && s >= s_end) mubar = 0.0;
     gb0 = fma(mubar, p0, gb0);
     if (!SB) {
       if (nb > 1) gb1 = fma(mubar, p1, gb1);

@@ -54,47 +54,13 @@ constexpr int ea_min_blocks(int N, bool pv) {
 // shared per cloud, fetched in pairs; ' = times log2(e) (arguments of chi_exp2).  The Gaussian case
 // reads A B C forward and A C D in reverse:
 //   A [c, -k']  B [-AG_e', f*Ts]  C [f, -AG_a']  D [Ts, -f AG_e']  E [-AL_e', -AL_a']  F [h, -f AL_e']
-// --- bulk async copy (TMA, 1-D) + mbarrier helpers of the STAGED channel pipeline -----------
-__device__ __forceinline__ void mbar_init(unsigned bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-}
-// one lane: expect 2048 bytes on `bar`, then copy one packed channel group global -> shared
-__device__ __forceinline__ void tma_fetch(const double* src, unsigned dst, unsigned bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 2048;" ::"r"(bar) : "memory");
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 2048, [%2];" ::"r"(dst),
-      "l"(src), "r"(bar)
-      : "memory");
-}
-// all lanes: wait for the phase with the given parity; a protocol error traps instead of hanging
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  unsigned ok = 0;
-  for (int spin = 0; spin < (1 << 22); ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-  }
-  __trap();
-}
-
 __device__ __forceinline__ void ldg2(const double* p, double& x, double& y) {
   const double2 t = __ldg(reinterpret_cast<const double2*>(p));
   x = t.x;
   y = t.y;
 }
 
-// STAGED (survey mode, one spectrum pair per sightline): warps of a block read different
-// sightlines, so the channel data has no L1 reuse and every iteration's loads would be L2 / HBM
-// latency on the critical path.  Each warp then streams its sightline through a double buffer in
-// shared memory: one lane issues a 2 KB bulk async copy (cp.async.bulk, completion on an
-// mbarrier) for the NEXT channel group while the current one is consumed -- no registers are held
-// across the load latency.  (With one shared spectrum the L1-cached loads are faster: the bulk
-// copies bypass L1 and would re-read every group from L2 for every warp.)
+// STAGED: see the bulk-async helpers in moments.cuh.
 template <int N, bool PV, bool SB, bool STAGED = false>
 __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(FusedArgs a) {
   constexpr int NF = FusedLayout<PV>::NF;
@@ -163,7 +129,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
   const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&s_bar[STAGED ? warp : 0][0]);
   int it = 0;
   if (STAGED && lane == 0 && chunk * a.chunk_len < s_end)
-    tma_fetch(ch - lane + (int64_t)((chunk * a.chunk_len) >> 5) * 256, stage_addr, bar_addr);
+    tma_fetch<2048>(ch - lane + (int64_t)((chunk * a.chunk_len) >> 5) * 256, stage_addr, bar_addr);
   // STAGED: the whole warp runs every group (lanes past a ragged end carry zero weight) because
   // all lanes take part in the buffer hand-over
   for (int s = chunk * a.chunk_len + lane; (STAGED ? s - lane : s) < s_end; s += 32) {
@@ -175,7 +141,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
       const int buf = it & 1;
       __syncwarp();  // every lane is done reading the other buffer
       if (lane == 0 && s - lane + 32 < s_end)
-        tma_fetch(cs - lane + 256, stage_addr + (buf ^ 1) * 2048, bar_addr + (buf ^ 1) * 8);
+        tma_fetch<2048>(cs - lane + 256, stage_addr + (buf ^ 1) * 2048, bar_addr + (buf ^ 1) * 8);
       mbar_wait(bar_addr + buf * 8, (it >> 1) & 1);
       sg = &s_stage[warp][buf][lane];
       ++it;
