@@ -82,7 +82,7 @@ class ChiNutsConfig(C.Structure):
         ("n_tune", C.c_int32),
         ("n_draws", C.c_int32),
         ("max_treedepth", C.c_int32),
-        ("reserved", C.c_int32),
+        ("pool_mass", C.c_int32),
         ("seed", C.c_uint64),
         ("target_accept", C.c_double),
         ("init_step", C.c_double),

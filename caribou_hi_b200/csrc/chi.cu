@@ -1348,6 +1348,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   if (!cfg || cfg->chains < 1 || cfg->n_tune < 0 || cfg->n_draws < 1 || !draws_u)
     return fail(h, CHI_EINVAL, "chi_nuts_sample: bad configuration");
   const int max_depth = cfg->max_treedepth > 0 ? std::min(cfg->max_treedepth, CHI_NUTS_MAX_DEPTH) : 10;
+  const bool pool_mass = cfg->pool_mass != 0 && !sightline && cfg->chains > 1;
   const double target = cfg->target_accept > 0.0 ? cfg->target_accept : 0.8;
   CK(cudaSetDevice(h->device));
   const int64_t B = cfg->chains;
@@ -1507,11 +1508,19 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     a.tuning = tuning;
     a.adapt_step = tuning;
     a.collect_mass = tuning && it >= init_buf && it < n_tune - term_buf;
-    a.close_window = tuning && closes[it];
+    const bool close = tuning && closes[it];
+    a.close_window = close && !pool_mass;
+    // the averaged step size is adopted at the end of warm-up; with a pooled window that also closes
+    // there (never the case for Stan's schedule: the terminal buffer follows the last window)
     a.finalize = tuning && it == n_tune - 1;
     const int64_t k = it - n_tune;
     k_nuts_end_iter<<<grid, 64, 0, st>>>(s, a, tuning ? nullptr : d_draws, d_acc, d_depth, d_div, d_lp, d_eps, tuning ? 0 : k);
     h->launches++;
+    if (close && pool_mass) {
+      k_nuts_pool_mass<<<(unsigned)D, 128, 0, st>>>(s);
+      k_nuts_restart_window<<<grid, 64, 0, st>>>(s);
+      h->launches += 2;
+    }
     CK(cudaGetLastError());
   }
   cudaFreeHost(h_flags);

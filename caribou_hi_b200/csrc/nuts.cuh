@@ -318,6 +318,62 @@ struct NutsAdapt {
   double target_accept;
 };
 
+// Pooled mass adaptation (chains that share one posterior): at the end of an adaptation window the
+// variance of every free dimension is estimated from ALL chains' window samples (their Welford
+// statistics are merged), which needs B times fewer iterations per window than PyMC's per-chain
+// estimate for the same accuracy.  One block per dimension; then every chain restarts its window
+// and its step-size averaging (k_nuts_restart_window).
+__global__ void __launch_bounds__(128) k_nuts_pool_mass(NutsState s) {
+  const int d = blockIdx.x;
+  if (s.role[d] != 1) return;
+  __shared__ double sh[128];
+  auto block_sum = [&](double x) {
+    sh[threadIdx.x] = x;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+  };
+  double cnt = 0.0, sm = 0.0;
+  for (int64_t b = threadIdx.x; b < s.B; b += blockDim.x) {
+    const double n = s.w_count[b];
+    cnt += n;
+    sm += n * s.w_mean[b * s.D + d];
+  }
+  cnt = block_sum(cnt);
+  sm = block_sum(sm);
+  if (cnt < 2.0) return;
+  const double mean = sm / cnt;
+  double m2 = 0.0;
+  for (int64_t b = threadIdx.x; b < s.B; b += blockDim.x) {
+    const double n = s.w_count[b], dm = s.w_mean[b * s.D + d] - mean;
+    m2 += s.w_m2[b * s.D + d] + n * dm * dm;
+  }
+  m2 = block_sum(m2);
+  const double var = m2 / (cnt - 1.0);
+  const double inv = (cnt / (cnt + 5.0)) * var + 1e-3 * (5.0 / (cnt + 5.0));  // Stan's regularisation
+  for (int64_t b = threadIdx.x; b < s.B; b += blockDim.x) s.inv_mass[b * s.D + d] = inv;
+}
+
+__global__ void k_nuts_restart_window(NutsState s) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B) return;
+  const int64_t o = b * s.D;
+  for (int d = 0; d < s.D; ++d) {
+    s.w_mean[o + d] = 0.0;
+    s.w_m2[o + d] = 0.0;
+  }
+  s.w_count[b] = 0;
+  s.da_mu[b] = log(10.0 * s.eps[b]);
+  s.da_hbar[b] = 0.0;
+  s.da_logeps_bar[b] = 0.0;
+  s.da_count[b] = 0;
+}
+
 __global__ void k_nuts_end_iter(NutsState s, NutsAdapt a, double* draws, double* stat_accept, int* stat_depth,
                                 int* stat_diverged, double* stat_logp, double* stat_eps, int64_t draw_index) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -334,7 +334,9 @@ typedef struct chi_nuts_config {
   int64_t chains;
   int32_t n_tune, n_draws;
   int32_t max_treedepth;   /* <= 12; 0 -> 10 */
-  int32_t reserved;
+  int32_t pool_mass;       /* 1: the diagonal mass matrix of a window is estimated from all chains'
+                              samples (chains must share one posterior: ignored when `sightline`
+                              is given); 0: per chain, as PyMC does */
   uint64_t seed;
   double target_accept;    /* 0 -> 0.8 */
   double init_step;        /* 0 -> 0.25 / n_free^(1/4) (PyMC's default scaling) */
