@@ -86,6 +86,8 @@ class ChiNutsConfig(C.Structure):
         ("seed", C.c_uint64),
         ("target_accept", C.c_double),
         ("init_step", C.c_double),
+        ("lock_step", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

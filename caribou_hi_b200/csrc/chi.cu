@@ -19,6 +19,7 @@
 #include "launch.cuh"
 #include "moments_ea.cuh"
 #include "nuts.cuh"
+#include "nuts_warp.cuh"
 
 #define CHI_STAGE_RING 64
 
@@ -1349,6 +1350,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     return fail(h, CHI_EINVAL, "chi_nuts_sample: bad configuration");
   const int max_depth = cfg->max_treedepth > 0 ? std::min(cfg->max_treedepth, CHI_NUTS_MAX_DEPTH) : 10;
   const bool pool_mass = cfg->pool_mass != 0 && !sightline && cfg->chains > 1;
+  const bool lock_step = cfg->lock_step != 0 || pool_mass;  // pooled windows close for all chains at once
   const double target = cfg->target_accept > 0.0 ? cfg->target_accept : 0.8;
   CK(cudaSetDevice(h->device));
   const int64_t B = cfg->chains;
@@ -1459,10 +1461,64 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   // one leapfrog step (half kick + drift, batched logp+grad, half kick + tree bookkeeping) as a
   // CUDA graph: ~8 dependent launches per step would otherwise be pure launch latency for a few
   // dozen chains
+  int* h_flags = nullptr;
+  CK(cudaMallocHost(&h_flags, 2 * sizeof(int)));
+  const int total = n_tune + cfg->n_draws;
+  if (!lock_step) {
+    // asynchronous chains (nuts.cuh: k_nuts_tick): one graph = tick + batched evaluation, replayed
+    // until every chain has done its n_tune + n_draws iterations; the host looks at one counter
+    // every 32 ticks
+    Buf abuf;
+    const size_t ab = (2 * (size_t)B + 4) * sizeof(int) + (size_t)std::max(n_tune, 1);
+    CK(abuf.ensure(ab));
+    CK(cudaMemsetAsync(abuf.p, 0, ab, st));
+    NutsAsync A;
+    memset(&A, 0, sizeof(A));
+    A.n_tune = n_tune; A.n_total = total; A.init_buf = init_buf; A.term_buf = term_buf; A.max_depth = max_depth;
+    A.target_accept = target;
+    A.iter = (int*)abuf.p; A.started = A.iter + B; A.n_done = A.started + B;
+    unsigned char* d_closes = (unsigned char*)(A.n_done + 4);
+    if (n_tune > 0) CK(cudaMemcpyAsync(d_closes, closes.data(), n_tune, cudaMemcpyHostToDevice, st));
+    A.closes = d_closes;
+    A.draws = d_draws; A.stat_accept = d_acc; A.stat_logp = d_lp; A.stat_eps = d_eps;
+    A.stat_depth = d_depth; A.stat_diverged = d_div;
+    cudaGraph_t tg = nullptr;
+    cudaGraphExec_t tgx = nullptr;
+    size_t tn = 0;
+    h->capturing = true;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    if (getenv("CHI_NUTS_THREAD")) k_nuts_tick<<<grid, 64, 0, st>>>(s, A);  // A/B: one thread per chain
+    else k_nuts_tick_w<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(s, A);        // one warp per chain
+    rc = evaluate();
+    cudaError_t cap_err = cudaStreamEndCapture(st, &tg);
+    h->capturing = false;
+    if (rc) return rc;
+    CK(cap_err);
+    CK(cudaGraphInstantiate(&tgx, tg, 0));
+    CK(cudaGraphGetNodes(tg, nullptr, &tn));
+    // every chain needs at most total * (2^max_depth + 1) ticks
+    const int64_t tick_cap = (int64_t)total * ((1LL << max_depth) + 1) + 64;
+    int64_t ticks = 0;
+    h_flags[0] = 0;
+    while (h_flags[0] < B && ticks < tick_cap) {
+      for (int i = 0; i < 32; ++i) CK(cudaGraphLaunch(tgx, st));
+      ticks += 32;
+      h->launches += 32 * (int64_t)tn;
+      CK(cudaMemcpyAsync(h_flags, A.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    cudaGraphExecDestroy(tgx);
+    cudaGraphDestroy(tg);
+    abuf.release();
+    if (h_flags[0] < B) {
+      cudaFreeHost(h_flags);
+      return fail(h, CHI_ECUDA, "chi_nuts_sample: chains did not finish within the tick budget");
+    }
+  }
   cudaGraph_t graph[2] = {nullptr, nullptr};
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   size_t n_nodes[2] = {0, 0};
-  for (int g = 0; g < 2; ++g) {  // g = 0: first leaf of a doubling (no pending half step), 1: the others
+  for (int g = 0; g < 2 && lock_step; ++g) {  // g = 0: first leaf of a doubling (no pending half step), 1: the others
     h->capturing = true;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     k_nuts_leap<<<grid, 64, 0, st>>>(s, g, 1);
@@ -1474,10 +1530,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     CK(cudaGraphInstantiate(&gexec[g], graph[g], 0));
     CK(cudaGraphGetNodes(graph[g], nullptr, &n_nodes[g]));
   }
-  int* h_flags = nullptr;
-  CK(cudaMallocHost(&h_flags, 2 * sizeof(int)));
-  const int total = n_tune + cfg->n_draws;
-  for (int it = 0; it < total; ++it) {
+  for (int it = 0; it < total && lock_step; ++it) {
     k_nuts_begin_iter<<<grid, 64, 0, st>>>(s);
     h->launches++;
     for (int depth = 0; depth < max_depth; ++depth) {
@@ -1524,7 +1577,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     CK(cudaGetLastError());
   }
   cudaFreeHost(h_flags);
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < 2 && lock_step; ++g) {
     cudaGraphExecDestroy(gexec[g]);
     cudaGraphDestroy(graph[g]);
   }

@@ -128,9 +128,7 @@ __global__ void k_nuts_adopt(NutsState s) {
 }
 
 // ---- start of a NUTS iteration: fresh momentum, single-node tree --------------------------
-__global__ void k_nuts_begin_iter(NutsState s) {
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= s.B) return;
+__device__ __forceinline__ void nuts_begin_iter(const NutsState& s, int64_t b) {
   const int64_t o = b * s.D;
   unsigned long long st = s.rng[b];
   double kin = 0.0;
@@ -153,13 +151,16 @@ __global__ void k_nuts_begin_iter(NutsState s) {
   s.depth[b] = 0;
   s.diverged[b] = 0;
   s.active[b] = 1;
+}
+__global__ void k_nuts_begin_iter(NutsState s) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B) return;
+  nuts_begin_iter(s, b);
   if (b == 0) *s.n_active = (int)s.B;
 }
 
 // ---- start of a doubling: pick the direction, put the cursor on that edge -----------------
-__global__ void k_nuts_begin_subtree(NutsState s) {
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= s.B) return;
+__device__ __forceinline__ void nuts_begin_subtree(const NutsState& s, int64_t b) {
   const int64_t o = b * s.D;
   s.sub_stop[b] = s.active[b] ? 0 : 1;
   if (!s.active[b]) {
@@ -180,6 +181,11 @@ __global__ void k_nuts_begin_subtree(NutsState s) {
   }
   s.lw_sub[b] = -INFINITY;
   s.leaf[b] = 0;
+}
+__global__ void k_nuts_begin_subtree(NutsState s) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B) return;
+  nuts_begin_subtree(s, b);
 }
 
 // ---- leapfrog, first half: half kick + drift; the new position becomes the evaluation point ---
@@ -277,9 +283,7 @@ __global__ void k_nuts_leap(NutsState s, int do_b, int do_a) {
 }
 
 // ---- end of a doubling: merge the sub-tree into the tree ------------------------------------
-__global__ void k_nuts_end_subtree(NutsState s, int max_depth) {
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= s.B || !s.active[b]) return;
+__device__ __forceinline__ void nuts_end_subtree(const NutsState& s, int64_t b, int max_depth) {
   const int64_t o = b * s.D;
   const int dir = s.dir[b];
   const bool sub_bad = s.sub_stop[b] >= 2;
@@ -306,6 +310,11 @@ __global__ void k_nuts_end_subtree(NutsState s, int max_depth) {
     s.active[b] = 0;
     atomicSub(s.n_active, 1);
   }
+}
+__global__ void k_nuts_end_subtree(NutsState s, int max_depth) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B || !s.active[b]) return;
+  nuts_end_subtree(s, b, max_depth);
 }
 
 // ---- end of the iteration: move to the proposal, adapt, record -------------------------------
@@ -374,10 +383,9 @@ __global__ void k_nuts_restart_window(NutsState s) {
   s.da_count[b] = 0;
 }
 
-__global__ void k_nuts_end_iter(NutsState s, NutsAdapt a, double* draws, double* stat_accept, int* stat_depth,
-                                int* stat_diverged, double* stat_logp, double* stat_eps, int64_t draw_index) {
-  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= s.B) return;
+__device__ __forceinline__ void nuts_end_iter(const NutsState& s, const NutsAdapt& a, int64_t b, double* draws,
+                                              double* stat_accept, int* stat_depth, int* stat_diverged,
+                                              double* stat_logp, double* stat_eps, int64_t draw_index) {
   const int64_t o = b * s.D;
   for (int d = 0; d < s.D; ++d) {
     s.q[o + d] = s.qp[o + d];
@@ -431,6 +439,68 @@ __global__ void k_nuts_end_iter(NutsState s, NutsAdapt a, double* draws, double*
     stat_logp[draw_index * s.B + b] = s.logp[b];
     stat_eps[draw_index * s.B + b] = s.eps[b];
   }
+}
+__global__ void k_nuts_end_iter(NutsState s, NutsAdapt a, double* draws, double* stat_accept, int* stat_depth,
+                                int* stat_diverged, double* stat_logp, double* stat_eps, int64_t draw_index) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B) return;
+  nuts_end_iter(s, a, b, draws, stat_accept, stat_depth, stat_diverged, stat_logp, stat_eps, draw_index);
+}
+
+// ---- asynchronous chains ----------------------------------------------------------------------
+// In lock step every chain waits, in every iteration, for the deepest tree among the chains, so the
+// cost of an iteration is 2^(max depth over chains) leapfrog steps.  Here each chain runs its own
+// state machine: one tick = one batched logp+grad evaluation that serves the leaf in flight of
+// every chain, whatever iteration / doubling that chain is in; a chain that finishes its tree
+// records the draw, adapts (its own iteration index drives the warm-up schedule) and starts the next
+// iteration in the same tick.  Total ticks = the largest per-chain sum of tree sizes, not the sum
+// of per-iteration maxima.
+struct NutsAsync {
+  int n_tune, n_total, init_buf, term_buf, max_depth;
+  double target_accept;
+  const unsigned char* closes;  // [n_tune] 1 where an adaptation window closes
+  int* iter;                    // [B] iteration the chain is in
+  int* started;                 // [B] 0 before the chain's first leaf
+  int* n_done;                  // [1] chains that completed n_total iterations
+  double *draws, *stat_accept, *stat_logp, *stat_eps;
+  int *stat_depth, *stat_diverged;
+};
+
+__global__ void k_nuts_tick(NutsState s, NutsAsync A) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B) return;
+  int it = A.iter[b];
+  if (it >= A.n_total) return;  // finished: its evaluation point stays at the last state
+  if (A.started[b]) {
+    nuts_leap_b(s, b);  // the logp / gradient of the leaf in flight has arrived
+    if (s.sub_stop[b] || s.leaf[b] >= (1 << s.depth[b])) {
+      nuts_end_subtree(s, b, A.max_depth);
+      if (!s.active[b]) {
+        NutsAdapt a;
+        a.target_accept = A.target_accept;
+        a.tuning = it < A.n_tune;
+        a.adapt_step = a.tuning;
+        a.collect_mass = a.tuning && it >= A.init_buf && it < A.n_tune - A.term_buf;
+        a.close_window = a.tuning && A.closes[it];
+        a.finalize = a.tuning && it == A.n_tune - 1;
+        nuts_end_iter(s, a, b, a.tuning ? nullptr : A.draws, A.stat_accept, A.stat_depth, A.stat_diverged,
+                      A.stat_logp, A.stat_eps, a.tuning ? 0 : it - A.n_tune);
+        A.iter[b] = ++it;
+        if (it >= A.n_total) {
+          nuts_set_eval(s, b, s.q + b * s.D);
+          atomicAdd(A.n_done, 1);
+          return;
+        }
+        nuts_begin_iter(s, b);
+      }
+      nuts_begin_subtree(s, b);
+    }
+  } else {
+    A.started[b] = 1;
+    nuts_begin_iter(s, b);
+    nuts_begin_subtree(s, b);
+  }
+  nuts_leap_a(s, b);
 }
 
 // initial per-chain state of the adaptation

@@ -395,7 +395,7 @@ class Engine:
         )
 
     def nuts_sample(self, init_u, init_ce=None, init_ca=None, *, n_tune=1000, n_draws=1000, seed=1234,
-                    target_accept=0.8, max_treedepth=10, init_step=0.0, sightline=None, pool_mass=False):
+                    target_accept=0.8, max_treedepth=10, init_step=0.0, sightline=None, pool_mass=False, lock_step=False):
         """Chain-batched NUTS on the device.  ``init_u [chains, NSLOT, N]`` are unconstrained
         starting points with finite model logp.  Returns a dict with ``u [n_draws, chains, NSLOT,
         N]`` (unconstrained draws), ``coeff_e``/``coeff_a`` and the sampler statistics
@@ -409,7 +409,7 @@ class Engine:
         ca = self._coeffs(np.zeros((chains, self.nb_a)) if init_ca is None else init_ca, self.nb_a, chains, "init_ca")
         sl = None if sightline is None else np.ascontiguousarray(sightline, dtype=np.int32)
         cfg = _lib.ChiNutsConfig(chains=chains, n_tune=int(n_tune), n_draws=int(n_draws),
-                                 max_treedepth=int(max_treedepth), pool_mass=int(bool(pool_mass)), seed=int(seed),
+                                 max_treedepth=int(max_treedepth), pool_mass=int(bool(pool_mass)), lock_step=int(bool(lock_step)), seed=int(seed),
                                  target_accept=float(target_accept), init_step=float(init_step))
         out = {
             "u": np.empty((n_draws, chains, layout.NSLOT, N)),

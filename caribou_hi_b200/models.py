@@ -138,7 +138,7 @@ class _HIBase(ABC):
         return logp, grads
 
     def sample(self, draws=1000, tune=1000, chains=8, seed=None, target_accept=0.8, max_treedepth=10,
-               init_point=None, jitter=None, pool_mass=False):
+               init_point=None, jitter=None, pool_mass=False, lock_step=False):
         """Batched NUTS over ``chains`` on the device -- the role of ``BaseModel.sample`` /
         ``pm.sample`` in the reference (optimization.ipynb cell 12), but with all chains in one
         process and one batched logp+grad kernel pipeline per leapfrog step.
@@ -200,7 +200,7 @@ class _HIBase(ABC):
         start = self._strip(start)
         u0, ce, ca, _ = self._split(start)
         res = eng.nuts_sample(u0, ce, ca, n_tune=tune, n_draws=draws, seed=int(rng.integers(1 << 62)),
-                              target_accept=target_accept, max_treedepth=max_treedepth, pool_mass=pool_mass)
+                              target_accept=target_accept, max_treedepth=max_treedepth, pool_mass=pool_mass, lock_step=lock_step)
         x = eng.transform(res["u"].reshape(draws * chains, layout.NSLOT, self.n_clouds), +1)
         x = x.reshape(draws, chains, layout.NSLOT, self.n_clouds).transpose(1, 0, 2, 3)
         post = {k: (x[:, :, s, :1] if k in layout.scalar_rvs(self.kind) else x[:, :, s, :])

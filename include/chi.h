@@ -340,6 +340,10 @@ typedef struct chi_nuts_config {
   uint64_t seed;
   double target_accept;    /* 0 -> 0.8 */
   double init_step;        /* 0 -> 0.25 / n_free^(1/4) (PyMC's default scaling) */
+  int32_t lock_step;       /* 0: every chain runs its own tree / iteration state machine, one batched
+                              evaluation per tick serves them all (default); 1: all chains wait for
+                              the deepest tree of every iteration */
+  int32_t reserved;
 } chi_nuts_config;
 int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* init_u, const double* init_ce,
                     const double* init_ca, const int32_t* sightline, double* draws_u, double* draws_ce,

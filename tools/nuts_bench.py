@@ -21,7 +21,7 @@ def run(cls, N, S_e, S_a, chains, tune, draws, **priors):
     l0 = model.engine.launch_count()
     t0 = time.perf_counter()
     post, stats = model.sample(draws=draws, tune=tune, chains=chains, seed=2, init_point=truth, jitter=0.05,
-                               pool_mass=bool(os.environ.get("POOL")))
+                               pool_mass=bool(os.environ.get("POOL")), lock_step=bool(os.environ.get("LOCK_STEP")))
     dt = time.perf_counter() - t0
     nl = (2.0 ** stats["depth"]).sum()  # upper bound on leapfrogs of the kept draws
     print(f"{cls.__name__} N={N} S={S_e}+{S_a} chains={chains}: {tune}+{draws} iterations in {dt:.2f} s "
