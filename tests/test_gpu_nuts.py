@@ -81,3 +81,39 @@ def test_nuts_recovers_generating_parameters(cuda_device):
         assert chain_means.std() < 0.5 * s + 1e-3, f"{name}: chains disagree"
     # the likelihood at the posterior mean is as good as at the truth
     assert stats["logp"].max() > -1e4
+
+
+def test_lock_step_and_asynchronous_chains_agree(cuda_device):
+    """The lock-step mode (every chain waits for the deepest tree; thread per chain) and the default
+    asynchronous mode (warp per chain) sample the same posterior: posterior means agree within
+    their Monte-Carlo error, tree depths and acceptance rates are alike; the pooled mass adaptation
+    (lock step only) runs."""
+    from caribou_hi_b200 import AbsorptionModel, SpecData
+
+    rng = np.random.default_rng(5)
+    v = np.linspace(-25, 25, 200)
+    truth = {"fwhm2_norm": np.array([[0.05]]), "velocity_norm": np.array([[0.3]]),
+             "log10_nHI_norm": np.array([[0.0]]), "log10_n_alpha_norm": np.array([[0.0]]),
+             "tau_total_norm": np.array([[0.8]]), "tkin_factor": np.array([[0.5]]),
+             "baseline_absorption_norm": np.array([[0.0]])}
+    sim = AbsorptionModel({"absorption": SpecData(v, np.zeros(200), 0.01)}, 1, baseline_degree=0)
+    sim.add_priors(); sim.add_likelihood()
+    clean = sim.predict(truth)["absorption"][0]
+    model = AbsorptionModel({"absorption": SpecData(v, clean + 0.01 * rng.standard_normal(200), 0.01)}, 1, baseline_degree=0)
+    model.add_priors(); model.add_likelihood()
+    init = {k: x * 1.2 for k, x in truth.items()}
+    runs = {}
+    for mode, kw in (("async", {}), ("lock", {"lock_step": True}), ("pooled", {"pool_mass": True})):
+        post, stats = model.sample(draws=300, tune=400, chains=32, seed=3, init_point=init, **kw)
+        assert np.all(np.isfinite(post["velocity_norm"])) and stats["diverging"].mean() < 0.05
+        runs[mode] = (post, stats)
+    for name in ("velocity_norm", "fwhm2_norm", "tau_total_norm"):
+        ref = runs["async"][0][name][:, :, 0]
+        for mode in ("lock", "pooled"):
+            x = runs[mode][0][name][:, :, 0]
+            se = np.hypot(ref.std(), x.std()) / np.sqrt(32 * 300 / 10.0)  # ESS ~ draws / 10
+            assert abs(x.mean() - ref.mean()) < 6 * se + 1e-4, f"{mode} {name}: {x.mean()} vs {ref.mean()}"
+            assert 0.6 < x.std() / ref.std() < 1.6, f"{mode} {name}: spread {x.std()} vs {ref.std()}"
+    d_async, d_lock = runs["async"][1]["depth"].mean(), runs["lock"][1]["depth"].mean()
+    assert abs(d_async - d_lock) < 1.0
+    assert abs(runs["async"][1]["accept"].mean() - runs["lock"][1]["accept"].mean()) < 0.1
