@@ -1487,9 +1487,19 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     size_t tn = 0;
     h->capturing = true;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    if (getenv("CHI_NUTS_THREAD")) k_nuts_tick<<<grid, 64, 0, st>>>(s, A);  // A/B: one thread per chain
-    else k_nuts_tick_w<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(s, A);        // one warp per chain
-    rc = evaluate();
+    if (getenv("CHI_NUTS_THREAD")) {  // A/B: one thread per chain, separate map kernel
+      k_nuts_tick<<<grid, 64, 0, st>>>(s, A);
+      rc = evaluate();
+    } else {  // one warp per chain; the tick also maps the new evaluation point
+      Lane& L0 = h->lanes[0];
+      CK(L0.xcon.ensure((size_t)B * CHI_NSLOT * N * sizeof(double)));
+      MODEL_SWITCH(h->cfg.model, (k_nuts_tick_w<M><<<(unsigned)((B + 3) / 4), 128, 0, st>>>(s, A, h->map, h->rm,
+                                                                                        L0.cc.d(), L0.xcon.d())));
+      CK(cudaEventRecord(L0.ev_fork, L0.st));  // the cloud constants are ready from here on
+      h->call_first_stage = h->stage_calls;
+      rc = run_backward(h, L0, B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, nullptr, nullptr, false,
+                        s.elogp, s.egu, nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, PHASE_REST);
+    }
     cudaError_t cap_err = cudaStreamEndCapture(st, &tg);
     h->capturing = false;
     if (rc) return rc;

@@ -37,15 +37,12 @@ struct RowMap {
   signed char row[CHI_NSLOT];
 };
 
+// the map of one (draw, cloud); also called from the sampler's tick kernel (nuts_warp.cuh)
 template <int MODEL>
-__global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, RowMap rm, int64_t B, int N,
-                                                   const double* __restrict__ theta,
-                                                   double* __restrict__ cc,
-                                                   double* __restrict__ constrained) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= B * N) return;
-  int64_t b = t / N;
-  int n = (int)(t - b * N);
+__device__ __forceinline__ void cloud_map_one(const MapCfg& cfg, const RowMap& rm, int N, const double* __restrict__ theta,
+                                              double* __restrict__ cc, double* __restrict__ constrained, int64_t b,
+                                              int n) {
+  const int64_t t = b * N + n;
   double th[CHI_NSLOT];
   const double* tp = theta + (b * rm.n_rows) * N + n;
 #pragma unroll
@@ -72,6 +69,17 @@ __global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, RowMap rm, int64_
                                                 cfg.wch2_a, cfg.lorentzian != 0);
   o[CC_KA] = pa.k; o[CC_AGA] = pa.AG; o[CC_ALA] = pa.AL; o[CC_HA] = pa.h;
   o[11] = 0.0;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_cloud_map(MapCfg cfg, RowMap rm, int64_t B, int N,
+                                                   const double* __restrict__ theta,
+                                                   double* __restrict__ cc,
+                                                   double* __restrict__ constrained) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * N) return;
+  const int64_t b = t / N;
+  cloud_map_one<MODEL>(cfg, rm, N, theta, cc, constrained, b, (int)(t - b * N));
 }
 
 // ---------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 // numbers of the chain come from lane 0's stream and are broadcast, the momentum of dimension d
 // from a stream derived from (chain stream, d).
 #pragma once
+#include "kernels.cuh"
 #include "nuts.cuh"
 
 namespace chi {
@@ -314,8 +315,13 @@ __device__ __forceinline__ void nw_end_iter(const NutsState& s, const NutsAdapt&
   __syncwarp();
 }
 
-// one tick of every chain's state machine (see NutsAsync in nuts.cuh); 4 chains per block
-__global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A) {
+// one tick of every chain's state machine (see NutsAsync in nuts.cuh); 4 chains per block.  The
+// cloud map of the new evaluation point (k_cloud_map's work: transforms, parameter map, profile
+// constants) is done here by lanes 0..N-1, which takes one kernel out of the dependent chain of a
+// tick.
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A, MapCfg cfg, RowMap rm,
+                                                     double* __restrict__ cc, double* __restrict__ xcon) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= s.B) return;
@@ -352,6 +358,7 @@ __global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A) {
     nw_begin_subtree(s, b, lane);
   }
   nw_leap_a(s, b, lane);
+  if (lane < s.N) cloud_map_one<MODEL>(cfg, rm, s.N, s.eu, cc, xcon, b, lane);
 }
 
 #undef CHI_FOR_D
