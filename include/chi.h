@@ -322,8 +322,9 @@ int chi_transform(chi_handle* h, int64_t B, int direction, const double* in, dou
 
 /* ---- chain-batched NUTS -------------------------------------------
  * Replaces PyMC's process-per-chain pm.sample(...) loop (optimization.ipynb cell 12) for the model
- * logp above: all `chains` advance in lock step on the device, one batched logp+grad evaluation
- * per leapfrog step; multinomial NUTS with iterative U-turn checks, dual-averaging step size and
+ * logp above: all `chains` live on the device and one batched logp+grad evaluation per tick serves
+ * the leapfrog step in flight of every chain (each chain runs its own tree / iteration state
+ * machine, see chi_nuts_config::lock_step); multinomial NUTS with iterative U-turn checks, dual-averaging step size and
  * windowed diagonal mass adaptation during the n_tune warm-up iterations.  Draws come back in
  * the unconstrained space (chi_transform maps them), host pointers:
  *   init_u[chains][CHI_NSLOT][N], init_ce/_ca[chains][n_baseline]   starting points (finite logp!)
