@@ -99,4 +99,11 @@ def test_random_configuration(cuda_device, i):
             x.append(gca[sel][fin]); r.append(ref_g["baseline_absorption_norm"][fin])
         if fin.any():
             assert_close(np.concatenate(x, axis=1), np.concatenate(r, axis=1), what=f"{c} gradient")
+    if n_sl == 1:  # predicted spectra (fused forward kernel on a shared axis, one kernel per dataset otherwise)
+        ref_mu = mr.predict(spec, per_sl[0], free, baseline)
+        mu_e, mu_a = eng.spectra(eng.pack(free), ce, ca)
+        if mu_e is not None:
+            assert_close(mu_e, ref_mu["emission"], what=f"{c} mu_e")
+        if mu_a is not None:
+            assert_close(mu_a, ref_mu["absorption"], what=f"{c} mu_a")
     eng.close()
