@@ -73,6 +73,12 @@ struct Lane {
   // small batches run the absorption kernel on `aux`, concurrently with the emission kernel
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // pipelined host path: the epilogue and the downloads of a piece run on a high-priority stream, so
+  // that they are not starved by the channel kernels of the following pieces (which were queued
+  // first and would otherwise keep every SM until they drain) and the lane is free again early
+  cudaStream_t hi = nullptr;
+  cudaEvent_t ev_mom = nullptr, ev_tail = nullptr;
+  bool tail_pending = false;
   Buf cc, mom_e, mom_a;                                           // kernel workspace
   Buf xcon, prior;                                                // constrained values, per-cloud priors
   Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca;    // staging of the host entry points
@@ -110,6 +116,7 @@ struct chi_handle {
   bool capturing = false;  // inside a stream capture: no timing events
   double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];
   int64_t call_draws = 0;        // draws of the host call in flight (0 outside the pipelined host path)
+  bool epilogue_on_hi = false;   // pipelined host path: epilogue + downloads on the lane's priority stream
   int map_ahead = 0;             // PHASE_MAP: ring slots between the piece being mapped and stage_calls
   int64_t call_first_stage = 0;  // stage_calls at the start of the current model-level call
   int64_t launches = 0;
@@ -305,9 +312,15 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     CK(cudaStreamWaitEvent(L.st, L.ev_join, 0));
   }
   if (!h->capturing) CK(cudaEventRecord(evs[3], L.st));
+  cudaStream_t es = L.st;  // stream of the epilogue
+  if (h->epilogue_on_hi) {
+    CK(cudaEventRecord(L.ev_mom, L.st));
+    CK(cudaStreamWaitEvent(L.hi, L.ev_mom, 0));
+    es = L.hi;
+  }
   // baseline-coefficient gradients of a dataset that did not run are zero
-  if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), L.st));
-  if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), L.st));
+  if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), es));
+  if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), es));
 
   // small batches are bound by the dependent chain of the per-cloud map: split the tangent
   // directions over threads; large batches take the fused form (half the arithmetic)
@@ -320,22 +333,22 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     if (model) {  // whole draws per block
       const int per = N * K, bd = (128 / per) * per;
       const unsigned gp = (unsigned)((B + bd / per - 1) / (bd / per));
-      MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, true><<<gp, bd, 0, L.st>>>(h->map, ea)));
+      MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, true><<<gp, bd, 0, es>>>(h->map, ea)));
     }
-    else { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, false><<<grid, 128, 0, L.st>>>(h->map, ea))); }
+    else { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, true, false><<<grid, 128, 0, es>>>(h->map, ea))); }
   } else {
     unsigned grid = (unsigned)((B * N + 127) / 128);
     if (model) {  // whole draws per block
       const int bd = (128 / N) * N;
       const unsigned gp = (unsigned)((B + bd / N - 1) / (bd / N));
-      MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, true><<<gp, bd, 0, L.st>>>(h->map, ea)));
+      MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, true><<<gp, bd, 0, es>>>(h->map, ea)));
     }
-    else { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, false><<<grid, 128, 0, L.st>>>(h->map, ea))); }
+    else { MODEL_SWITCH(h->cfg.model, (k_epilogue<M, false, false><<<grid, 128, 0, es>>>(h->map, ea))); }
   }
 
   h->launches++;
   CK(cudaGetLastError());
-  if (!h->capturing) CK(cudaEventRecord(evs[4], L.st));
+  if (!h->capturing) CK(cudaEventRecord(evs[4], es));
   if (!h->capturing) h->stage_calls++;
   return CHI_OK;
 }
@@ -541,6 +554,14 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
     ok = cudaStreamCreateWithFlags(&h->lanes[i].aux, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&h->lanes[i].ev_fork, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&h->lanes[i].ev_join, cudaEventDisableTiming) == cudaSuccess;
+  {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    for (int i = 0; ok && i < CHI_LANES; ++i)
+      ok = cudaStreamCreateWithPriority(&h->lanes[i].hi, cudaStreamNonBlocking, greatest) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->lanes[i].ev_mom, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->lanes[i].ev_tail, cudaEventDisableTiming) == cudaSuccess;
+  }
   if (!ok) {
     delete h;
     return fail(nullptr, CHI_ECUDA, "chi_create: stream/event creation failed");
@@ -552,8 +573,10 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
 void chi_destroy(chi_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  for (Lane& L : h->lanes)
+  for (Lane& L : h->lanes) {
     if (L.st) cudaStreamSynchronize(L.st);
+    if (L.hi) cudaStreamSynchronize(L.hi);
+  }
   h->e.release(); h->a.release(); h->lconst.release(); h->chan.release();
   for (Lane& L : h->lanes) L.release();
   Buf* bufs[] = {&h->w_gbe, &h->w_gba, &h->w_mue, &h->w_mua};
@@ -567,6 +590,9 @@ void chi_destroy(chi_handle* h) {
   for (Lane& L : h->lanes) {
     if (L.ev_fork) cudaEventDestroy(L.ev_fork);
     if (L.ev_join) cudaEventDestroy(L.ev_join);
+    if (L.ev_mom) cudaEventDestroy(L.ev_mom);
+    if (L.ev_tail) cudaEventDestroy(L.ev_tail);
+    if (L.hi) cudaStreamDestroy(L.hi);
     if (L.aux) cudaStreamDestroy(L.aux);
     if (L.st) cudaStreamDestroy(L.st);
   }
@@ -973,6 +999,10 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
     Lane& L = h->lanes[k % CHI_LANES];
     Piece& p = P[k];
     const int64_t nb = p.nb, b0 = p.b0;
+    if (L.tail_pending) {  // the lane's previous piece must have left its buffers
+      CK(cudaStreamWaitEvent(L.st, L.ev_tail, 0));
+      L.tail_pending = false;
+    }
     CK(L.w_theta.ensure(nb * th_b));
     CK(L.w_logp.ensure(nb * sizeof(double)));
     CK(cudaMemcpyAsync(L.w_theta.p, theta + b0 * n_rows * N, nb * th_b, cudaMemcpyHostToDevice, L.st));
@@ -1009,6 +1039,7 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
     ~CallScope() { h->call_draws = 0; }
   } scope{h};
   h->call_draws = B;
+  const bool use_hi = sizes.size() > 1 && !getenv("CHI_NO_HI");
   h->map_ahead = 0;
   rc = issue_upload_and_map(0);
   if (rc) return rc;
@@ -1022,15 +1053,26 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
     Lane& L = h->lanes[k % CHI_LANES];
     const Piece& p = P[k];
     const int64_t nb = p.nb, b0 = p.b0;
+    h->epilogue_on_hi = use_hi;
     rc = run_backward(h, L, nb, L.w_theta.d(), p.d_ce, p.d_ca, p.d_sl, nullptr, nullptr, false, L.w_logp.d(), p.d_grad,
                       p.d_gce, p.d_gca, model, PHASE_REST);
+    h->epilogue_on_hi = false;
     if (rc) return rc;
-    CK(cudaMemcpyAsync(logp + b0, L.w_logp.p, nb * sizeof(double), cudaMemcpyDeviceToHost, L.st));
-    if (p.d_grad) CK(cudaMemcpyAsync(grad + b0 * n_rows * N, p.d_grad, nb * th_b, cudaMemcpyDeviceToHost, L.st));
-    if (p.d_gce) CK(cudaMemcpyAsync(gce + b0 * nbe, p.d_gce, nb * nbe * sizeof(double), cudaMemcpyDeviceToHost, L.st));
-    if (p.d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, p.d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, L.st));
+    cudaStream_t ds = use_hi ? L.hi : L.st;
+    CK(cudaMemcpyAsync(logp + b0, L.w_logp.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ds));
+    if (p.d_grad) CK(cudaMemcpyAsync(grad + b0 * n_rows * N, p.d_grad, nb * th_b, cudaMemcpyDeviceToHost, ds));
+    if (p.d_gce) CK(cudaMemcpyAsync(gce + b0 * nbe, p.d_gce, nb * nbe * sizeof(double), cudaMemcpyDeviceToHost, ds));
+    if (p.d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, p.d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, ds));
+    if (use_hi) {
+      CK(cudaEventRecord(L.ev_tail, L.hi));
+      L.tail_pending = true;
+    }
   }
-  for (Lane& L : h->lanes) CK(cudaStreamSynchronize(L.st));
+  for (Lane& L : h->lanes) {
+    CK(cudaStreamSynchronize(L.st));
+    CK(cudaStreamSynchronize(L.hi));
+    L.tail_pending = false;
+  }
   if (getenv("CHI_TIMELINE")) {  // development aid: when each piece's stages ran, relative to the first
     const int first = h->call_first_stage, n = h->stage_calls - first;
     cudaEvent_t t0 = h->ring[first % CHI_STAGE_RING][0];
