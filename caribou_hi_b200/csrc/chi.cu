@@ -57,6 +57,8 @@ static RowMap identity_rows() {
   return m;
 }
 
+#define CHI_TICKETS 8
+
 struct DevDataset {
   int S = 0, nb = 0;
   bool has_offset = false;
@@ -110,6 +112,9 @@ struct chi_handle {
   // further staging of the host entry points (single-lane paths)
   Buf w_gbe, w_gba, w_mue, w_mua, w_misc[8];
   RowMap rm;                 // layout of the caller's theta / grad blocks for the call in flight
+  // asynchronous host calls: completion events of the last CHI_TICKETS calls, two per lane
+  cudaEvent_t tickets[CHI_TICKETS][2 * CHI_LANES] = {};
+  int64_t next_ticket = 0;
   bool shared_axis = false;  // both datasets on the same spectral axis: fused kernel
   Buf chan;                  // its packed per-channel data [n_sl][S][8]
   bool priors_set = false;
@@ -587,6 +592,9 @@ void chi_destroy(chi_handle* h) {
   for (auto& row : h->ring)
     for (cudaEvent_t e : row)
       if (e) cudaEventDestroy(e);
+  for (auto& row : h->tickets)
+    for (cudaEvent_t e : row)
+      if (e) cudaEventDestroy(e);
   for (Lane& L : h->lanes) {
     if (L.ev_fork) cudaEventDestroy(L.ev_fork);
     if (L.ev_join) cudaEventDestroy(L.ev_join);
@@ -604,7 +612,23 @@ void* chi_stream(chi_handle* h) { return h ? (void*)h->stream : nullptr; }
 int chi_synchronize(chi_handle* h) {
   if (!h) return CHI_EINVAL;
   CK(cudaSetDevice(h->device));
-  for (Lane& L : h->lanes) CK(cudaStreamSynchronize(L.st));
+  for (Lane& L : h->lanes) {
+    CK(cudaStreamSynchronize(L.st));
+    if (L.hi) CK(cudaStreamSynchronize(L.hi));
+    L.tail_pending = false;
+  }
+  return CHI_OK;
+}
+
+int chi_wait(chi_handle* h, int64_t ticket) {
+  if (!h) return CHI_EINVAL;
+  if (ticket < 0) return chi_synchronize(h);
+  if (ticket >= h->next_ticket) return fail(h, CHI_EINVAL, "chi_wait: unknown ticket");
+  // a ticket that has left the ring: the oldest one still in it was queued later on the same streams,
+  // so its completion implies the older one's
+  ticket = std::max<int64_t>(ticket, h->next_ticket - CHI_TICKETS);
+  CK(cudaSetDevice(h->device));
+  for (cudaEvent_t e : h->tickets[ticket % CHI_TICKETS]) CK(cudaEventSynchronize(e));
   return CHI_OK;
 }
 
@@ -931,7 +955,8 @@ int chi_spectra_vjp_dev(chi_handle* h, int64_t B, const double* theta, const dou
 
 // ---- model-level, host pointers ---------------------------------------------------
 static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
-                          const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model) {
+                          const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model,
+                          int64_t* ticket_out = nullptr) {
   int rc = check_model_call(h, B, theta);
   if (rc) return rc;
   if (model) {
@@ -1068,6 +1093,19 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
       L.tail_pending = true;
     }
   }
+  if (ticket_out) {
+    // asynchronous call: completion = everything queued on the lanes' streams so far
+    const int64_t t = h->next_ticket++;
+    cudaEvent_t* ev = h->tickets[t % CHI_TICKETS];
+    for (int i = 0; i < CHI_LANES; ++i) {
+      for (int j = 0; j < 2; ++j)
+        if (!ev[2 * i + j]) CK(cudaEventCreateWithFlags(&ev[2 * i + j], cudaEventDisableTiming));
+      CK(cudaEventRecord(ev[2 * i], h->lanes[i].st));
+      CK(cudaEventRecord(ev[2 * i + 1], h->lanes[i].hi));
+    }
+    *ticket_out = t;
+    return CHI_OK;
+  }
   for (Lane& L : h->lanes) {
     CK(cudaStreamSynchronize(L.st));
     CK(cudaStreamSynchronize(L.hi));
@@ -1115,6 +1153,23 @@ int chi_logp_grad_rows(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* 
   if (rc) return rc;
   h->rm = m;
   rc = host_logp_grad(h, B, rows, ce, ca, sl, logp, grad_rows, gce, gca, false);
+  h->rm = identity_rows();
+  return rc;
+}
+
+int chi_logp_grad_rows_async(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* slot_of_row, const double* rows,
+                             const double* ce, const double* ca, const int32_t* sl, double* logp, double* grad_rows,
+                             double* gce, double* gca, int64_t* ticket_out) {
+  if (!h || !ticket_out) return CHI_EINVAL;
+  RowMap m;
+  int rc = make_row_map(h, n_rows, slot_of_row, &m);
+  if (rc) return rc;
+  if (B == 0) {  // nothing to enqueue: a ticket that is already complete
+    *ticket_out = -1;
+    return CHI_OK;
+  }
+  h->rm = m;
+  rc = host_logp_grad(h, B, rows, ce, ca, sl, logp, grad_rows, gce, gca, false, ticket_out);
   h->rm = identity_rows();
   return rc;
 }

@@ -309,6 +309,45 @@ class Engine:
         )
         return logp, grad, gce, gca
 
+    def logp_grad_rows_async(self, rows, coeff_e, coeff_a, out, sightline=None):
+        """Asynchronous :meth:`logp_grad_rows` (C ABI ``chi_logp_grad_rows_async``): enqueues the
+        call and returns a ticket for :meth:`wait`.  ``rows``, the coefficients and every array of
+        ``out`` (``logp``, ``grad`` and, with baselines, ``gcoeff_e`` / ``gcoeff_a``) must be
+        :class:`PinnedArray` views that stay untouched until the wait returns.  Keeping two calls
+        in flight hides one call's pipeline fill and drain behind the other's kernels."""
+        N = self.n_clouds
+        slots = self.row_slots
+        if rows.dtype != np.float64 or not rows.flags.c_contiguous or rows.shape[1:] != (slots.size, N):
+            raise ValueError(f"rows: expected a C-contiguous float64 [B, {slots.size}, {N}] array")
+        B = rows.shape[0]
+        for name, a, shape in (("coeff_e", coeff_e, (B, self.nb_e)), ("coeff_a", coeff_a, (B, self.nb_a)),
+                               ("logp", out.get("logp"), (B,)), ("grad", out.get("grad"), rows.shape),
+                               ("gcoeff_e", out.get("gcoeff_e"), (B, self.nb_e)),
+                               ("gcoeff_a", out.get("gcoeff_a"), (B, self.nb_a))):
+            if shape[-1] == 0 and name != "logp":
+                continue
+            if a is None or a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != shape:
+                raise ValueError(f"{name}: expected a C-contiguous float64 array of shape {shape}")
+        sl = None
+        if sightline is not None:
+            sl = np.ascontiguousarray(sightline, dtype=np.int32)
+        ticket = C.c_int64(-1)
+        self._check(
+            self._lib.chi_logp_grad_rows_async(
+                self._h, B, int(slots.size), _lib.as_ip(slots), _lib.as_dp(rows),
+                _lib.as_dp(coeff_e if self.nb_e else None), _lib.as_dp(coeff_a if self.nb_a else None), _lib.as_ip(sl),
+                _lib.as_dp(out["logp"]), _lib.as_dp(out["grad"]),
+                _lib.as_dp(out.get("gcoeff_e") if self.nb_e else None),
+                _lib.as_dp(out.get("gcoeff_a") if self.nb_a else None), C.byref(ticket),
+            )
+        )
+        self._keep = (rows, coeff_e, coeff_a, sl, out)  # the arrays of the newest call stay referenced
+        return int(ticket.value)
+
+    def wait(self, ticket=-1):
+        """Block until the asynchronous call ``ticket`` (default: everything) has completed."""
+        self._check(self._lib.chi_wait(self._h, int(ticket)))
+
     def spectra(self, theta, coeff_e=None, coeff_a=None):
         """Predicted spectra ``(mu_e [B, S_e] | None, mu_a [B, S_a] | None)``."""
         N = self.n_clouds

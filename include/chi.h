@@ -259,6 +259,17 @@ int chi_logp_grad_rows(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* 
                        const double* rows, const double* coeff_e, const double* coeff_a,
                        const int32_t* sightline, double* logp_out, double* grad_rows_out,
                        double* gcoeff_e_out, double* gcoeff_a_out);
+/* Asynchronous form of chi_logp_grad_rows: enqueues the uploads, kernels and downloads and returns
+ * at once with a ticket; chi_wait(h, ticket) blocks until that call's outputs are in host memory
+ * (ticket < 0: everything enqueued on the handle).  All host buffers must be page-locked
+ * (chi_host_alloc) and stay untouched until the wait returns.  Calls complete in the order they
+ * were issued; keeping two in flight (double-buffered inputs / outputs) hides the pipeline's fill
+ * and drain of one call behind the kernels of the other. */
+int chi_logp_grad_rows_async(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* slot_of_row,
+                             const double* rows, const double* coeff_e, const double* coeff_a,
+                             const int32_t* sightline, double* logp_out, double* grad_rows_out,
+                             double* gcoeff_e_out, double* gcoeff_a_out, int64_t* ticket_out);
+int chi_wait(chi_handle* h, int64_t ticket);
 int chi_logp_grad_rows_dev(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* slot_of_row,
                            const double* rows, const double* coeff_e, const double* coeff_a,
                            const int32_t* sightline, double* logp_out, double* grad_rows_out,

@@ -485,3 +485,40 @@ def test_branch_edges_of_the_parameter_maps(cuda_device, kind):
         if k in det and k in d_dev:
             assert_close(d_dev[k][fin], np.broadcast_to(det[k], (B, N))[fin], rtol=1e-12, what=k)
     eng.close()
+
+
+def test_asynchronous_host_calls(cuda_device):
+    """chi_logp_grad_rows_async + chi_wait: several calls in flight on double-buffered pinned arrays
+    give the same bits as the synchronous call, in issue order, including tickets that have left
+    the ring."""
+    from caribou_hi_b200 import PinnedArray
+
+    spec, data, free, baseline = make_case("emission_absorption_physical", 3, 160, 160, 20000, seed=81, shared_axis=True)
+    eng = engine_for(spec, data, 0)
+    rows = eng.pack_rows(free)
+    ce, ca = baseline["baseline_emission_norm"], baseline["baseline_absorption_norm"]
+    B = rows.shape[0]
+    ref = [eng.logp_grad_rows(np.roll(rows, k, axis=0), np.roll(ce, k, axis=0), np.roll(ca, k, axis=0)) for k in range(3)]
+    keep, bufs = [], []
+    for k in range(3):
+        p = {"rows": PinnedArray(rows.shape), "ce": PinnedArray(ce.shape), "ca": PinnedArray(ca.shape),
+             "logp": PinnedArray((B,)), "grad": PinnedArray(rows.shape), "gce": PinnedArray(ce.shape), "gca": PinnedArray(ca.shape)}
+        p["rows"].array[...] = np.roll(rows, k, axis=0)
+        p["ce"].array[...] = np.roll(ce, k, axis=0)
+        p["ca"].array[...] = np.roll(ca, k, axis=0)
+        keep.append(p)
+        bufs.append(dict(logp=p["logp"].array, grad=p["grad"].array, gcoeff_e=p["gce"].array, gcoeff_a=p["gca"].array))
+    tickets = []
+    for rep in range(4):  # 12 calls: more than the ticket ring holds
+        for k in range(3):
+            if rep > 0:
+                eng.wait(tickets[-3])  # the buffers of set k are about to be reused
+            tickets.append(eng.logp_grad_rows_async(keep[k]["rows"].array, keep[k]["ce"].array, keep[k]["ca"].array, bufs[k]))
+    eng.wait(tickets[0])   # long gone from the ring: completed by stream order
+    eng.wait()             # everything
+    for k in range(3):
+        assert np.array_equal(bufs[k]["logp"], ref[k][0], equal_nan=True)
+        assert np.array_equal(bufs[k]["grad"], ref[k][1], equal_nan=True)
+        assert np.array_equal(bufs[k]["gcoeff_e"], ref[k][2], equal_nan=True)
+        assert np.array_equal(bufs[k]["gcoeff_a"], ref[k][3], equal_nan=True)
+    eng.close()
