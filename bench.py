@@ -335,6 +335,7 @@ def run_b200(args):
         step(i)
     barrier()
     launches0 = eng.launch_count()
+    stage0 = eng.stage_count()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -352,7 +353,11 @@ def run_b200(args):
     t_end = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
-    stage = eng.stage_ms(min(args.steps, 64)).mean(axis=0)  # events recorded during the timed steps
+    # the library runs a large device batch as `pieces` launches of every kernel (three lanes): the
+    # stage events are per piece, i.e. per LAUNCH
+    n_stage = eng.stage_count() - stage0
+    pieces = max(1, round(n_stage / max(args.steps, 1)))
+    stage = eng.stage_ms(min(n_stage, 63)).mean(axis=0)  # events recorded during the timed steps
     clocks = None
     if rank == 0:
         # a timed region shorter than a few NVML queries: hold the same load (untimed) until the
@@ -433,10 +438,11 @@ def run_b200(args):
         t_em = float(stage[1]) * 1e-3
         flops_unit = FLOPS_EM + FLOPS_ABS if fused else FLOPS_EM
         kernel_name = "k_moments_ea<4,false> (fused emission+absorption)" if fused else "k_moments_em<4,false>"
-        flops_em = draws * N * S_E * flops_unit
+        draws_launch = draws / pieces  # draws one launch of the kernel processes
+        flops_em = draws_launch * N * S_E * flops_unit
         achieved = flops_em / t_em / 1e12
         rec = (3 + 6 * N) if fused else (2 + 5 * N)
-        bytes_em = draws * (N * 12 * 8 + rec * 8)  # cc read + moment record written per draw
+        bytes_em = draws_launch * (N * 12 * 8 + rec * 8)  # cc read + moment record written per draw
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -462,17 +468,20 @@ def run_b200(args):
                     "async_ms_per_step": t_async * 1e3},
             "gpu_launches": launches,
             "stage_ms": {"cloud_map": float(stage[0]), "moments_emission": float(stage[1]),
-                         "moments_absorption": float(stage[2]), "epilogue": float(stage[3])},
+                         "moments_absorption": float(stage[2]), "epilogue": float(stage[3]),
+                         "launches_per_step_of_each_kernel": pieces,
+                         "note": "average duration of ONE launch of each kernel (CUDA events on its lane's stream); "
+                                 "the pieces of a step run on three lanes and overlap"},
             "roofline": {"kernel": kernel_name, "bound": "fp64", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "own DFMA microbenchmark on this GPU (chi_microbench_fp64); "
                                         "MEASURED_PEAKS.json has no CUDA-core FP64 figure",
-                         "flops_per_unit": flops_unit, "units_per_launch": draws * N * S_E,
+                         "flops_per_unit": flops_unit, "units_per_launch": draws_launch * N * S_E,
                          "unit_of_launch": "draw*cloud*channel-pair" if fused else "draw*cloud*channel",
                          # dram__bytes_read+write of this kernel from the ncu --set full capture in
                          # profiles/ (20000 draws per launch: 8.09 MB read, writes absorbed by L2),
                          # scaled to this launch's draws
-                         "traffic": (NCU_DRAM_BYTES_PER_DRAW * draws) if fused else None,
+                         "traffic": (NCU_DRAM_BYTES_PER_DRAW * draws_launch) if fused else None,
                          "traffic_source": "profiles/r1f_ncu_full_summary.txt" if fused else None,
                          "hbm": {"achieved": bytes_em / t_em / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_em / t_em / 1e9 / hbm_peak,

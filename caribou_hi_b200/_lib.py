@@ -124,6 +124,7 @@ SYMBOLS = {
     "chi_logp_grad_rows_async": (C.c_int, [_H, C.c_int64, C.c_int32, _ip, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp,
                                            C.POINTER(C.c_int64)]),
     "chi_wait": (C.c_int, [_H, C.c_int64]),
+    "chi_stage_count": (C.c_int64, [_H]),
     "chi_spectra": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
     "chi_spectra_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 5),
     "chi_spectra_vjp": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

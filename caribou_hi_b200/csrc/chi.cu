@@ -988,6 +988,9 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
     for (int64_t b0 = 0; b0 < B; b0 += sub) sizes.push_back(std::min(sub, B - b0));
   } else {
     std::vector<double> den = {24, 12, 8, 6, 6, 6, 8, 12, 24};
+    // asynchronous calls overlap with their neighbours: fill and drain are hidden anyway, three equal
+    // pieces keep the kernels efficient (measured: 1.69 ms per 1e5-draw call against 1.87 with the ramp)
+    if (ticket_out) den = {3, 3, 3};
     if (const char* e = getenv("CHI_PIPE_RAMP")) {  // tuning knob: comma-separated denominators
       den.clear();
       for (const char* c = e; *c;) {
@@ -1407,6 +1410,7 @@ int chi_stage_ms(chi_handle* h, int n, float* ms_out) {
 }
 
 int64_t chi_launch_count(const chi_handle* h) { return h ? h->launches : 0; }
+int64_t chi_stage_count(const chi_handle* h) { return h ? h->stage_calls : 0; }
 
 int chi_microbench_fp64(chi_handle* h, double* tflops_out) {
   if (!h || !tflops_out) return CHI_EINVAL;

@@ -344,6 +344,11 @@ class Engine:
         self._keep = (rows, coeff_e, coeff_a, sl, out)  # the arrays of the newest call stay referenced
         return int(ticket.value)
 
+    def stage_count(self):
+        """Number of logp / VJP kernel pipelines (cloud map -> moments -> epilogue) issued so far on
+        this handle; :meth:`stage_ms` holds the timings of the latest 64."""
+        return int(self._lib.chi_stage_count(self._h))
+
     def wait(self, ticket=-1):
         """Block until the asynchronous call ``ticket`` (default: everything) has completed."""
         self._check(self._lib.chi_wait(self._h, int(ticket)))

@@ -371,6 +371,9 @@ int chi_last_kernel_ms(chi_handle* h, float* ms_out);
  * oldest first: ms_out[n][4].  CUDA events on the handle's stream, recorded on every
  * batch; the library keeps the last 64.  Synchronises on the newest batch asked for. */
 int chi_stage_ms(chi_handle* h, int n, float* ms_out);
+/* Number of logp / VJP batches (kernel pipelines) enqueued so far; large device batches and the
+ * pipelined host path enqueue several per call. */
+int64_t chi_stage_count(const chi_handle* h);
 /* Number of kernel launches issued by this handle since creation. */
 int64_t chi_launch_count(const chi_handle* h);
 /* Own-microbenchmark peaks of the device the handle is on (the driver's

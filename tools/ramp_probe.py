@@ -15,7 +15,34 @@ prow, plp, pgr = PinnedArray(rows.shape), PinnedArray((B,)), PinnedArray(rows.sh
 pins = [PinnedArray((B, 1)) for _ in range(4)]
 prow.array[...] = rows; pins[0].array[...] = 0; pins[1].array[...] = 0
 out = {"logp": plp.array, "grad": pgr.array, "gcoeff_e": pins[2].array, "gcoeff_a": pins[3].array}
+prow2, plp2, pgr2 = PinnedArray(rows.shape), PinnedArray((B,)), PinnedArray(rows.shape)
+pins2 = [PinnedArray((B, 1)) for _ in range(2)]
+prow2.array[...] = rows
+outs = [out, {"logp": plp2.array, "grad": pgr2.array, "gcoeff_e": pins2[0].array, "gcoeff_a": pins2[1].array}]
+ins = [prow.array, prow2.array]
+
+
+def run_async(n):
+    prev = None
+    for i in range(n):
+        tk = eng.logp_grad_rows_async(ins[i % 2], pins[0].array, pins[1].array, outs[i % 2])
+        if prev is not None:
+            eng.wait(prev)
+        prev = tk
+    eng.wait(prev)
+
+
 for ramp in sys.argv[1:]:
+    if os.environ.get("ASYNC"):
+        os.environ["CHI_PIPE_RAMP"] = ramp
+        best = 1e9
+        for rep in range(3):
+            run_async(4)
+            t0 = time.perf_counter()
+            run_async(30)
+            best = min(best, (time.perf_counter() - t0) / 30 * 1e3)
+        print(f"async ramp {ramp}: {best:.3f} ms", flush=True)
+        continue
     os.environ["CHI_PIPE_RAMP"] = ramp
     best = 1e9
     for rep in range(3):
