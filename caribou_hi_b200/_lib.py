@@ -31,6 +31,7 @@ ERROR_NAMES = {0: "CHI_OK", -1: "CHI_EINVAL", -2: "CHI_ECUDA", -3: "CHI_ENODEV",
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
+_fp = C.POINTER(C.c_float)
 
 
 class ChiConfig(C.Structure):
@@ -127,6 +128,8 @@ SYMBOLS = {
     "chi_stage_count": (C.c_int64, [_H]),
     "chi_spectra": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
     "chi_spectra_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 5),
+    "chi_spectra_f32": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _fp, _fp]),
+    "chi_spectra_f32_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 5),
     "chi_spectra_vjp": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "chi_spectra_vjp_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 8),
     "chi_deterministics": (C.c_int, [_H, C.c_int64, _dp, _dp]),
@@ -171,6 +174,12 @@ def as_dp(a):
     if a is None:
         return None
     return a.ctypes.data_as(_dp)
+
+
+def as_fp(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(_fp)
 
 
 def as_ip(a):

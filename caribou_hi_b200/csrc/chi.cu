@@ -63,7 +63,8 @@ struct DevDataset {
   int S = 0, nb = 0;
   bool has_offset = false;
   Buf vax, chan, basis, offset;  // chan: packed v / p_0 / y / w planes (ChanArgs::chan)
-  void release() { vax.release(); chan.release(); basis.release(); offset.release(); }
+  Buf vax32;                     // (hi, lo) float pair per channel: the single-precision spectra kernels
+  void release() { vax.release(); chan.release(); basis.release(); offset.release(); vax32.release(); }
 };
 
 // One pipeline lane: a stream plus the device workspace a batch needs.  Lane 0 uses the
@@ -403,6 +404,46 @@ int run_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce,
   return CHI_OK;
 }
 
+// single-precision outputs (launch_spectra_f32.cu); the cloud map is the fp64 one
+int run_spectra32(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                  float* mu_e, float* mu_a) {
+  const int N = h->cfg.n_clouds;
+  h->call_first_stage = h->stage_calls;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int rc = launch_cloud_map(h, h->lanes[0], B, theta);
+  if (rc) return rc;
+  Spec32Args a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.cc = h->lanes[0].cc.d();
+  const bool pv = h->cfg.lorentzian != 0;
+  const bool do_e = mu_e && h->has_e, do_a = mu_a && h->has_a;
+  if (do_e) {
+    a.S = h->e.S; a.bg = (float)h->cfg.bg_temp; a.vax32 = (const float*)h->e.vax32.p;
+    a.n_base = h->e.nb; a.basis = h->e.basis.d(); a.offset = h->e.has_offset ? h->e.offset.d() : nullptr;
+    a.coeff = ce; a.mu = mu_e; a.mode = 0;
+    if (do_a && h->shared_axis) {  // one pass for both spectra of a shared axis
+      a.mode = 2;
+      a.n_base_a = h->a.nb; a.basis_a = h->a.basis.d(); a.offset_a = h->a.has_offset ? h->a.offset.d() : nullptr;
+      a.coeff_a = ca; a.mu_a = mu_a;
+    }
+    if (launch_spectra32(N, pv, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  if (do_a && !(do_e && h->shared_axis)) {
+    a.S = h->a.S; a.bg = 0.f; a.vax32 = (const float*)h->a.vax32.p;
+    a.n_base = h->a.nb; a.basis = h->a.basis.d(); a.offset = h->a.has_offset ? h->a.offset.d() : nullptr;
+    a.coeff = ca; a.mu = mu_a; a.mode = 1;
+    a.n_base_a = 0; a.basis_a = nullptr; a.offset_a = nullptr; a.coeff_a = nullptr; a.mu_a = nullptr;
+    if (launch_spectra32(N, pv, a, h->stream)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->ev_pending = true;
+  return CHI_OK;
+}
+
 int check_model_call(chi_handle* h, int64_t B, const double* theta) {
   if (!h) return CHI_EINVAL;
   if (B < 0 || (B > 0 && !theta)) return fail(h, CHI_EINVAL, "theta is NULL or B < 0");
@@ -451,6 +492,16 @@ int upload_dataset(chi_handle* h, DevDataset& d, const chi_dataset* src, int n_s
   CK(d.basis.ensure(std::max<size_t>(1, (size_t)d.nb * S) * sizeof(double)));
   CK(d.offset.ensure(S * sizeof(double)));
   CK(cudaMemcpy(d.vax.p, src->spectral, S * sizeof(double), cudaMemcpyHostToDevice));
+  {
+    std::vector<float> v32(((size_t)S + 1) / 2 * 4, 0.f);
+    for (int s = 0; s < S; ++s) {
+      const float hi = (float)src->spectral[s];
+      v32[2 * s] = hi;
+      v32[2 * s + 1] = (float)(src->spectral[s] - (double)hi);
+    }
+    CK(d.vax32.ensure(v32.size() * sizeof(float)));
+    CK(cudaMemcpy(d.vax32.p, v32.data(), v32.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   CK(cudaMemcpy(d.chan.p, chan.data(), chan.size() * sizeof(double), cudaMemcpyHostToDevice));
   if (d.nb > 0) CK(cudaMemcpy(d.basis.p, src->basis, (size_t)d.nb * S * sizeof(double), cudaMemcpyHostToDevice));
   if (src->offset) CK(cudaMemcpy(d.offset.p, src->offset, S * sizeof(double), cudaMemcpyHostToDevice));
@@ -482,6 +533,56 @@ int finish_timing(chi_handle* h) {
   return CHI_OK;
 }
 
+}  // namespace
+
+namespace {
+inline int run_spectra_any(chi_handle* h, int64_t B, const double* th, const double* ce, const double* ca, double* e, double* a) {
+  return run_spectra(h, B, th, ce, ca, e, a);
+}
+inline int run_spectra_any(chi_handle* h, int64_t B, const double* th, const double* ce, const double* ca, float* e, float* a) {
+  return run_spectra32(h, B, th, ce, ca, e, a);
+}
+
+// host entry point of the predicted spectra, T = double (chi_spectra) or float (chi_spectra_f32)
+template <typename T>
+int host_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca, T* mu_e, T* mu_a) {
+  int rc = check_model_call(h, B, theta);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.n_clouds;
+  const size_t th_b = (size_t)CHI_NSLOT * N * sizeof(double);
+  const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
+  const int Se = h->has_e ? h->e.S : 0, Sa = h->has_a ? h->a.S : 0;
+  const int64_t sub = host_sub_batch(h, (size_t)(Se + Sa) * sizeof(T) + 4096);
+  h->kernel_ms = 0.f;
+  for (int64_t b0 = 0; b0 < B; b0 += sub) {
+    const int64_t nb = std::min(sub, B - b0);
+    CK(h->lanes[0].w_theta.ensure(nb * th_b));
+    CK(cudaMemcpyAsync(h->lanes[0].w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
+    double *d_ce = nullptr, *d_ca = nullptr;
+    T *d_me = nullptr, *d_ma = nullptr;
+    if (ce && nbe) {
+      CK(h->lanes[0].w_ce.ensure(nb * nbe * sizeof(double)));
+      CK(cudaMemcpyAsync(h->lanes[0].w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ce = h->lanes[0].w_ce.d();
+    }
+    if (ca && nba) {
+      CK(h->lanes[0].w_ca.ensure(nb * nba * sizeof(double)));
+      CK(cudaMemcpyAsync(h->lanes[0].w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      d_ca = h->lanes[0].w_ca.d();
+    }
+    if (mu_e && Se) { CK(h->w_mue.ensure((size_t)nb * Se * sizeof(T))); d_me = (T*)h->w_mue.p; }
+    if (mu_a && Sa) { CK(h->w_mua.ensure((size_t)nb * Sa * sizeof(T))); d_ma = (T*)h->w_mua.p; }
+    rc = run_spectra_any(h, nb, h->lanes[0].w_theta.d(), d_ce, d_ca, d_me, d_ma);
+    if (rc) return rc;
+    if (d_me) CK(cudaMemcpyAsync(mu_e + b0 * Se, d_me, (size_t)nb * Se * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    if (d_ma) CK(cudaMemcpyAsync(mu_a + b0 * Sa, d_ma, (size_t)nb * Sa * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    rc = finish_timing(h);
+    if (rc) return rc;
+  }
+  return CHI_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -941,6 +1042,16 @@ int chi_spectra_dev(chi_handle* h, int64_t B, const double* theta, const double*
   return run_spectra(h, B, theta, ce, ca, mu_e, mu_a);
 }
 
+int chi_spectra_f32_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                        float* mu_e, float* mu_a) {
+  int rc = check_model_call(h, B, theta);
+  if (rc) return rc;
+  if (B == 0) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  h->kernel_ms = 0.f;
+  return run_spectra32(h, B, theta, ce, ca, mu_e, mu_a);
+}
+
 int chi_spectra_vjp_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
                         const double* gbar_e, const double* gbar_a, double* grad, double* gce, double* gca) {
   int rc = check_model_call(h, B, theta);
@@ -1263,41 +1374,12 @@ int chi_transform(chi_handle* h, int64_t B, int direction, const double* in, dou
 
 int chi_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
                 double* mu_e, double* mu_a) {
-  int rc = check_model_call(h, B, theta);
-  if (rc) return rc;
-  CK(cudaSetDevice(h->device));
-  const int N = h->cfg.n_clouds;
-  const size_t th_b = (size_t)CHI_NSLOT * N * sizeof(double);
-  const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
-  const int Se = h->has_e ? h->e.S : 0, Sa = h->has_a ? h->a.S : 0;
-  const int64_t sub = host_sub_batch(h, (size_t)(Se + Sa) * sizeof(double) + 4096);
-  h->kernel_ms = 0.f;
-  for (int64_t b0 = 0; b0 < B; b0 += sub) {
-    const int64_t nb = std::min(sub, B - b0);
-    CK(h->lanes[0].w_theta.ensure(nb * th_b));
-    CK(cudaMemcpyAsync(h->lanes[0].w_theta.p, theta + b0 * CHI_NSLOT * N, nb * th_b, cudaMemcpyHostToDevice, h->stream));
-    double *d_ce = nullptr, *d_ca = nullptr, *d_me = nullptr, *d_ma = nullptr;
-    if (ce && nbe) {
-      CK(h->lanes[0].w_ce.ensure(nb * nbe * sizeof(double)));
-      CK(cudaMemcpyAsync(h->lanes[0].w_ce.p, ce + b0 * nbe, nb * nbe * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      d_ce = h->lanes[0].w_ce.d();
-    }
-    if (ca && nba) {
-      CK(h->lanes[0].w_ca.ensure(nb * nba * sizeof(double)));
-      CK(cudaMemcpyAsync(h->lanes[0].w_ca.p, ca + b0 * nba, nb * nba * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-      d_ca = h->lanes[0].w_ca.d();
-    }
-    if (mu_e && Se) { CK(h->w_mue.ensure((size_t)nb * Se * sizeof(double))); d_me = h->w_mue.d(); }
-    if (mu_a && Sa) { CK(h->w_mua.ensure((size_t)nb * Sa * sizeof(double))); d_ma = h->w_mua.d(); }
-    rc = run_spectra(h, nb, h->lanes[0].w_theta.d(), d_ce, d_ca, d_me, d_ma);
-    if (rc) return rc;
-    if (d_me) CK(cudaMemcpyAsync(mu_e + b0 * Se, d_me, (size_t)nb * Se * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (d_ma) CK(cudaMemcpyAsync(mu_a + b0 * Sa, d_ma, (size_t)nb * Sa * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    rc = finish_timing(h);
-    if (rc) return rc;
-  }
-  return CHI_OK;
+  return host_spectra<double>(h, B, theta, ce, ca, mu_e, mu_a);
+}
+
+int chi_spectra_f32(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                    float* mu_e, float* mu_a) {
+  return host_spectra<float>(h, B, theta, ce, ca, mu_e, mu_a);
 }
 
 int chi_spectra_vjp(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,

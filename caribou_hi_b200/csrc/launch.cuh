@@ -28,6 +28,26 @@ struct SpecArgs {
   const double* __restrict__ coeff_a;
   double* __restrict__ mu_a;
 };
+// argument block of the single-precision spectra kernels (launch_spectra_f32.cu)
+struct Spec32Args {
+  int64_t B;
+  int N;
+  int S;
+  int mode;  // 0: emission, 1: absorption, 2: both spectra of a shared axis
+  int n_base, n_base_a;
+  float bg;
+  const float* __restrict__ vax32;    // [2*ceil(S/2)][2]: (hi, lo) float pair per channel
+  const double* __restrict__ basis;   // dataset of the first output (absorption in mode 1)
+  const double* __restrict__ offset;
+  const double* __restrict__ coeff;
+  const double* __restrict__ basis_a; // absorption dataset of mode 2
+  const double* __restrict__ offset_a;
+  const double* __restrict__ coeff_a;
+  const double* __restrict__ cc;
+  float* __restrict__ mu;             // [B][S]
+  float* __restrict__ mu_a;           // [B][S], mode 2
+};
+int launch_spectra32(int N, bool pv, const Spec32Args& a, cudaStream_t st);
 int launch_spectra(int N, bool pv, const SpecArgs& a, cudaStream_t st);
 int launch_spectra_ea(int N, bool pv, const SpecArgs& a, cudaStream_t st);
 struct FusedArgs;

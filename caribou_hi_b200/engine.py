@@ -353,8 +353,14 @@ class Engine:
         """Block until the asynchronous call ``ticket`` (default: everything) has completed."""
         self._check(self._lib.chi_wait(self._h, int(ticket)))
 
-    def spectra(self, theta, coeff_e=None, coeff_a=None):
-        """Predicted spectra ``(mu_e [B, S_e] | None, mu_a [B, S_a] | None)``."""
+    def spectra(self, theta, coeff_e=None, coeff_a=None, dtype=np.float64):
+        """Predicted spectra ``(mu_e [B, S_e] | None, mu_a [B, S_a] | None)``.  ``dtype=np.float32``
+        selects the single-precision kernels (``chi_spectra_f32``: float32 outputs within 1e-5 of the
+        largest value of each fp64 spectrum; parameters and their maps stay fp64)."""
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("spectra: dtype must be float64 or float32")
+        f32 = dtype == np.dtype(np.float32)
         N = self.n_clouds
         theta = _f64(theta)
         B = theta.shape[0]
@@ -362,12 +368,18 @@ class Engine:
             raise ValueError("theta: bad shape")
         ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
         ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
-        mu_e = np.empty((B, self.S_e), dtype=np.float64) if self.has_emission else None
-        mu_a = np.empty((B, self.S_a), dtype=np.float64) if self.has_absorption else None
-        self._check(
-            self._lib.chi_spectra(self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca),
-                                  _lib.as_dp(mu_e), _lib.as_dp(mu_a))
-        )
+        mu_e = np.empty((B, self.S_e), dtype=dtype) if self.has_emission else None
+        mu_a = np.empty((B, self.S_a), dtype=dtype) if self.has_absorption else None
+        if f32:
+            self._check(
+                self._lib.chi_spectra_f32(self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca),
+                                          _lib.as_fp(mu_e), _lib.as_fp(mu_a))
+            )
+        else:
+            self._check(
+                self._lib.chi_spectra(self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca),
+                                      _lib.as_dp(mu_e), _lib.as_dp(mu_a))
+            )
         return mu_e, mu_a
 
     def spectra_vjp(self, theta, gbar_e=None, gbar_a=None, coeff_e=None, coeff_a=None):
@@ -522,6 +534,11 @@ class Engine:
     def spectra_dev(self, B, theta, mu_e=None, mu_a=None, coeff_e=None, coeff_a=None):
         p = self._ptr
         self._check(self._lib.chi_spectra_dev(self._h, int(B), p(theta), p(coeff_e), p(coeff_a), p(mu_e), p(mu_a)))
+
+    def spectra_f32_dev(self, B, theta, mu_e=None, mu_a=None, coeff_e=None, coeff_a=None):
+        """:meth:`spectra_dev` with float32 outputs (``chi_spectra_f32_dev``)."""
+        p = self._ptr
+        self._check(self._lib.chi_spectra_f32_dev(self._h, int(B), p(theta), p(coeff_e), p(coeff_a), p(mu_e), p(mu_a)))
 
     def spectra_vjp_dev(self, B, theta, grad, gbar_e=None, gbar_a=None, coeff_e=None, coeff_a=None,
                         gcoeff_e=None, gcoeff_a=None):

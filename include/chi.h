@@ -282,6 +282,15 @@ int chi_spectra(chi_handle* h, int64_t B, const double* theta, const double* coe
                 const double* coeff_a, double* mu_e_out, double* mu_a_out);
 int chi_spectra_dev(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
                     const double* coeff_a, double* mu_e_out, double* mu_a_out);
+/* The same spectra in single precision (the optional fp32 path of posterior / prior predictive
+ * generation: half the output bytes, channel loop on the FP32 pipe and the SFU).  theta and the
+ * parameter maps stay fp64; each spectrum agrees with chi_spectra to 1e-5 of its largest value
+ * (compensated v - c, cancellation-free 1 - exp(-tau)).  logp and gradients have no fp32 form:
+ * at realistic signal-to-noise the residual y - mu loses 3-4 digits. */
+int chi_spectra_f32(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                    const double* coeff_a, float* mu_e_out, float* mu_a_out);
+int chi_spectra_f32_dev(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                        const double* coeff_a, float* mu_e_out, float* mu_a_out);
 
 /* Vector-Jacobian product of chi_spectra: given cotangents gbar_e[B][S_e],
  * gbar_a[B][S_a] (NULL = zeros) returns grad_out[B][CHI_NSLOT][N] and the baseline

@@ -24,9 +24,26 @@ def run(B, N, S, pv):
     ms = e0.elapsed_time(e1) / 5
     units = B * N * 2 * S
     print(f"spectra B={B} N={N} S={S}+{S} pv={int(pv)}: {ms:.3f} ms -> {units/ms/1e6:.1f} Gunits/s, output {2*B*S*8/ms/1e6:.0f} GB/s", flush=True)
+    # single precision (chi_spectra_f32_dev): same draws, float32 outputs
+    e32 = torch.empty((B, S), dtype=torch.float32, device="cuda"); a32 = torch.empty((B, S), dtype=torch.float32, device="cuda")
+    for _ in range(2): eng.spectra_f32_dev(B, theta, e32, a32)
+    eng.synchronize()
+    e0.record(stream)
+    for _ in range(5): eng.spectra_f32_dev(B, theta, e32, a32)
+    e1.record(stream); eng.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    def worst(x32, x64):
+        ok = torch.isfinite(x64).all(dim=1)
+        scale = x64[ok].abs().amax(dim=1, keepdim=True)
+        return float(((x32[ok].double() - x64[ok]).abs() / scale).max())
+    print(f"  f32: {ms:.3f} ms -> {units/ms/1e6:.1f} Gunits/s, output {2*B*S*4/ms/1e6:.0f} GB/s; worst |f32-f64|/max|f64| "
+          f"emission {worst(e32, mu_e):.2e} absorption {worst(a32, mu_a):.2e}", flush=True)
     eng.close()
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "c5":  # profiling target: BASELINE configs[4] per-GPU shape only
+        run(int(sys.argv[2]) if len(sys.argv) > 2 else 25000, 8, 4096, True)
+        sys.exit(0)
     run(25000, 8, 4096, True)
     run(25000, 8, 4096, False)
     run(100000, 4, 1000, False)
