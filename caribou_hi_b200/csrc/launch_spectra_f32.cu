@@ -12,10 +12,10 @@
 //     pairs, d = (v_hi - c_hi) + (v_lo - c_lo): the first difference is correctly rounded
 //     relative to d itself.
 //   * 1 - exp(-tau) for optically thin warm gas (tau ~ 1e-3, Ts ~ 1e4 K): the cancellation
-//     leaves 6e-8 * Ts absolute.  For -tau' > -0.25 a degree-5 polynomial of 1 - 2^x is selected
-//     (branch-free) instead of 1 - ex2(x).
-//   * bg * P - bg with P = prod(1 - f + f e^-tau) ~ 1: the kernel accumulates R = 1 - P.
-// Two adjacent channels per thread (float4 axis load, float2 stores, constants loaded once).
+//     leaves 6e-8 * Ts absolute.  For -tau' > -1/8 a cubic-times-x polynomial of 1 - 2^x is
+//     selected (branch-free) instead of 1 - ex2(x).
+//   * bg * P - bg with P = prod(1 - f + f e^-tau) ~ 1: the kernel accumulates R = 1 - P beside P.
+// Adjacent channel pairs per thread (float4 axis loads, float2 stores).
 #include "launch.cuh"
 
 namespace chi {
@@ -30,26 +30,31 @@ __device__ __forceinline__ float rcpf(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 1 - 2^x for x <= 0 to ~2e-7 relative: polynomial near 0 (no cancellation), 1 - ex2 elsewhere
+// 1 - 2^x for x <= 0 to ~1.5e-6 relative: cubic near 0 (no cancellation), 1 - ex2 elsewhere
 __device__ __forceinline__ float one_minus_exp2(float x) {
   const float direct = 1.0f - ex2f(x);
-  // -(2^x - 1) = -x (c1 + x (c2 + x (c3 + x (c4 + x (c5 + x c6))))), c_k = ln2^k / k!
-  float p = fmaf(x, 1.5403530e-4f, 1.3333558e-3f);
-  p = fmaf(x, p, 9.6181291e-3f);
-  p = fmaf(x, p, 5.5504109e-2f);
+  // -(2^x - 1) = -x (c1 + x (c2 + x (c3 + x c4))), c_k = ln2^k / k!; |x| <= 1/8: next term 5e-7
+  float p = fmaf(x, 9.6181291e-3f, 5.5504109e-2f);
   p = fmaf(x, p, 2.4022651e-1f);
   p = fmaf(x, p, 6.9314718e-1f);
-  return x > -0.25f ? -x * p : direct;
+  return x > -0.125f ? -x * p : direct;
 }
 
-// MODE 0: emission only, 1: absorption only, 2: both spectra of a shared axis in one pass
 #ifndef CHI_S32_MINB
-#define CHI_S32_MINB 4
+#define CHI_S32_MINB 5
 #endif
+#ifndef CHI_S32_CPT
+#define CHI_S32_CPT 4
+#endif
+
+// MODE 0: emission only, 1: absorption only, 2: both spectra of a shared axis in one pass.
+// A thread carries CPT channels (CPT/2 adjacent pairs, 512 channels apart) through the cloud loop,
+// so the constants of a cloud are loaded once per CPT channels.
 template <int N, bool PV, int MODE>
-__global__ void __launch_bounds__(256, CHI_S32_MINB) k_spectra32_t(Spec32Args a) {
-  constexpr bool EM = MODE != 1, AB = MODE != 0;
-  // per cloud: [c_hi, c_lo, -k', -AG_e' (or -AG_a' in MODE 1)] [f*Ts, f, -AG_a', h] [-AL_e' (-AL_a' in MODE 1), -AL_a', -, -]
+__global__ void __launch_bounds__(256, (N <= 8 ? CHI_S32_MINB : 3)) k_spectra32_t(Spec32Args a) {
+  constexpr bool EM = MODE != 1;
+  constexpr int CPT = CHI_S32_CPT, NP = CPT / 2;
+  // per cloud: [c_hi, c_lo, -k', -AG_e' (-AG_a' in MODE 1)] [f*Ts, f, -AG_a', h] [-AL_e' (-AL_a' in MODE 1), -AL_a', -, -]
   __shared__ __align__(16) float s_c[N][12];
   __shared__ double s_beta[2][CHI_MAX_BASELINE];
   const int64_t b = blockIdx.x;
@@ -85,32 +90,19 @@ __global__ void __launch_bounds__(256, CHI_S32_MINB) k_spectra32_t(Spec32Args a)
   float* __restrict__ out0 = a.mu + b * S;      // emission (MODE 0, 2) or absorption (MODE 1)
   float* __restrict__ out1 = a.mu_a + b * S;    // absorption of MODE 2
   const float4* __restrict__ vax = reinterpret_cast<const float4*>(a.vax32);  // padded to an even channel count
-  for (int s = 2 * threadIdx.x; s < S; s += 2 * blockDim.x) {
-    const float4 v = vax[s >> 1];  // (hi, lo) of channels s and s + 1
-    const bool two = s + 1 < S;
-    float base0[2] = {0.0f, 0.0f}, base1[2] = {0.0f, 0.0f};
-    if (a.offset || a.n_base) {
+  const float nbg = -a.bg;
+  for (int s0 = 2 * threadIdx.x; s0 < S; s0 += 512 * NP) {
+    float vh[CPT], vl[CPT];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int sj = two ? s + j : s;
-        double t = a.offset ? a.offset[sj] : 0.0;
-#pragma unroll 1
-        for (int i = 0; i < a.n_base; ++i) t = fma(s_beta[0][i], a.basis[(int64_t)i * S + sj], t);
-        base0[j] = (float)t;
-      }
+    for (int p = 0; p < NP; ++p) {
+      const int s = s0 + 512 * p;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s < S) v = vax[s >> 1];  // (hi, lo) of channels s and s + 1
+      vh[2 * p] = v.x; vl[2 * p] = v.y; vh[2 * p + 1] = v.z; vl[2 * p + 1] = v.w;
     }
-    if (MODE == 2 && (a.offset_a || a.n_base_a)) {
+    float R[CPT], P[CPT], T[CPT], xs[CPT];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int sj = two ? s + j : s;
-        double t = a.offset_a ? a.offset_a[sj] : 0.0;
-#pragma unroll 1
-        for (int i = 0; i < a.n_base_a; ++i) t = fma(s_beta[1][i], a.basis_a[(int64_t)i * S + sj], t);
-        base1[j] = (float)t;
-      }
-    }
-    const float vh[2] = {v.x, v.z}, vl[2] = {v.y, v.w};
-    float R[2] = {0.0f, 0.0f}, P[2] = {1.0f, 1.0f}, T[2] = {0.0f, 0.0f}, xs[2] = {0.0f, 0.0f};
+    for (int j = 0; j < CPT; ++j) { R[j] = 0.0f; P[j] = 1.0f; T[j] = 0.0f; xs[j] = 0.0f; }
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       const float4 q0 = *reinterpret_cast<const float4*>(&s_c[n][0]);
@@ -118,7 +110,7 @@ __global__ void __launch_bounds__(256, CHI_S32_MINB) k_spectra32_t(Spec32Args a)
       float2 q2 = make_float2(0.0f, 0.0f);
       if (PV) q2 = *reinterpret_cast<const float2*>(&s_c[n][8]);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < CPT; ++j) {
         const float d = (vh[j] - q0.x) + (vl[j] - q0.y);
         const float d2 = d * d;
         const float E = ex2f(q0.z * d2);
@@ -132,33 +124,53 @@ __global__ void __launch_bounds__(256, CHI_S32_MINB) k_spectra32_t(Spec32Args a)
         if (EM) {
           const float u = one_minus_exp2(x) * P[j];
           T[j] = fmaf(q1.x, u, T[j]);
-          R[j] = fmaf(q1.y, u, R[j]);
-          P[j] = 1.0f - R[j];
+          R[j] = fmaf(q1.y, u, R[j]);   // 1 - P without the cancellation
+          P[j] = fmaf(-q1.y, u, P[j]);
         } else {
           xs[j] += x;
         }
       }
     }
-    float r0[2], r1[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (EM) r0[j] = fmaf(-a.bg, R[j], T[j]) + base0[j];
-      else r0[j] = one_minus_exp2(xs[j]) + base0[j];
-      if (MODE == 2) r1[j] = one_minus_exp2(xs[j]) + base1[j];
-    }
-    if (even) {
-      *reinterpret_cast<float2*>(out0 + s) = make_float2(r0[0], r0[1]);
-      if (MODE == 2) *reinterpret_cast<float2*>(out1 + s) = make_float2(r1[0], r1[1]);
-    } else {
-      out0[s] = r0[0];
-      if (two) out0[s + 1] = r0[1];
-      if (MODE == 2) {
-        out1[s] = r1[0];
-        if (two) out1[s + 1] = r1[1];
+    for (int p = 0; p < NP; ++p) {
+      const int s = s0 + 512 * p;
+      if (s >= S) break;
+      const bool two = s + 1 < S;
+      float r0[2], r1[2] = {0.0f, 0.0f};
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * p + jj;
+        const int sj = two ? s + jj : s;
+        float base0 = 0.0f, base1 = 0.0f;
+        if (a.offset || a.n_base) {
+          double t = a.offset ? a.offset[sj] : 0.0;
+#pragma unroll 1
+          for (int i = 0; i < a.n_base; ++i) t = fma(s_beta[0][i], a.basis[(int64_t)i * S + sj], t);
+          base0 = (float)t;
+        }
+        if (MODE == 2 && (a.offset_a || a.n_base_a)) {
+          double t = a.offset_a ? a.offset_a[sj] : 0.0;
+#pragma unroll 1
+          for (int i = 0; i < a.n_base_a; ++i) t = fma(s_beta[1][i], a.basis_a[(int64_t)i * S + sj], t);
+          base1 = (float)t;
+        }
+        if (EM) r0[jj] = fmaf(nbg, R[j], T[j]) + base0;
+        else r0[jj] = one_minus_exp2(xs[j]) + base0;
+        if (MODE == 2) r1[jj] = one_minus_exp2(xs[j]) + base1;
+      }
+      if (even) {
+        *reinterpret_cast<float2*>(out0 + s) = make_float2(r0[0], r0[1]);
+        if (MODE == 2) *reinterpret_cast<float2*>(out1 + s) = make_float2(r1[0], r1[1]);
+      } else {
+        out0[s] = r0[0];
+        if (two) out0[s + 1] = r0[1];
+        if (MODE == 2) {
+          out1[s] = r1[0];
+          if (two) out1[s + 1] = r1[1];
+        }
       }
     }
   }
-  (void)AB;
 }
 
 template <int N, bool PV>
