@@ -244,10 +244,11 @@ class _HIBase(ABC):
         theta, ce, ca, _ = self._split(point)
         return self.engine.logp_grad(theta, ce, ca, want_grad=False)[0]
 
-    def predict(self, point):
-        """Predicted spectra per draw: the ``mu`` of the observed Normal nodes."""
+    def predict(self, point, dtype=np.float64):
+        """Predicted spectra per draw: the ``mu`` of the observed Normal nodes.  ``dtype=np.float32``
+        takes the single-precision kernels (1e-5 of each spectrum's largest value, half the bytes)."""
         theta, ce, ca, _ = self._split(point)
-        mu_e, mu_a = self.engine.spectra(theta, ce, ca)
+        mu_e, mu_a = self.engine.spectra(theta, ce, ca, dtype=dtype)
         out = {}
         if mu_e is not None:
             out["emission"] = mu_e
