@@ -76,6 +76,10 @@ struct Lane {
   // small batches run the absorption kernel on `aux`, concurrently with the emission kernel
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // small batches: the Jacobian of the parameter maps (k_jacobian) runs on `jac` next to the channel kernels
+  cudaStream_t jac = nullptr;
+  cudaEvent_t ev_jac = nullptr;
+  Buf jacbuf;
   // pipelined host path: the epilogue and the downloads of a piece run on a high-priority stream, so
   // that they are not starved by the channel kernels of the following pieces (which were queued
   // first and would otherwise keep every SM until they drain) and the lane is free again early
@@ -86,7 +90,7 @@ struct Lane {
   Buf xcon, prior;                                                // constrained values, per-cloud priors
   Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca;    // staging of the host entry points
   void release() {
-    Buf* bufs[] = {&cc, &mom_e, &mom_a, &xcon, &prior, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
+    Buf* bufs[] = {&cc, &mom_e, &mom_a, &xcon, &prior, &jacbuf, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
     for (Buf* b : bufs) b->release();
   }
 };
@@ -176,7 +180,11 @@ int ab_record(const chi_handle* h) {
 void pick_chunks(const chi_handle* h, int64_t B, int S, int* n_chunks, int* chunk_len) {
   const int64_t target = (int64_t)h->n_sm * 16;  // warp items wanted per launch
   int64_t want = (target + B - 1) / B;
-  int max_chunks = std::max(1, S / 128);  // at least 4 channel iterations per lane
+  static const int min_len = [] {  // tuning knob: shortest chunk, in channels
+    const char* e = getenv("CHI_CHUNK_MIN");
+    return e ? std::max(32, atoi(e)) : 128;
+  }();
+  int max_chunks = std::max(1, S / min_len);  // at least 4 channel iterations per lane
   int nc = (int)std::min<int64_t>(std::max<int64_t>(want, 1), max_chunks);
   int len = (S + nc - 1) / nc;
   len = (len + 31) / 32 * 32;
@@ -250,6 +258,34 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   const bool do_e = h->has_e && (!vjp || gbar_e);
   const bool do_a = h->has_a && (!vjp || gbar_a);
   bool fused_done = false;
+
+  // Small batches are bound by dependent latency, not throughput: the Jacobian of the per-cloud maps
+  // (forward-mode duals, needs theta only) runs on the lane's `jac` stream NEXT TO the channel
+  // kernels, and a short contraction kernel replaces the epilogue behind them.  (The choice follows
+  // the size of the caller's batch, not of a pipeline piece: every draw of a call goes through the
+  // same arithmetic whatever piece it lands in.)
+  const int K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
+  const int64_t B_call = std::max<int64_t>(B, h->call_draws);
+  const bool small = B_call * N * K <= (int64_t)h->n_sm * 1024 && N * K <= 128;
+  static const bool old_split = getenv("CHI_OLD_SPLIT") != nullptr;  // A/B knob: split epilogue on the main stream
+  const bool side_jac = small && !old_split && !h->epilogue_on_hi;
+  if (side_jac && (grad || model)) {
+    const bool fused = h->shared_axis && (do_e || do_a);
+    JacArgs ja;
+    memset(&ja, 0, sizeof(ja));
+    ja.B = B; ja.N = N; ja.rm = h->rm; ja.has_e = (fused || do_e) ? 1 : 0; ja.has_a = (fused || do_a) ? 1 : 0;
+    ja.theta = theta; ja.u = u;
+    CK(L.jacbuf.ensure((size_t)B * N * K * CHI_JAC_W * sizeof(double)));
+    CK(L.prior.ensure((size_t)B * N * sizeof(double)));
+    ja.jac = L.jacbuf.d(); ja.prior = L.prior.d();
+    CK(cudaStreamWaitEvent(L.jac, L.ev_fork, 0));  // theta (and, in model mode, the constrained values) are ready
+    const unsigned gj = (unsigned)((B * N * K + 127) / 128);
+    if (model) { MODEL_SWITCH(h->cfg.model, (k_jacobian<M, true><<<gj, 128, 0, L.jac>>>(h->map, ja))); }
+    else { MODEL_SWITCH(h->cfg.model, (k_jacobian<M, false><<<gj, 128, 0, L.jac>>>(h->map, ja))); }
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(L.ev_jac, L.jac));
+  }
   if (h->shared_axis && (do_e || do_a)) {
     // both datasets on one axis: one pass evaluates exp(-k d^2) once for the two of them
     FusedArgs a;
@@ -328,13 +364,17 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   if (gce && !do_e && h->e.nb > 0) CK(cudaMemsetAsync(gce, 0, (size_t)B * h->e.nb * sizeof(double), es));
   if (gca && !do_a && h->a.nb > 0) CK(cudaMemsetAsync(gca, 0, (size_t)B * h->a.nb * sizeof(double), es));
 
-  // small batches are bound by the dependent chain of the per-cloud map: split the tangent
-  // directions over threads; large batches take the fused form (half the arithmetic)
-  const int K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
-  // (the choice follows the size of the caller's batch, not of a pipeline piece: every draw of a
-  // call goes through the same arithmetic whatever piece it lands in)
-  const int64_t B_call = std::max<int64_t>(B, h->call_draws);
-  if (B_call * N * K <= (int64_t)h->n_sm * 1024 && N * K <= 128) {
+  if (side_jac) {
+    ConArgs ca_;
+    memset(&ca_, 0, sizeof(ca_));
+    ca_.e = ea; ca_.K = K; ca_.cc = L.cc.d();
+    ca_.jac = (grad || model) ? L.jacbuf.d() : nullptr; ca_.prior = L.prior.d();
+    if (grad || model) CK(cudaStreamWaitEvent(es, L.ev_jac, 0));
+    if (model) k_contract<true><<<(unsigned)B, 128, 0, es>>>(ca_);
+    else k_contract<false><<<(unsigned)B, 128, 0, es>>>(ca_);
+  } else
+  // split epilogue (kept as the A/B reference of the path above; N * K > 128 also lands here)
+  if (small) {
     unsigned grid = (unsigned)((B * N * K + 127) / 128);
     if (model) {  // whole draws per block
       const int per = N * K, bd = (128 / per) * per;
@@ -659,7 +699,9 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
   for (int i = 0; ok && i < CHI_LANES; ++i)
     ok = cudaStreamCreateWithFlags(&h->lanes[i].aux, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&h->lanes[i].ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&h->lanes[i].ev_join, cudaEventDisableTiming) == cudaSuccess;
+         cudaEventCreateWithFlags(&h->lanes[i].ev_join, cudaEventDisableTiming) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&h->lanes[i].jac, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->lanes[i].ev_jac, cudaEventDisableTiming) == cudaSuccess;
   {
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
@@ -699,6 +741,8 @@ void chi_destroy(chi_handle* h) {
   for (Lane& L : h->lanes) {
     if (L.ev_fork) cudaEventDestroy(L.ev_fork);
     if (L.ev_join) cudaEventDestroy(L.ev_join);
+    if (L.ev_jac) cudaEventDestroy(L.ev_jac);
+    if (L.jac) cudaStreamDestroy(L.jac);
     if (L.ev_mom) cudaEventDestroy(L.ev_mom);
     if (L.ev_tail) cudaEventDestroy(L.ev_tail);
     if (L.hi) cudaStreamDestroy(L.hi);

@@ -323,6 +323,204 @@ __global__ void __launch_bounds__(128) k_epilogue(MapCfg cfg, EpiArgs a) {
       if (a.rm.row[s] >= 0) go[(int64_t)a.rm.row[s] * a.N] = 0.0;
 }
 
+// ---------------------------------------------------------------------------
+// Small batches (a few dozen chains): the epilogue above is one dependent chain -- chunk sums, then
+// the Dual evaluation of the map, then the contraction -- and it sits behind the channel kernels.
+// The Jacobian of the map depends on theta only, so it is split off: k_jacobian runs on a side
+// stream NEXT TO the channel kernels, and k_contract (a block per draw: coalesced chunk sums into
+// shared memory, then one thread per (cloud, direction)) is all that is left on the critical path.
+// Same arithmetic as k_epilogue<MODEL, true, PRIOR>; record per (draw, cloud, direction):
+//   [dk_e, dAG_e, dAL_e, dh_e, dk_a, dAG_a, dAL_a, dh_a, dTs, df, dc, d(prior density), dx/du, w dlogJ/du]
+// ---------------------------------------------------------------------------
+#define CHI_JAC_W 14
+struct JacArgs {
+  int64_t B;
+  int N;
+  RowMap rm;
+  int has_e, has_a;
+  const double* __restrict__ theta;  // constrained values
+  const double* __restrict__ u;      // unconstrained values (PRIOR)
+  double* __restrict__ jac;          // [B][N][K][CHI_JAC_W]
+  double* __restrict__ prior;        // [B][N] prior density + log-Jacobian of the cloud (PRIOR)
+};
+
+template <int MODEL, bool PRIOR>
+__global__ void __launch_bounds__(128) k_jacobian(MapCfg cfg, JacArgs a) {
+  constexpr int K = (MODEL == CHI_MODEL_PHYSICS) ? 7 : CHI_NSLOT;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.B * a.N * K) return;
+  const int j0 = (int)(t % K);
+  const int64_t bn = t / K;
+  const int64_t b = bn / a.N;
+  const int n = (int)(bn - b * a.N);
+  typedef Dual<1> D;
+  D th[CHI_NSLOT];
+  const double* tp = a.theta + (b * a.rm.n_rows) * a.N + n;
+#pragma unroll
+  for (int s = 0; s < CHI_NSLOT; ++s) {
+    th[s] = D(a.rm.row[s] >= 0 ? tp[(int64_t)a.rm.row[s] * a.N] : 0.0);
+    th[s].d[0] = (s == j0) ? 1.0 : 0.0;
+  }
+  CloudPhys<D> ph = cloud_phys<MODEL, D>(cfg, th);
+  double* o = a.jac + t * CHI_JAC_W;
+#pragma unroll
+  for (int i = 0; i < CHI_JAC_W; ++i) o[i] = 0.0;
+  if (a.has_e) {
+    ProfConst<D> pe = profile_consts<D>(ph.fwhm2, ph.fwhm_L, ph.tau_total, cfg.wch2_e, cfg.lorentzian != 0);
+    o[0] = pe.k.d[0]; o[1] = pe.AG.d[0]; o[2] = pe.AL.d[0]; o[3] = pe.h.d[0];
+  }
+  if (a.has_a) {
+    ProfConst<D> pa = profile_consts<D>(ph.fwhm2, ph.fwhm_L, D(ph.wt * ph.tau_total), cfg.wch2_a,
+                                        cfg.lorentzian != 0);
+    o[4] = pa.k.d[0]; o[5] = pa.AG.d[0]; o[6] = pa.AL.d[0]; o[7] = pa.h.d[0];
+  }
+  o[8] = ph.tspin.d[0]; o[9] = ph.ff.d[0]; o[10] = ph.velocity.d[0];
+  if (PRIOR) {
+    const double* up = a.u + (b * CHI_NSLOT) * a.N + n;
+    const D thermal = (MODEL == CHI_MODEL_EMISSION_ABSORPTION) ? ph.tkin : ph.fwhm2_thermal;
+    D lp(0.0);
+    double logj = 0.0;
+#pragma unroll
+    for (int s = 0; s < CHI_NSLOT; ++s) {
+      const int dist = slot_dist<MODEL>(cfg, s);
+      if (dist == PD_NONE) continue;
+      const double w = (s == CHI_FR_FWHM_L_NORM) ? cfg.fwhm_L_weight : 1.0;
+      lp = lp + w * slot_density<D>(cfg, dist, th[s], thermal);
+      logj += w * slot_backward(dist, up[(int64_t)s * a.N]).logj;
+    }
+    const int dist = slot_dist<MODEL>(cfg, j0);
+    const double w = (j0 == CHI_FR_FWHM_L_NORM) ? cfg.fwhm_L_weight : 1.0;
+    const Transformed tr = slot_backward(dist, up[(int64_t)j0 * a.N]);
+    o[11] = lp.d[0]; o[12] = tr.dxdu; o[13] = w * tr.dlogj;
+    if (j0 == 0) a.prior[bn] = lp.v + logj;
+  }
+}
+
+struct ConArgs {
+  EpiArgs e;
+  int K;                            // tangent directions per cloud
+  const double* __restrict__ cc;    // [B][N][CHI_CC_STRIDE]
+  const double* __restrict__ jac;   // k_jacobian's records (null: no gradient wanted)
+  const double* __restrict__ prior; // [B][N] (PRIOR)
+};
+
+#define CHI_CON_MAXREC 192
+template <bool PRIOR>
+__global__ void __launch_bounds__(128) k_contract(ConArgs c) {
+  const EpiArgs& a = c.e;
+  __shared__ double s_e[CHI_CON_MAXREC], s_a[CHI_CON_MAXREC];
+  const int64_t b = blockIdx.x;
+  const bool use_e = a.fused || a.has_e, use_a = a.has_a && !a.fused;
+  // --- sums over channel chunks (fixed order: deterministic), one record element per thread ---
+  if (use_e) {
+    const double* p = a.mom_e + (b * a.chunks_e) * a.stride_e;
+    for (int t = threadIdx.x; t < a.stride_e; t += blockDim.x) {
+      double v = 0.0;
+#pragma unroll 4
+      for (int ch = 0; ch < a.chunks_e; ++ch) v += p[(int64_t)ch * a.stride_e + t];
+      s_e[t] = v;
+    }
+  }
+  if (use_a) {
+    const double* p = a.mom_a + (b * a.chunks_a) * a.stride_a;
+    for (int t = threadIdx.x; t < a.stride_a; t += blockDim.x) {
+      double v = 0.0;
+#pragma unroll 4
+      for (int ch = 0; ch < a.chunks_a; ++ch) v += p[(int64_t)ch * a.stride_a + t];
+      s_a[t] = v;
+    }
+  }
+  __syncthreads();
+  // --- baseline-coefficient gradients: thread i handles coefficient i ---
+  const int nbe = use_e ? a.nb_e : 0, nba = (a.fused || use_a) ? a.nb_a : 0;
+  if ((int)threadIdx.x < nbe + nba) {
+    const int i = threadIdx.x;
+    if (i < nbe) {
+      double g = s_e[1 + i];
+      if (PRIOR) g -= (a.coeff_e ? a.coeff_e[b * a.nb_e + i] : 0.0) / (a.bsig_e[i] * a.bsig_e[i]);
+      if (a.gcoeff_e) a.gcoeff_e[b * a.nb_e + i] = g;
+    } else {
+      const int k = i - nbe;
+      double g = a.fused ? s_e[1 + a.nb_e + k] : s_a[1 + k];
+      if (PRIOR) g -= (a.coeff_a ? a.coeff_a[b * a.nb_a + k] : 0.0) / (a.bsig_a[k] * a.bsig_a[k]);
+      if (a.gcoeff_a) a.gcoeff_a[b * a.nb_a + k] = g;
+    }
+  }
+  // --- logp: last warp's first thread (the first threads carry the gradient) ---
+  if (threadIdx.x == blockDim.x - 32 && a.logp) {
+    double lp = (use_e ? s_e[0] : 0.0) + (use_a ? s_a[0] : 0.0);
+    if (PRIOR) {
+      for (int i = 0; i < nbe; ++i) {
+        const double x = a.coeff_e ? a.coeff_e[b * a.nb_e + i] : 0.0, s = a.bsig_e[i];
+        lp += -0.5 * (x / s) * (x / s) - log(s) - CHI_HALF_LOG_2PI;
+      }
+      for (int i = 0; i < nba; ++i) {
+        const double x = a.coeff_a ? a.coeff_a[b * a.nb_a + i] : 0.0, s = a.bsig_a[i];
+        lp += -0.5 * (x / s) * (x / s) - log(s) - CHI_HALF_LOG_2PI;
+      }
+    }
+    lp += a.lconst ? a.lconst[a.sl ? a.sl[b] : 0] : 0.0;
+    if (PRIOR)
+      for (int n = 0; n < a.N; ++n) lp += c.prior[b * a.N + n];
+    a.logp[b] = lp;
+  }
+  if (!a.grad || (int)threadIdx.x >= a.N * c.K) return;
+
+  // --- one thread per (cloud, direction): adjoints of the cloud constants times their tangents ---
+  const int n = threadIdx.x / c.K, j0 = threadIdx.x - n * c.K;
+  const double* cc = c.cc + (b * a.N + n) * CHI_CC_STRIDE;
+  const double* J = c.jac + ((b * a.N + n) * c.K + j0) * CHI_JAC_W;
+  const double f = cc[CC_F];
+  double g = 0.0, cbar = 0.0;
+  if (a.fused) {
+    const int NF = a.pv ? 10 : 6;
+    const double* mf = s_e + 1 + a.nb_e + a.nb_a + n * NF;
+    cbar = 2.0 * cc[CC_KE] * mf[2] + (a.pv ? 2.0 * mf[9] : 0.0);
+    g = fma(-mf[3], J[0], g);
+    g = fma(f * mf[0], J[1], g);
+    if (a.pv) {
+      g = fma(f * mf[6], J[2], g);
+      g = fma(-mf[8], J[3], g);
+    }
+    g = fma(mf[1], J[5], g);
+    if (a.pv) g = fma(mf[7], J[6], g);
+    g = fma(f * mf[4], J[8], g);
+    g = fma(mf[5], J[9], g);
+  } else if (a.has_e) {
+    const int NE = a.pv ? 8 : 5;
+    const double* me = s_e + 1 + a.nb_e + n * NE;
+    const double AG = cc[CC_AGE], AL = cc[CC_ALE];
+    cbar += f * (2.0 * cc[CC_KE] * AG * me[1] + (a.pv ? 2.0 * AL * me[7] : 0.0));
+    g = fma(-f * AG * me[2], J[0], g);
+    g = fma(f * me[0], J[1], g);
+    if (a.pv) {
+      g = fma(f * me[5], J[2], g);
+      g = fma(-f * AL * me[6], J[3], g);
+    }
+    g = fma(f * me[3], J[8], g);
+    g = fma(me[4], J[9], g);
+  }
+  if (use_a) {
+    const int NA = a.pv ? 6 : 3;
+    const double* ma = s_a + 1 + a.nb_a + n * NA;
+    const double AG = cc[CC_AGA], AL = cc[CC_ALA];
+    cbar += 2.0 * cc[CC_KA] * AG * ma[1] + (a.pv ? 2.0 * AL * ma[5] : 0.0);
+    g = fma(-AG * ma[2], J[4], g);
+    g = fma(ma[0], J[5], g);
+    if (a.pv) {
+      g = fma(ma[3], J[6], g);
+      g = fma(-AL * ma[4], J[7], g);
+    }
+  }
+  g = fma(cbar, J[10], g);
+  if (PRIOR) g = (g + J[11]) * J[12] + J[13];
+  double* go = a.grad + (b * a.rm.n_rows) * a.N + n;
+  if (a.rm.row[j0] >= 0) go[(int64_t)a.rm.row[j0] * a.N] = g;
+  if (j0 == 0)
+    for (int s = c.K; s < CHI_NSLOT; ++s)  // slots the model kind does not use
+      if (a.rm.row[s] >= 0) go[(int64_t)a.rm.row[s] * a.N] = 0.0;
+}
+
 // unconstrained <-> constrained values of the free RVs (direction = +1: u -> x, -1: x -> u)
 template <int MODEL>
 __global__ void k_transform(MapCfg cfg, int64_t total, int N, int direction, const double* __restrict__ in,
