@@ -181,6 +181,43 @@ __device__ __forceinline__ double warp_sum(double x) {
   return x;
 }
 
+// Warp totals of M per-lane values with sum_k ceil(M / 2^k) (~M) exchanges instead of 5 M: in each of
+// the five butterfly steps a lane hands one half of its values to its partner and keeps, and
+// completes, the other half.  Afterwards lane L holds, in v[i] for i < OUT, the total of the
+// original value number index(i, L) (-1: nothing).  Fixed summation tree: deterministic.
+template <int M>
+struct WarpFold {
+  static constexpr int N1 = (M + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2, OUT = (N4 + 1) / 2;
+  template <int NIN, int MASK>
+  static __device__ __forceinline__ void step(double (&v)[M], int lane) {
+    constexpr int H = (NIN + 1) / 2;
+    const bool up = (lane & MASK) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const double lo = v[i], hi = (i + H < NIN) ? v[i + H] : 0.0;
+      const double send = up ? lo : hi, keep = up ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(CHI_FULL, send, MASK);
+    }
+  }
+  static __device__ __forceinline__ void run(double (&v)[M], int lane) {
+    step<M, 16>(v, lane);
+    step<N1, 8>(v, lane);
+    step<N2, 4>(v, lane);
+    step<N3, 2>(v, lane);
+    step<N4, 1>(v, lane);
+  }
+  static __device__ __forceinline__ int index(int i, int lane) {
+    int p = i;
+    bool ok = true;
+    if (lane & 1) { p += OUT; ok = ok && p < N4; }
+    if (lane & 2) { p += N4; ok = ok && p < N3; }
+    if (lane & 4) { p += N3; ok = ok && p < N2; }
+    if (lane & 8) { p += N2; ok = ok && p < N1; }
+    if (lane & 16) { p += N1; ok = ok && p < M; }
+    return ok ? p : -1;
+  }
+};
+
 // --- bulk async copy (TMA, 1-D) + mbarrier helpers of the STAGED channel pipeline -----------
 // STAGED instantiations (survey mode, one spectrum per sightline): warps of a block read different
 // sightlines, so the channel data has no L1 reuse and every iteration's loads would be L2 / HBM
@@ -436,27 +473,27 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
   }
 
   double* out = a.mom + item * a.mom_stride;
-  lp = -0.5 * warp_sum(lp);
-  gb0 = warp_sum(gb0);
-  gb1 = warp_sum(gb1);
-  if (lane == 0) {
-    out[0] = lp;
-    if (nb > 0) out[1] = gb0;
-    if (nb > 1) out[2] = gb1;
-  }
   if (!SB)
     for (int i = CHI_BASE_REG; i < nb; ++i) {
       double g = warp_sum(s_gb[i - CHI_BASE_REG][threadIdx.x]);
       if (lane == 0) out[1 + i] = g;
     }
-  double* om_ = out + 1 + nb;
+  // logp, the two register-held baseline gradients and the N * NE moments: one folded reduction
+  typedef WarpFold<3 + N * NE> Fold;
+  double v[3 + N * NE];
+  v[0] = lp; v[1] = gb0; v[2] = gb1;
 #pragma unroll
   for (int n = 0; n < N; ++n)
 #pragma unroll
-    for (int j = 0; j < NE; ++j) {
-      double r = warp_sum(acc[n][j]);
-      if (lane == ((n * NE + j) & 31)) om_[n * NE + j] = r;
-    }
+    for (int j = 0; j < NE; ++j) v[3 + n * NE + j] = acc[n][j];
+  Fold::run(v, lane);
+#pragma unroll
+  for (int i = 0; i < Fold::OUT; ++i) {
+    const int idx = Fold::index(i, lane);
+    if (idx >= 3) out[1 + nb + (idx - 3)] = v[i];
+    else if (idx == 0) out[0] = -0.5 * v[i];
+    else if (idx > 0 && idx <= nb) out[idx] = v[i];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -602,27 +639,27 @@ __global__ void __launch_bounds__(CHI_BLOCK, ab_min_blocks(N, PV)) k_moments_abs
   }
 
   double* out = a.mom + item * a.mom_stride;
-  lp = -0.5 * warp_sum(lp);
-  gb0 = warp_sum(gb0);
-  gb1 = warp_sum(gb1);
-  if (lane == 0) {
-    out[0] = lp;
-    if (nb > 0) out[1] = gb0;
-    if (nb > 1) out[2] = gb1;
-  }
   if (!SB)
     for (int i = CHI_BASE_REG; i < nb; ++i) {
       double g = warp_sum(s_gb[i - CHI_BASE_REG][threadIdx.x]);
       if (lane == 0) out[1 + i] = g;
     }
-  double* om_ = out + 1 + nb;
+  // logp, the two register-held baseline gradients and the N * NA moments: one folded reduction
+  typedef WarpFold<3 + N * NA> Fold;
+  double v[3 + N * NA];
+  v[0] = lp; v[1] = gb0; v[2] = gb1;
 #pragma unroll
   for (int n = 0; n < N; ++n)
 #pragma unroll
-    for (int j = 0; j < NA; ++j) {
-      double r = warp_sum(acc[n][j]);
-      if (lane == ((n * NA + j) & 31)) om_[n * NA + j] = r;
-    }
+    for (int j = 0; j < NA; ++j) v[3 + n * NA + j] = acc[n][j];
+  Fold::run(v, lane);
+#pragma unroll
+  for (int i = 0; i < Fold::OUT; ++i) {
+    const int idx = Fold::index(i, lane);
+    if (idx >= 3) out[1 + nb + (idx - 3)] = v[i];
+    else if (idx == 0) out[0] = -0.5 * v[i];
+    else if (idx > 0 && idx <= nb) out[idx] = v[i];
+  }
 }
 
 }  // namespace chi

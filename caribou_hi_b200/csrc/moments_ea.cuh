@@ -255,14 +255,6 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
   }
 
   double* out = a.mom + item * a.mom_stride;
-  lp = -0.5 * warp_sum(lp);
-  gbe0 = warp_sum(gbe0);
-  gba0 = warp_sum(gba0);
-  if (lane == 0) {
-    out[0] = lp;
-    if (nbe > 0) out[1] = gbe0;
-    if (nba > 0) out[1 + nbe] = gba0;
-  }
   if (!SB) {
     for (int i = 1; i < nbe; ++i) {
       double g = warp_sum(s_gb[i][threadIdx.x]);
@@ -273,15 +265,31 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
       if (lane == 0) out[1 + nbe + i] = g;
     }
   }
-  double* om_ = out + 1 + nbe + nba;
+  // logp, the two register-held baseline gradients and the N * NF moments: one folded reduction
+  typedef WarpFold<3 + N * NF> Fold;
+  double v[3 + N * NF];
+  v[0] = lp; v[1] = gbe0; v[2] = gba0;
 #pragma unroll
   for (int n = 0; n < N; ++n)
 #pragma unroll
-    for (int j = 0; j < NF; ++j) {
-      double r = warp_sum(acc[n][j]);
-      if (j == 2 || j == 3 || j == 8 || j == 9) r *= CHI_LN2;  // combined moments carry log2(e)
-      if (lane == ((n * NF + j) & 31)) om_[n * NF + j] = r;
+    for (int j = 0; j < NF; ++j) v[3 + n * NF + j] = acc[n][j];
+  Fold::run(v, lane);
+  double* om_ = out + 1 + nbe + nba;
+#pragma unroll
+  for (int i = 0; i < Fold::OUT; ++i) {
+    const int idx = Fold::index(i, lane);
+    if (idx >= 3) {
+      const int j = (idx - 3) % NF;
+      // combined moments carry log2(e)
+      om_[idx - 3] = (j == 2 || j == 3 || j == 8 || j == 9) ? v[i] * CHI_LN2 : v[i];
+    } else if (idx == 0) {
+      out[0] = -0.5 * v[i];
+    } else if (idx == 1) {
+      if (nbe > 0) out[1] = v[i];
+    } else if (idx == 2) {
+      if (nba > 0) out[1 + nbe] = v[i];
     }
+  }
 }
 
 }  // namespace chi
