@@ -46,7 +46,7 @@ def workload_name(draws):
 # --------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------
-NCU_DRAM_BYTES_PER_DRAW = 8087296.0 / 20000.0  # k_moments_ea<4,0,1>, profiles/r1f_ncu_full_summary.txt
+NCU_DRAM_BYTES_PER_DRAW = 8084224.0 / 20000.0  # k_moments_ea<4,0,1>, profiles/r1g_ncu_full_summary.txt
 
 
 class ClockSampler:
@@ -482,7 +482,7 @@ def run_b200(args):
                          # profiles/ (20000 draws per launch: 8.09 MB read, writes absorbed by L2),
                          # scaled to this launch's draws
                          "traffic": (NCU_DRAM_BYTES_PER_DRAW * draws_launch) if fused else None,
-                         "traffic_source": "profiles/r1f_ncu_full_summary.txt" if fused else None,
+                         "traffic_source": "profiles/r1g_ncu_full_summary.txt" if fused else None,
                          "hbm": {"achieved": bytes_em / t_em / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_em / t_em / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},

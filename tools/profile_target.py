@@ -15,6 +15,14 @@ eng.set_spectra(emission=dict(spectral=v, brightness=rng.normal(10, 5, S), noise
                 absorption=dict(spectral=v, brightness=rng.normal(0.3, 0.1, S), noise=0.01, basis=np.full((1, S), 0.01)))
 th = lambda trial: eng.deterministics(eng.pack(trial))["fwhm2_thermal"]
 theta = eng.pack(synthetic.draw_free(kind, N, B, rng, lorentzian=pv, thermal_fn=th))
+# device-resident call: ONE launch of each kernel per batch (the host entry point would cut the
+# batch into pipeline pieces)
+import torch
+t_theta = torch.from_numpy(theta).cuda()
+lp = torch.empty(B, dtype=torch.float64, device="cuda"); gr = torch.empty((B, 10, N), dtype=torch.float64, device="cuda")
+ce = torch.zeros((B, 1), dtype=torch.float64, device="cuda"); ca = torch.zeros((B, 1), dtype=torch.float64, device="cuda")
+ge = torch.empty_like(ce); ga = torch.empty_like(ca)
 for _ in range(3):
-    lp, g, _, _ = eng.logp_grad(theta, np.zeros((B, 1)), np.zeros((B, 1)))
-print("ok", np.isfinite(lp).mean(), eng.stage_ms(1))
+    eng.logp_grad_dev(B, t_theta, lp, gr, coeff_e=ce, coeff_a=ca, gcoeff_e=ge, gcoeff_a=ga)
+eng.synchronize()
+print("ok", float(torch.isfinite(lp).double().mean()), eng.stage_ms(1))
