@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
       lds2(&s_c[n][0], c0, nk);
       lds2(&s_c[n][2], nAG, nAL);
       const double d = v - c0, d2 = d * d;
-      E[n] = chi_exp2<false>(nk * d2, ek);
+      E[n] = chi_exp2_prod<false>(nk, d2, ek);
       x[n] = nAG * E[n];  // -tau log2(e)
       if (PV) x[n] = fma(nAL, chi_rcp(d2 + s_c[n][4]), x[n]);
     }
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_spectra_ea_t(SpecArgs a) {
       lds2(&s_c[n][2], nAGe, fTs);
       lds2(&s_c[n][4], f, nAGa);
       const double d = v - c0, d2 = d * d;
-      const double E = chi_exp2<false>(nk * d2, ek);
+      const double E = chi_exp2_prod<false>(nk, d2, ek);
       double x = nAGe * E;
       xs = fma(nAGa, E, xs);
       if (PV) {

@@ -166,18 +166,20 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
       lds2(&sc[n][2], nAGe, fTs);
       lds2(&sc[n][4], f, nAGa);
       const double d = v - c0, d2 = d * d;
-      E[n] = chi_exp2<false>(nk * d2, ek);
-      double x = nAGe * E[n];
+      E[n] = chi_exp2_prod<false>(nk, d2, ek);
       xs = fma(nAGa, E[n], xs);
       if (PV) {
+        double x = nAGe * E[n];
         double h, fALe, nALe, nALa;
         lds2(&sc[n][8], nALe, nALa);
         lds2(&sc[n][10], h, fALe);
         q[n] = chi_rcp(d2 + h);
         x = fma(nALe, q[n], x);
         xs = fma(nALa, q[n], xs);
+        om[n] = 1.0 - chi_exp2<true>(x, ek);
+      } else {
+        om[n] = 1.0 - chi_exp2_prod<true>(nAGe, E[n], ek);
       }
-      om[n] = 1.0 - chi_exp2<true>(x, ek);
       Pn[n] = P;
       const double u = om[n] * P;
       T = fma(fTs, u, T);
