@@ -522,3 +522,29 @@ def test_asynchronous_host_calls(cuda_device):
         assert np.array_equal(bufs[k]["gcoeff_e"], ref[k][2], equal_nan=True)
         assert np.array_equal(bufs[k]["gcoeff_a"], ref[k][3], equal_nan=True)
     eng.close()
+
+
+@pytest.mark.parametrize("B", [24, 20000])
+def test_logp_only_calls_match_the_gradient_calls(cuda_device, B):
+    """want_grad=False (no Jacobian / no gradient buffers) gives the same logp, bit for bit, as the
+    call that also returns the gradient -- small batches (side-stream Jacobian + contraction) and
+    large ones (fused epilogue), likelihood and total model logp."""
+    spec, data, free, baseline = make_case("emission_absorption_physical", 3, 160, 160, B, seed=77, lorentzian=True,
+                                           baseline_degree=1, shared_axis=True)
+    eng = engine_for(spec, data, 1)
+    theta = eng.pack(free)
+    ce, ca = baseline["baseline_emission_norm"], baseline["baseline_absorption_norm"]
+    lp_g = eng.logp_grad(theta, ce, ca)[0]
+    lp_only, g, gce, gca = eng.logp_grad(theta, ce, ca, want_grad=False)
+    assert g is None and gce is None and gca is None
+    assert np.array_equal(lp_only, lp_g, equal_nan=True)
+    if B < 1000:
+        assert_close(lp_only, oracle_logp_grad(spec, data, free, baseline)[0], what="logp only", axis=None)
+    eng.set_priors()
+    u = eng.transform(theta, direction=-1)
+    fin = np.isfinite(u).all(axis=(1, 2))
+    m_g = eng.model_logp_grad(u[fin], ce[fin], ca[fin])[0]
+    m_only = eng.model_logp_grad(u[fin], ce[fin], ca[fin], want_grad=False)[0]
+    assert np.array_equal(m_only, m_g, equal_nan=True)
+    assert np.isfinite(m_only).sum() > 0.3 * fin.sum()
+    eng.close()
