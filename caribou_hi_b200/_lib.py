@@ -130,6 +130,10 @@ SYMBOLS = {
     "chi_spectra_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 5),
     "chi_spectra_f32": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _fp, _fp]),
     "chi_spectra_f32_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 5),
+    "chi_predictive": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _ip, C.c_uint64, C.c_int64, _dp, _dp]),
+    "chi_predictive_f32": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _ip, C.c_uint64, C.c_int64, _fp, _fp]),
+    "chi_predictive_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 4 + [C.c_uint64, C.c_int64] + [C.c_void_p] * 2),
+    "chi_predictive_f32_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 4 + [C.c_uint64, C.c_int64] + [C.c_void_p] * 2),
     "chi_spectra_vjp": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "chi_spectra_vjp_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 8),
     "chi_deterministics": (C.c_int, [_H, C.c_int64, _dp, _dp]),

@@ -583,11 +583,41 @@ inline int run_spectra_any(chi_handle* h, int64_t B, const double* th, const dou
   return run_spectra32(h, B, th, ce, ca, e, a);
 }
 
-// host entry point of the predicted spectra, T = double (chi_spectra) or float (chi_spectra_f32)
+// predictive draws: y = mu + sigma z on top of spectra already in mu_e / mu_a (device), same stream
+struct NoiseSpec {
+  unsigned long long seed;
+  int64_t draw_offset;
+  const int32_t* sl;  // device, per draw, or null
+};
 template <typename T>
-int host_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca, T* mu_e, T* mu_a) {
+int add_noise(chi_handle* h, int64_t B, const NoiseSpec& ns, T* mu_e, T* mu_a) {
+  if (mu_e && h->has_e) {
+    const int64_t n = B * ((h->e.S + 1) / 2);
+    k_add_noise<T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(B, h->e.S, mu_e, h->e.chan.d(), ns.sl, ns.seed,
+                                                                        ns.draw_offset, 0);
+    h->launches++;
+  }
+  if (mu_a && h->has_a) {
+    const int64_t n = B * ((h->a.S + 1) / 2);
+    k_add_noise<T><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(B, h->a.S, mu_a, h->a.chan.d(), ns.sl, ns.seed,
+                                                                        ns.draw_offset, 1);
+    h->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, h->stream));  // the timed region of the call ends after the noise
+  return CHI_OK;
+}
+
+// host entry point of the predicted spectra, T = double (chi_spectra) or float (chi_spectra_f32);
+// with `noise` the predictive draws of the observed nodes (chi_predictive[_f32]), `sl` = host sightlines
+template <typename T>
+int host_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca, T* mu_e, T* mu_a,
+                 const NoiseSpec* noise = nullptr, const int32_t* sl = nullptr) {
   int rc = check_model_call(h, B, theta);
   if (rc) return rc;
+  if (noise && sl)
+    for (int64_t i = 0; i < B; ++i)
+      if (sl[i] < 0 || sl[i] >= h->n_sl) return fail(h, CHI_EINVAL, "chi_predictive: sightline index out of range");
   CK(cudaSetDevice(h->device));
   const int N = h->cfg.n_clouds;
   const size_t th_b = (size_t)CHI_NSLOT * N * sizeof(double);
@@ -615,6 +645,18 @@ int host_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce
     if (mu_a && Sa) { CK(h->w_mua.ensure((size_t)nb * Sa * sizeof(T))); d_ma = (T*)h->w_mua.p; }
     rc = run_spectra_any(h, nb, h->lanes[0].w_theta.d(), d_ce, d_ca, d_me, d_ma);
     if (rc) return rc;
+    if (noise) {
+      NoiseSpec ns = *noise;
+      ns.draw_offset += b0;
+      ns.sl = nullptr;
+      if (sl) {
+        CK(h->lanes[0].w_sl.ensure(nb * sizeof(int32_t)));
+        CK(cudaMemcpyAsync(h->lanes[0].w_sl.p, sl + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        ns.sl = (const int32_t*)h->lanes[0].w_sl.p;
+      }
+      rc = add_noise<T>(h, nb, ns, d_me, d_ma);
+      if (rc) return rc;
+    }
     if (d_me) CK(cudaMemcpyAsync(mu_e + b0 * Se, d_me, (size_t)nb * Se * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     if (d_ma) CK(cudaMemcpyAsync(mu_a + b0 * Sa, d_ma, (size_t)nb * Sa * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1424,6 +1466,34 @@ int chi_spectra(chi_handle* h, int64_t B, const double* theta, const double* ce,
 int chi_spectra_f32(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
                     float* mu_e, float* mu_a) {
   return host_spectra<float>(h, B, theta, ce, ca, mu_e, mu_a);
+}
+
+int chi_predictive(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                   const int32_t* sl, uint64_t seed, int64_t draw_offset, double* y_e, double* y_a) {
+  NoiseSpec ns{seed, draw_offset, nullptr};
+  return host_spectra<double>(h, B, theta, ce, ca, y_e, y_a, &ns, sl);
+}
+
+int chi_predictive_f32(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                       const int32_t* sl, uint64_t seed, int64_t draw_offset, float* y_e, float* y_a) {
+  NoiseSpec ns{seed, draw_offset, nullptr};
+  return host_spectra<float>(h, B, theta, ce, ca, y_e, y_a, &ns, sl);
+}
+
+int chi_predictive_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                       const int32_t* sl, uint64_t seed, int64_t draw_offset, double* y_e, double* y_a) {
+  int rc = chi_spectra_dev(h, B, theta, ce, ca, y_e, y_a);
+  if (rc || B == 0) return rc;
+  NoiseSpec ns{seed, draw_offset, sl};
+  return add_noise<double>(h, B, ns, y_e, y_a);
+}
+
+int chi_predictive_f32_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
+                           const int32_t* sl, uint64_t seed, int64_t draw_offset, float* y_e, float* y_a) {
+  int rc = chi_spectra_f32_dev(h, B, theta, ce, ca, y_e, y_a);
+  if (rc || B == 0) return rc;
+  NoiseSpec ns{seed, draw_offset, sl};
+  return add_noise<float>(h, B, ns, y_e, y_a);
 }
 
 int chi_spectra_vjp(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,

@@ -521,6 +521,63 @@ __global__ void __launch_bounds__(128) k_contract(ConArgs c) {
       if (a.rm.row[s] >= 0) go[(int64_t)a.rm.row[s] * a.N] = 0.0;
 }
 
+// ---------------------------------------------------------------------------
+// Predictive draws of the observed nodes (pm.Normal(mu, sigma = data.noise), emission_model.py:164-169
+// and the other add_likelihood bodies; what sample_posterior_predictive / sample_prior_predictive
+// return): y = mu + sigma z.  z comes from a COUNTER-BASED generator -- splitmix64's finaliser on
+// (seed, global draw index, dataset, channel pair) -- so a sharded or sub-batched job reproduces the
+// single-call draws bit for bit and the CPU test restates it in a few lines.  Box-Muller on two
+// uniforms per channel pair: 53-bit uniforms and fp64 libm for double outputs, two 24-bit uniforms
+// from one hash and fp32 libm for float outputs.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long chi_mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+#define CHI_GOLDEN64 0x9E3779B97F4A7C15ULL
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_add_noise(int64_t B, int S, T* __restrict__ y,
+                                                   const double* __restrict__ chan,  // [n_sl][ceil(S/32)][4][32], plane 3 = 1/sigma^2
+                                                   const int32_t* __restrict__ sl, unsigned long long seed,
+                                                   int64_t draw_offset, int dataset) {
+  const int P = (S + 1) >> 1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * P) return;
+  const int64_t b = t / P;
+  const int p = (int)(t - b * P), s0 = 2 * p;
+  const unsigned long long g = (unsigned long long)(draw_offset + b);
+  const unsigned long long base = chi_mix64(seed + CHI_GOLDEN64 * (2ULL * g + (unsigned long long)dataset + 1ULL));
+  const int64_t groups = (S + 31) >> 5;
+  const double* w = chan + ((int64_t)(sl ? sl[b] : 0) * groups) * 128 + 96;
+  const double sig0 = rsqrt(w[(int64_t)(s0 >> 5) * 128 + (s0 & 31)]);
+  const bool two = s0 + 1 < S;
+  const int s1 = two ? s0 + 1 : s0;
+  const double sig1 = rsqrt(w[(int64_t)(s1 >> 5) * 128 + (s1 & 31)]);
+  T* row = y + b * S;
+  if (sizeof(T) == 8) {
+    const unsigned long long h1 = chi_mix64(base + CHI_GOLDEN64 * (2ULL * p + 1ULL));
+    const unsigned long long h2 = chi_mix64(base + CHI_GOLDEN64 * (2ULL * p + 2ULL));
+    const double u1 = ((double)(h1 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(h2 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    row[s0] = (T)((double)row[s0] + sig0 * (r * cs));
+    if (two) row[s1] = (T)((double)row[s1] + sig1 * (r * sn));
+  } else {
+    const unsigned long long h1 = chi_mix64(base + CHI_GOLDEN64 * (2ULL * p + 1ULL));
+    const float u1 = ((float)(unsigned)(h1 >> 40) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(unsigned)((h1 >> 16) & 0xFFFFFFu) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));  // libm logf: the fast intrinsic loses the relative accuracy near u1 = 1
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    row[s0] = (T)((float)row[s0] + (float)sig0 * (r * cs));
+    if (two) row[s1] = (T)((float)row[s1] + (float)sig1 * (r * sn));
+  }
+}
+
 // unconstrained <-> constrained values of the free RVs (direction = +1: u -> x, -1: x -> u)
 template <int MODEL>
 __global__ void k_transform(MapCfg cfg, int64_t total, int N, int direction, const double* __restrict__ in,

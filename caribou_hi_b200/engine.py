@@ -382,6 +382,42 @@ class Engine:
             )
         return mu_e, mu_a
 
+    def predictive(self, theta, coeff_e=None, coeff_a=None, seed=0, draw_offset=0, sightline=None, dtype=np.float64):
+        """Predictive draws of the observed nodes, ``y = mu + noise * z`` (``chi_predictive``): what
+        ``sample_posterior_predictive`` / ``sample_prior_predictive`` return for the likelihood nodes.
+        ``z`` is keyed by ``(seed, draw_offset + b, dataset, channel)``, so shards and sub-batches that
+        pass their offset reproduce one big call.  Returns ``(y_e | None, y_a | None)``."""
+        N = self.n_clouds
+        theta = _f64(theta)
+        B = theta.shape[0]
+        if theta.shape[1:] != (layout.NSLOT, N):
+            raise ValueError("theta: bad shape")
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("predictive: dtype must be float64 or float32")
+        ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
+        ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
+        sl = None if sightline is None else np.ascontiguousarray(sightline, dtype=np.int32)
+        if sl is not None and sl.shape != (B,):
+            raise ValueError("sightline: expected [B]")
+        y_e = np.empty((B, self.S_e), dtype=dtype) if self.has_emission else None
+        y_a = np.empty((B, self.S_a), dtype=dtype) if self.has_absorption else None
+        if dtype == np.dtype(np.float32):
+            fn, cast = self._lib.chi_predictive_f32, _lib.as_fp
+        else:
+            fn, cast = self._lib.chi_predictive, _lib.as_dp
+        self._check(fn(self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca), _lib.as_ip(sl),
+                       int(seed) & 0xFFFFFFFFFFFFFFFF, int(draw_offset), cast(y_e), cast(y_a)))
+        return y_e, y_a
+
+    def predictive_dev(self, B, theta, y_e=None, y_a=None, coeff_e=None, coeff_a=None, seed=0, draw_offset=0,
+                       sightline=None, f32=False):
+        """:meth:`predictive` on device pointers (``chi_predictive_dev`` / ``chi_predictive_f32_dev``)."""
+        p = self._ptr
+        fn = self._lib.chi_predictive_f32_dev if f32 else self._lib.chi_predictive_dev
+        self._check(fn(self._h, int(B), p(theta), p(coeff_e), p(coeff_a), p(sightline),
+                       int(seed) & 0xFFFFFFFFFFFFFFFF, int(draw_offset), p(y_e), p(y_a)))
+
     def spectra_vjp(self, theta, gbar_e=None, gbar_a=None, coeff_e=None, coeff_a=None):
         """VJP of :meth:`spectra`: returns ``(grad, gcoeff_e, gcoeff_a)``."""
         N = self.n_clouds

@@ -256,6 +256,19 @@ class _HIBase(ABC):
             out["absorption"] = mu_a
         return out
 
+    def sample_predictive(self, point, seed=1234, dtype=np.float64):
+        """Draws of the observed nodes at the given parameter draws -- ``pm.sample_posterior_predictive``
+        (posterior draws) / ``pm.sample_prior_predictive`` (prior draws) for the ``pm.Normal(mu,
+        sigma=data.noise)`` likelihood nodes: ``{"emission": [B, S_e], "absorption": [B, S_a]}``."""
+        theta, ce, ca, _ = self._split(point)
+        y_e, y_a = self.engine.predictive(theta, ce, ca, seed=seed, dtype=dtype)
+        out = {}
+        if y_e is not None:
+            out["emission"] = y_e
+        if y_a is not None:
+            out["absorption"] = y_a
+        return out
+
     def deterministics(self, point):
         theta, _, _, _ = self._split(point)
         det = self.engine.deterministics(theta)

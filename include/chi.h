@@ -292,6 +292,26 @@ int chi_spectra_f32(chi_handle* h, int64_t B, const double* theta, const double*
 int chi_spectra_f32_dev(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
                         const double* coeff_a, float* mu_e_out, float* mu_a_out);
 
+/* Predictive DRAWS of the observed nodes, y = mu + sigma z with z ~ N(0, 1): what PyMC's
+ * sample_posterior_predictive / sample_prior_predictive return for the pm.Normal(mu, sigma =
+ * data.noise, observed = ...) nodes of the add_likelihood() bodies (emission_model.py:164-169,
+ * absorption_model.py:99-104, ...).  sigma is the noise of sightline[b] (sightline 0 if NULL).
+ * z comes from a counter-based generator keyed by (seed, draw_offset + b, dataset, channel):
+ * shards and sub-batches that pass their offset reproduce the single-call draws bit for bit.
+ * fp64: 53-bit uniforms, Box-Muller in fp64; _f32: 24-bit uniforms, fp32 (chi_spectra_f32 + noise). */
+int chi_predictive(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                   const double* coeff_a, const int32_t* sightline, uint64_t seed, int64_t draw_offset,
+                   double* y_e_out, double* y_a_out);
+int chi_predictive_dev(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                       const double* coeff_a, const int32_t* sightline, uint64_t seed, int64_t draw_offset,
+                       double* y_e_out, double* y_a_out);
+int chi_predictive_f32(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                       const double* coeff_a, const int32_t* sightline, uint64_t seed, int64_t draw_offset,
+                       float* y_e_out, float* y_a_out);
+int chi_predictive_f32_dev(chi_handle* h, int64_t B, const double* theta, const double* coeff_e,
+                           const double* coeff_a, const int32_t* sightline, uint64_t seed, int64_t draw_offset,
+                           float* y_e_out, float* y_a_out);
+
 /* Vector-Jacobian product of chi_spectra: given cotangents gbar_e[B][S_e],
  * gbar_a[B][S_a] (NULL = zeros) returns grad_out[B][CHI_NSLOT][N] and the baseline
  * coefficient gradients.  This is the L_op of the spectra Op. */
