@@ -38,6 +38,15 @@ def run(B, N, S, pv):
         return float(((x32[ok].double() - x64[ok]).abs() / scale).max())
     print(f"  f32: {ms:.3f} ms -> {units/ms/1e6:.1f} Gunits/s, output {2*B*S*4/ms/1e6:.0f} GB/s; worst |f32-f64|/max|f64| "
           f"emission {worst(e32, mu_e):.2e} absorption {worst(a32, mu_a):.2e}", flush=True)
+    # predictive draws (spectra + counter-based Normal noise), fp64 and fp32
+    for f32, (oe, oa) in ((False, (mu_e, mu_a)), (True, (e32, a32))):
+        for _ in range(2): eng.predictive_dev(B, theta, oe, oa, seed=1, f32=f32)
+        eng.synchronize()
+        e0.record(stream)
+        for _ in range(5): eng.predictive_dev(B, theta, oe, oa, seed=1, f32=f32)
+        e1.record(stream); eng.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"  predictive draws {'f32' if f32 else 'f64'}: {ms:.3f} ms -> {units/ms/1e6:.1f} Gunits/s", flush=True)
     eng.close()
 
 if __name__ == "__main__":
