@@ -495,11 +495,80 @@ def run_b200(args):
             vt, st_step, dn, ct = time_oracle(256, 2, 1, min_seconds=4.0)
             result["cpu_baseline_torch"] = {"value": vt, "unit": UNIT, "cores": ct, "kind": "port",
                                             "sample": f"256 draws x {dn} steps, torch-CPU fp64 autograd oracle"}
+        if world == 1 and not args.no_extras:
+            try:
+                result["other_configs"] = other_configs(local)
+            except Exception as exc:  # secondary numbers never break the bench line
+                result["other_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(result))
     barrier()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(local):
+    """Secondary, device-timed numbers beside the headline (not part of `value`): BASELINE configs[2]
+    shape (64 chains x 8 clouds x 2048+2048 channels, pseudo-Voigt: latency per logp+grad evaluation)
+    and configs[4] per-draw shape (8 clouds x 4096+4096 channels, pseudo-Voigt: spectra only, fp64 and
+    the optional fp32 path, 8000 draws)."""
+    import torch
+    from caribou_hi_b200 import Engine, synthetic
+
+    out = {}
+    dev = torch.device("cuda", local)
+    kind = "emission_absorption_physical"
+
+    def engine(N, S):
+        e = Engine(kind, N, device=local, lorentzian=True, prior_fwhm_L=1.0, prior_amplitude=1e21)
+        v = np.linspace(-100.0, 100.0, S)
+        rng = np.random.default_rng(0)
+        e.set_spectra(emission=dict(spectral=v, brightness=rng.normal(10, 5, S), noise=0.1, basis=np.full((1, S), 0.1)),
+                      absorption=dict(spectral=v, brightness=rng.normal(0.3, 0.1, S), noise=0.01, basis=np.full((1, S), 0.01)))
+        return e, rng
+
+    def timed(e, fn, reps):
+        stream = torch.cuda.ExternalStream(e.stream, device=dev)
+        for _ in range(3):
+            fn()
+        e.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        e.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # configs[2] shape
+    N, S, B = 8, 2048, 64
+    e, rng = engine(N, S)
+    th = lambda trial: e.deterministics(e.pack(trial))["fwhm2_thermal"]
+    theta = torch.from_numpy(e.pack(synthetic.draw_free(kind, N, B, rng, lorentzian=True, thermal_fn=th))).to(dev)
+    lp = torch.empty(B, dtype=torch.float64, device=dev); gr = torch.empty((B, 10, N), dtype=torch.float64, device=dev)
+    ce = torch.zeros((B, 1), dtype=torch.float64, device=dev); ca = torch.zeros_like(ce)
+    ge = torch.empty_like(ce); ga = torch.empty_like(ce)
+    ms = timed(e, lambda: e.logp_grad_dev(B, theta, lp, gr, coeff_e=ce, coeff_a=ca, gcoeff_e=ge, gcoeff_a=ga), 200)
+    out["configs[2] shape: 64 chains x 8 clouds x 2048+2048 channels, pseudo-Voigt, logp+grad"] = {
+        "us_per_evaluation": ms * 1e3, "units_per_s": B * N * 2 * S / (ms * 1e-3)}
+    e.close()
+    # configs[4] per-draw shape
+    N, S, B = 8, 4096, 8000
+    e, rng = engine(N, S)
+    th = lambda trial: e.deterministics(e.pack(trial))["fwhm2_thermal"]
+    theta = torch.from_numpy(e.pack(synthetic.draw_free(kind, N, B, rng, lorentzian=True, thermal_fn=th))).to(dev)
+    m64 = [torch.empty((B, S), dtype=torch.float64, device=dev) for _ in range(2)]
+    m32 = [torch.empty((B, S), dtype=torch.float32, device=dev) for _ in range(2)]
+    t64 = timed(e, lambda: e.spectra_dev(B, theta, m64[0], m64[1]), 10)
+    t32 = timed(e, lambda: e.spectra_f32_dev(B, theta, m32[0], m32[1]), 10)
+    ok = torch.isfinite(m64[0]).all(dim=1)
+    err = float(((m32[0][ok].double() - m64[0][ok]).abs() / m64[0][ok].abs().amax(dim=1, keepdim=True)).max())
+    units = B * N * 2 * S
+    out["configs[4] shape: 8000 draws x 8 clouds x 4096+4096 channels, pseudo-Voigt, spectra only"] = {
+        "fp64_units_per_s": units / (t64 * 1e-3), "fp32_units_per_s": units / (t32 * 1e-3),
+        "fp32_worst_error_over_peak_vs_fp64": err}
+    e.close()
+    return out
 
 
 def main():
@@ -510,6 +579,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--draws", type=int, default=DRAWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs[2] / configs[4] timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
