@@ -1,6 +1,8 @@
 // k_moments_ea<N, PV, SB> instantiations: fused emission+absorption for a shared spectral axis.
 // Built twice (launch_ea.cu: CHI_EA_SB=1, launch_ea_gb.cu: CHI_EA_SB=0) so the two halves compile
 // in parallel.
+#include <cstdlib>
+
 #include "launch.cuh"
 #include "moments_ea.cuh"
 
@@ -13,6 +15,13 @@ template <int N, bool PV>
 static void run(const FusedArgs& a, cudaStream_t st) {
   const int64_t items = a.B * a.n_chunks;
   const unsigned grid = (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
+#if CHI_EA_SB
+  static const int novjp = [] { const char* e = getenv("CHI_EA_NOVJP"); return e ? atoi(e) : 1; }();
+  if (!a.vjp && (novjp == 2 || (novjp == 1 && PV))) {  // logp + gradient: instantiation without the VJP plumbing
+    k_moments_ea<N, PV, true, false, false><<<grid, CHI_BLOCK, 0, st>>>(a);
+    return;
+  }
+#endif
   k_moments_ea<N, PV, CHI_EA_SB != 0><<<grid, CHI_BLOCK, 0, st>>>(a);
 }
 

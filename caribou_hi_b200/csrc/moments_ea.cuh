@@ -61,7 +61,9 @@ __device__ __forceinline__ void ldg2(const double* p, double& x, double& y) {
 }
 
 // STAGED: see the bulk-async helpers in moments.cuh.
-template <int N, bool PV, bool SB, bool STAGED = false>
+// VJP = false: logp mode only (a.vjp == 0 is the caller's promise): the cotangent pointers and the
+// mode test leave the channel loop, which is short of registers.
+template <int N, bool PV, bool SB, bool STAGED = false, bool VJP = true>
 __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(FusedArgs a) {
   constexpr int NF = FusedLayout<PV>::NF;
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][12];
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
 
   const int sl = a.sl ? a.sl[b] : 0;
   const double* __restrict__ ch = a.chan + (int64_t)sl * ((S + 31) >> 5) * 256 + lane;
-  const double* __restrict__ Ge = a.gbar_e ? a.gbar_e + b * S : nullptr;
-  const double* __restrict__ Ga = a.gbar_a ? a.gbar_a + b * S : nullptr;
+  const double* __restrict__ Ge = (VJP && a.gbar_e) ? a.gbar_e + b * S : nullptr;
+  const double* __restrict__ Ga = (VJP && a.gbar_a) ? a.gbar_a + b * S : nullptr;
 
   double acc[N][NF];
 #pragma unroll
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
     const double ea = chi_exp2<true>(xs, ek);
     const double mu_a = (1.0 - ea) + base_a;          // absorption_model.py:91
     double mbe, mba;
-    if (a.vjp) {
+    if (VJP && a.vjp) {
       mbe = Ge ? Ge[sx] : 0.0;
       mba = Ga ? Ga[sx] : 0.0;
     } else {
