@@ -30,14 +30,14 @@ __device__ __forceinline__ float rcpf(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 1 - 2^x for x <= 0 to ~1.5e-6 relative: cubic near 0 (no cancellation), 1 - ex2 elsewhere
+// 1 - 2^x to ~1.5e-6 relative: cubic near 0 (no cancellation), 1 - ex2 elsewhere
 __device__ __forceinline__ float one_minus_exp2(float x) {
   const float direct = 1.0f - ex2f(x);
   // -(2^x - 1) = -x (c1 + x (c2 + x (c3 + x c4))), c_k = ln2^k / k!; |x| <= 1/8: next term 5e-7
   float p = fmaf(x, 9.6181291e-3f, 5.5504109e-2f);
   p = fmaf(x, p, 2.4022651e-1f);
   p = fmaf(x, p, 6.9314718e-1f);
-  return x > -0.125f ? -x * p : direct;
+  return fabsf(x) < 0.125f ? -x * p : direct;  // |x|: a negative optical depth (physics-level callers) stays valid
 }
 
 #ifndef CHI_S32_MINB

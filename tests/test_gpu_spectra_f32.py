@@ -137,6 +137,27 @@ def test_f32_opaque_and_mixed_gas_against_the_oracle(cuda_device):
     assert_close(a32, ref_a, rtol=RTOL32, what="mixed gas, absorption vs oracle")
 
 
+def test_f32_negative_optical_depth(cuda_device):
+    """Physics-level callers may hand over tau_total < 0 (amplification): both branches of 1 - 2^x."""
+    rng = np.random.default_rng(12)
+    B, N = 32, 3
+    ve = np.linspace(-60, 60, 512)
+    va = np.linspace(-30, 30, 256)
+    inp = {
+        "velocity": rng.normal(0, 10, (B, N)),
+        "fwhm2": rng.uniform(10, 300, (B, N)),
+        "fwhm_L": rng.uniform(0.0, 2.0, (B, N)),
+        "tau_total": -(10 ** rng.uniform(-2, 1.3, (B, N))),
+        "tspin": rng.uniform(30, 300, (B, N)),
+        "filling_factor": rng.uniform(0.2, 1.0, (B, N)),
+        "absorption_weight": rng.uniform(0.5, 1.0, (B, N)),
+    }
+    (e32, a32), (e64, a64), (ref_e, ref_a) = _physics_case(inp, ve, va)
+    assert_close(e64, ref_e, what="negative tau, fp64 emission vs oracle")
+    assert_close(e32, e64, rtol=RTOL32, what="negative tau, emission")
+    assert_close(a32, a64, rtol=RTOL32, what="negative tau, absorption")
+
+
 def test_f32_device_pointer_form_and_sub_batches(cuda_device, monkeypatch):
     import torch
 
