@@ -28,7 +28,7 @@ for r in rows[hi + 1:]:
     a = agg.setdefault(key, [0, 0.0]); a[0] += 1; a[1] += float(r[mv].replace(",", ""))
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(out, f"{tag}_launch_list.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras\n")
     f.write("# per-launch times are cold-cache and serialised: compare SHARES with bench.py's stage_ms\n")
     f.write(f"{'kernel':52s} {'grid':>16s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}\n")
     for (k, g), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
