@@ -173,20 +173,25 @@ def load():
     return lib
 
 
-def as_dp(a):
-    """numpy float64 C-contiguous array -> double* (None -> NULL)."""
+def _checked(a, dtype, ptr):
+    # the library reads / writes through the raw pointer: a wrong dtype or a strided view would
+    # corrupt host memory silently, so the marshalling layer refuses it
     if a is None:
         return None
-    return a.ctypes.data_as(_dp)
+    if a.dtype != dtype or not a.flags.c_contiguous:
+        raise TypeError(f"libchi needs a C-contiguous {dtype} array, got {a.dtype} "
+                        f"({'contiguous' if a.flags.c_contiguous else 'strided'}, shape {a.shape})")
+    return a.ctypes.data_as(ptr)
+
+
+def as_dp(a):
+    """numpy float64 C-contiguous array -> double* (None -> NULL)."""
+    return _checked(a, "float64", _dp)
 
 
 def as_fp(a):
-    if a is None:
-        return None
-    return a.ctypes.data_as(_fp)
+    return _checked(a, "float32", _fp)
 
 
 def as_ip(a):
-    if a is None:
-        return None
-    return a.ctypes.data_as(_ip)
+    return _checked(a, "int32", _ip)

@@ -50,6 +50,24 @@ struct Buf {
   double* d() const { return (double*)p; }
 };
 
+// scope guards of the entry points that own temporaries (chi_nuts_sample): every early return
+// (CK, fail) releases them
+struct ScopedBuf : Buf {
+  ~ScopedBuf() { release(); }
+};
+struct ScopedPinned {
+  int* p = nullptr;
+  ~ScopedPinned() { if (p) cudaFreeHost(p); }
+};
+struct ScopedGraph {
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t x = nullptr;
+  ~ScopedGraph() {
+    if (x) cudaGraphExecDestroy(x);
+    if (g) cudaGraphDestroy(g);
+  }
+};
+
 static RowMap identity_rows() {
   RowMap m;
   m.n_rows = CHI_NSLOT;
@@ -136,6 +154,32 @@ struct chi_handle {
 namespace {
 
 bool make_ring(chi_handle* h);
+
+// ends a stream capture that an error path would otherwise leave open (the stream and the handle
+// would be unusable afterwards)
+struct CaptureGuard {
+  chi_handle* h;
+  cudaStream_t st;
+  bool active = false;
+  CaptureGuard(chi_handle* h_, cudaStream_t st_) : h(h_), st(st_) {}
+  cudaError_t begin() {
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) { active = true; h->capturing = true; }
+    return e;
+  }
+  cudaError_t end(cudaGraph_t* g) {
+    active = false;
+    h->capturing = false;
+    return cudaStreamEndCapture(st, g);
+  }
+  ~CaptureGuard() {
+    if (!active) return;
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(st, &g);
+    if (g) cudaGraphDestroy(g);
+    h->capturing = false;
+  }
+};
 
 int fail(chi_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
@@ -882,7 +926,12 @@ int chi_set_spectra(chi_handle* h, int n_sightlines, const chi_dataset* emission
   const bool got_a = absorption && absorption->n_channels > 0;
   if (h->has_e && !got_e) return fail(h, CHI_EINVAL, "chi_set_spectra: model needs an emission dataset");
   if (h->has_a && !got_a) return fail(h, CHI_EINVAL, "chi_set_spectra: model needs an absorption dataset");
-  CK(cudaStreamSynchronize(h->stream));
+  // every lane and priority stream: kernels of outstanding asynchronous tickets may still read the
+  // buffers replaced below (the tickets are complete when this returns)
+  {
+    int rc = chi_synchronize(h);
+    if (rc) return rc;
+  }
   std::vector<double> lconst(n_sightlines, 0.0);
   if (h->has_e) {
     int rc = upload_dataset(h, h->e, emission, n_sightlines, lconst.data(), "emission");
@@ -1678,7 +1727,11 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   const size_t bytes_i = (scal_i * B + D + 2) * sizeof(int) + (size_t)B * sizeof(unsigned long long);
   const int64_t n_keep = cfg->n_draws;
   const size_t bytes_out = (size_t)n_keep * B * (D + 3) * sizeof(double) + (size_t)n_keep * B * 2 * sizeof(int);
-  Buf arena;
+  if (sightline)
+    for (int64_t i = 0; i < B; ++i)
+      if (sightline[i] < 0 || sightline[i] >= h->n_sl) return fail(h, CHI_EINVAL, "chi_nuts_sample: sightline out of range");
+  ScopedBuf arena, slbuf, abuf;
+  ScopedPinned flags;
   CK(arena.ensure(bytes_d + bytes_i + bytes_out + 4096));
   CK(cudaMemsetAsync(arena.p, 0, bytes_d + bytes_i + 1024, st));
   char* cur = (char*)arena.p;
@@ -1713,10 +1766,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   int* d_depth = (int*)cur; cur += (size_t)n_keep * B * sizeof(int);
   int* d_div = (int*)cur; cur += (size_t)n_keep * B * sizeof(int);
   int32_t* d_sl = nullptr;
-  Buf slbuf;
   if (sightline) {
-    for (int64_t i = 0; i < B; ++i)
-      if (sightline[i] < 0 || sightline[i] >= h->n_sl) return fail(h, CHI_EINVAL, "chi_nuts_sample: sightline out of range");
     CK(slbuf.ensure(B * sizeof(int32_t)));
     CK(cudaMemcpyAsync(slbuf.p, sightline, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     d_sl = (int32_t*)slbuf.p;
@@ -1758,14 +1808,13 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   // one leapfrog step (half kick + drift, batched logp+grad, half kick + tree bookkeeping) as a
   // CUDA graph: ~8 dependent launches per step would otherwise be pure launch latency for a few
   // dozen chains
-  int* h_flags = nullptr;
-  CK(cudaMallocHost(&h_flags, 2 * sizeof(int)));
+  CK(cudaMallocHost(&flags.p, 2 * sizeof(int)));
+  int* h_flags = flags.p;
   const int total = n_tune + cfg->n_draws;
   if (!lock_step) {
     // asynchronous chains (nuts.cuh: k_nuts_tick): one graph = tick + batched evaluation, replayed
     // until every chain has done its n_tune + n_draws iterations; the host looks at one counter
     // every 32 ticks
-    Buf abuf;
     const size_t ab = (2 * (size_t)B + 4) * sizeof(int) + (size_t)std::max(n_tune, 1);
     CK(abuf.ensure(ab));
     CK(cudaMemsetAsync(abuf.p, 0, ab, st));
@@ -1779,11 +1828,12 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     A.closes = d_closes;
     A.draws = d_draws; A.stat_accept = d_acc; A.stat_logp = d_lp; A.stat_eps = d_eps;
     A.stat_depth = d_depth; A.stat_diverged = d_div;
-    cudaGraph_t tg = nullptr;
-    cudaGraphExec_t tgx = nullptr;
+    ScopedGraph tgs;
+    cudaGraph_t& tg = tgs.g;
+    cudaGraphExec_t& tgx = tgs.x;
     size_t tn = 0;
-    h->capturing = true;
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    CaptureGuard cap(h, st);
+    CK(cap.begin());
     if (getenv("CHI_NUTS_THREAD")) {  // A/B: one thread per chain, separate map kernel
       k_nuts_tick<<<grid, 64, 0, st>>>(s, A);
       rc = evaluate();
@@ -1797,8 +1847,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
       rc = run_backward(h, L0, B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, nullptr, nullptr, false,
                         s.elogp, s.egu, nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, PHASE_REST);
     }
-    cudaError_t cap_err = cudaStreamEndCapture(st, &tg);
-    h->capturing = false;
+    cudaError_t cap_err = cap.end(&tg);
     if (rc) return rc;
     CK(cap_err);
     CK(cudaGraphInstantiate(&tgx, tg, 0));
@@ -1814,28 +1863,24 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
       CK(cudaMemcpyAsync(h_flags, A.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
     }
-    cudaGraphExecDestroy(tgx);
-    cudaGraphDestroy(tg);
-    abuf.release();
     if (h_flags[0] < B) {
-      cudaFreeHost(h_flags);
       return fail(h, CHI_ECUDA, "chi_nuts_sample: chains did not finish within the tick budget");
     }
   }
-  cudaGraph_t graph[2] = {nullptr, nullptr};
+  ScopedGraph lgs[2];
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   size_t n_nodes[2] = {0, 0};
   for (int g = 0; g < 2 && lock_step; ++g) {  // g = 0: first leaf of a doubling (no pending half step), 1: the others
-    h->capturing = true;
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    CaptureGuard cap(h, st);
+    CK(cap.begin());
     k_nuts_leap<<<grid, 64, 0, st>>>(s, g, 1);
     rc = evaluate();
-    cudaError_t cap_err = cudaStreamEndCapture(st, &graph[g]);
-    h->capturing = false;
+    cudaError_t cap_err = cap.end(&lgs[g].g);
     if (rc) return rc;
     CK(cap_err);
-    CK(cudaGraphInstantiate(&gexec[g], graph[g], 0));
-    CK(cudaGraphGetNodes(graph[g], nullptr, &n_nodes[g]));
+    CK(cudaGraphInstantiate(&lgs[g].x, lgs[g].g, 0));
+    gexec[g] = lgs[g].x;
+    CK(cudaGraphGetNodes(lgs[g].g, nullptr, &n_nodes[g]));
   }
   for (int it = 0; it < total && lock_step; ++it) {
     k_nuts_begin_iter<<<grid, 64, 0, st>>>(s);
@@ -1883,11 +1928,6 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     }
     CK(cudaGetLastError());
   }
-  cudaFreeHost(h_flags);
-  for (int g = 0; g < 2 && lock_step; ++g) {
-    cudaGraphExecDestroy(gexec[g]);
-    cudaGraphDestroy(graph[g]);
-  }
   // draws back to the host in the layout of the API blocks
   CK(cudaStreamSynchronize(st));
   std::vector<double> tmp((size_t)n_keep * B * D);
@@ -1906,8 +1946,6 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   if (stat_step) CK(cudaMemcpy(stat_step, d_eps, (size_t)n_keep * B * sizeof(double), cudaMemcpyDeviceToHost));
   if (stat_depth) CK(cudaMemcpy(stat_depth, d_depth, (size_t)n_keep * B * sizeof(int), cudaMemcpyDeviceToHost));
   if (stat_diverged) CK(cudaMemcpy(stat_diverged, d_div, (size_t)n_keep * B * sizeof(int), cudaMemcpyDeviceToHost));
-  arena.release();
-  slbuf.release();
   return CHI_OK;
 }
 

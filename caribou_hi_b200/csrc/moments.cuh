@@ -102,7 +102,7 @@ __constant__ double c_expt[4] = {
     0x1.ebfbe039d53f1p-3,   // 2  q1
     0x1.c6b08da6e74bcp-5};  // 3  q2
 #define CHI_LOG2E 1.4426950408889634074
-#define CHI_LN2 0.69314718055994530942
+// CHI_LN2: cloud_map.cuh
 #define CHI_EXP_TABLE 1024
 
 struct ExpT {

@@ -17,6 +17,27 @@ def _f64(a, shape=None, name="array"):
     return a
 
 
+def _out_f64(out, key, shape):
+    """Caller-supplied output array ``out[key]`` (or a fresh one): the library writes ``prod(shape)``
+    doubles through its raw pointer, so it must be a C-contiguous float64 array of exactly that shape."""
+    a = out.get(key) if out else None
+    if a is None:
+        return np.empty(shape, dtype=np.float64)
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != tuple(shape):
+        raise ValueError(f"out[{key!r}]: expected a C-contiguous float64 array of shape {tuple(shape)}, got "
+                         f"{getattr(a, 'dtype', type(a))} {getattr(a, 'shape', '')}")
+    return a
+
+
+def _sightline(sightline, B):
+    if sightline is None:
+        return None
+    sl = np.ascontiguousarray(sightline, dtype=np.int32)
+    if sl.shape != (B,):
+        raise ValueError(f"sightline: expected [{B}], got {sl.shape}")
+    return sl
+
+
 class PinnedArray:
     """A NumPy view of page-locked host memory from ``chi_host_alloc`` (fast copies)."""
 
@@ -220,26 +241,13 @@ class Engine:
         B = theta.shape[0]
         ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
         ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
-        sl = None
-        if sightline is not None:
-            sl = np.ascontiguousarray(sightline, dtype=np.int32)
-            if sl.shape != (B,):
-                raise ValueError("sightline: expected [B]")
-        out = out or {}
-        logp = out.get("logp")
-        if logp is None:
-            logp = np.empty(B, dtype=np.float64)
+        sl = _sightline(sightline, B)
+        logp = _out_f64(out, "logp", (B,))
         grad = gce = gca = None
         if want_grad:
-            grad = out.get("grad")
-            if grad is None:
-                grad = np.empty((B, layout.NSLOT, N), dtype=np.float64)
-            if self.nb_e:
-                gce = out.get("gcoeff_e")
-                gce = np.empty((B, self.nb_e), dtype=np.float64) if gce is None else gce
-            if self.nb_a:
-                gca = out.get("gcoeff_a")
-                gca = np.empty((B, self.nb_a), dtype=np.float64) if gca is None else gca
+            grad = _out_f64(out, "grad", (B, layout.NSLOT, N))
+            gce = _out_f64(out, "gcoeff_e", (B, self.nb_e)) if self.nb_e else None
+            gca = _out_f64(out, "gcoeff_a", (B, self.nb_a)) if self.nb_a else None
         self._check(
             self._lib.chi_logp_grad(
                 self._h, B, _lib.as_dp(theta), _lib.as_dp(ce), _lib.as_dp(ca), _lib.as_ip(sl),
@@ -281,26 +289,13 @@ class Engine:
         B = rows.shape[0]
         ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
         ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
-        sl = None
-        if sightline is not None:
-            sl = np.ascontiguousarray(sightline, dtype=np.int32)
-            if sl.shape != (B,):
-                raise ValueError("sightline: expected [B]")
-        out = out or {}
-        logp = out.get("logp")
-        if logp is None:
-            logp = np.empty(B, dtype=np.float64)
+        sl = _sightline(sightline, B)
+        logp = _out_f64(out, "logp", (B,))
         grad = gce = gca = None
         if want_grad:
-            grad = out.get("grad")
-            if grad is None:
-                grad = np.empty((B, slots.size, N), dtype=np.float64)
-            if self.nb_e:
-                gce = out.get("gcoeff_e")
-                gce = np.empty((B, self.nb_e), dtype=np.float64) if gce is None else gce
-            if self.nb_a:
-                gca = out.get("gcoeff_a")
-                gca = np.empty((B, self.nb_a), dtype=np.float64) if gca is None else gca
+            grad = _out_f64(out, "grad", (B, slots.size, N))
+            gce = _out_f64(out, "gcoeff_e", (B, self.nb_e)) if self.nb_e else None
+            gca = _out_f64(out, "gcoeff_a", (B, self.nb_a)) if self.nb_a else None
         self._check(
             self._lib.chi_logp_grad_rows(
                 self._h, B, int(slots.size), _lib.as_ip(slots), _lib.as_dp(rows), _lib.as_dp(ce), _lib.as_dp(ca),
@@ -328,9 +323,7 @@ class Engine:
                 continue
             if a is None or a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != shape:
                 raise ValueError(f"{name}: expected a C-contiguous float64 array of shape {shape}")
-        sl = None
-        if sightline is not None:
-            sl = np.ascontiguousarray(sightline, dtype=np.int32)
+        sl = _sightline(sightline, B)
         ticket = C.c_int64(-1)
         self._check(
             self._lib.chi_logp_grad_rows_async(

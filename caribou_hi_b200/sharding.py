@@ -96,6 +96,7 @@ class ShardedLikelihood:
     def __init__(self, evaluate, device=None):
         self.evaluate = evaluate
         self.device = device
+        self.n_bad = 0  # non-finite draws (over all ranks) seen by the last total_logp_grad
 
     def logp_grad(self, theta):
         """``theta [B, ...]`` is the FULL batch, identical on every rank; returns the full
@@ -122,7 +123,13 @@ class ShardedLikelihood:
         lo, hi = shard_bounds(theta.shape[0], ws, rank)
         logp, grad = self.evaluate(theta[lo:hi])
         dev = self.device if self.device is not None else "cpu"
-        packed = torch.cat([torch.as_tensor(np.nansum(logp, keepdims=True)).reshape(1),
-                            torch.as_tensor(np.nansum(grad, axis=0)).reshape(-1)]).to(dev)
+        # plain sums: a NaN draw makes the total NaN, as it does in the reference (where the sampler
+        # then rejects the point); the third value counts this shard's non-finite draws for callers
+        # that want to know why
+        bad = np.count_nonzero(~np.isfinite(logp))
+        packed = torch.cat([torch.as_tensor(np.sum(logp, keepdims=True)).reshape(1),
+                            torch.as_tensor(np.sum(grad, axis=0)).reshape(-1),
+                            torch.as_tensor([float(bad)], dtype=torch.float64)]).to(dev)
         packed = reduce_sum(packed).cpu().numpy()
-        return packed[0], packed[1:].reshape(grad.shape[1:])
+        self.n_bad = int(packed[-1])
+        return packed[0], packed[1:-1].reshape(grad.shape[1:])

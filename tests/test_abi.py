@@ -61,3 +61,32 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_marshalling_refuses_wrong_dtype_and_strided_arrays():
+    """The library writes through raw pointers: float32, strided or wrongly shaped output arrays must be
+    refused on the Python side (silent host memory corruption otherwise)."""
+    import numpy as np
+
+    from caribou_hi_b200 import _lib
+    from caribou_hi_b200.engine import _out_f64, _sightline
+
+    assert _lib.as_dp(None) is None
+    _lib.as_dp(np.zeros(4))
+    with pytest.raises(TypeError):
+        _lib.as_dp(np.zeros(4, dtype=np.float32))
+    with pytest.raises(TypeError):
+        _lib.as_dp(np.zeros((4, 4))[:, 1])
+    with pytest.raises(TypeError):
+        _lib.as_ip(np.zeros(4, dtype=np.int64))
+    with pytest.raises(TypeError):
+        _lib.as_fp(np.zeros(4))
+    assert _out_f64(None, "logp", (3,)).shape == (3,)
+    ok = np.empty((3, 2))
+    assert _out_f64({"grad": ok}, "grad", (3, 2)) is ok
+    for bad in (np.empty((3, 2), dtype=np.float32), np.empty((4, 2)), np.empty((3, 4))[:, ::2]):
+        with pytest.raises(ValueError):
+            _out_f64({"grad": bad}, "grad", (3, 2))
+    with pytest.raises(ValueError):
+        _sightline(np.zeros(2), 3)
+    assert _sightline([0, 1, 2], 3).dtype == np.int32
