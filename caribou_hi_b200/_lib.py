@@ -27,6 +27,8 @@ MODEL_ABSORPTION_PHYSICAL = 4
 MODEL_EMISSION_PHYSICAL = 5
 MODEL_EMISSION_ABSORPTION_PHYSICAL = 6
 
+OPT_SMALL_PATH, OPT_SMALL_NL, OPT_SMALL_CHUNKS, OPT_SMALL_STAMPS = 0, 1, 2, 3
+
 ERROR_NAMES = {0: "CHI_OK", -1: "CHI_EINVAL", -2: "CHI_ECUDA", -3: "CHI_ENODEV", -4: "CHI_ESTATE", -5: "CHI_ENOMEM"}
 
 _dp = C.POINTER(C.c_double)
@@ -146,6 +148,7 @@ SYMBOLS = {
     "chi_last_kernel_ms":(C.c_int, [_H, C.POINTER(C.c_float)]),
     "chi_stage_ms": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float)]),
     "chi_launch_count": (C.c_int64, [_H]),
+    "chi_set_option": (C.c_int, [_H, C.c_int, C.c_int64]),
     "chi_microbench_fp64": (C.c_int, [_H, C.POINTER(C.c_double)]),
 }
 

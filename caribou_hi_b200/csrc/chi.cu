@@ -98,6 +98,8 @@ struct Lane {
   cudaStream_t jac = nullptr;
   cudaEvent_t ev_jac = nullptr;
   Buf jacbuf;
+  Buf cnt;            // small batches: blocks-done counter per draw (k_eval_small), zero between launches
+  size_t cnt_zeroed = 0;
   // pipelined host path: the epilogue and the downloads of a piece run on a high-priority stream, so
   // that they are not starved by the channel kernels of the following pieces (which were queued
   // first and would otherwise keep every SM until they drain) and the lane is free again early
@@ -108,7 +110,8 @@ struct Lane {
   Buf xcon, prior;                                                // constrained values, per-cloud priors
   Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca;    // staging of the host entry points
   void release() {
-    Buf* bufs[] = {&cc, &mom_e, &mom_a, &xcon, &prior, &jacbuf, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
+    cnt_zeroed = 0;
+    Buf* bufs[] = {&cc, &mom_e, &mom_a, &xcon, &prior, &jacbuf, &cnt, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
     for (Buf* b : bufs) b->release();
   }
 };
@@ -142,12 +145,14 @@ struct chi_handle {
   Buf chan;                  // its packed per-channel data [n_sl][S][8]
   bool priors_set = false;
   bool capturing = false;  // inside a stream capture: no timing events
+  bool graph_path = false; // the evaluations of this call are replayed from a CUDA graph (the sampler)
   double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];
   int64_t call_draws = 0;        // draws of the host call in flight (0 outside the pipelined host path)
   bool epilogue_on_hi = false;   // pipelined host path: epilogue + downloads on the lane's priority stream
   int map_ahead = 0;             // PHASE_MAP: ring slots between the piece being mapped and stage_calls
   int64_t call_first_stage = 0;  // stage_calls at the start of the current model-level call
   int64_t launches = 0;
+  int64_t opt[CHI_OPT_COUNT] = {};  // chi_set_option
   std::string err;
 };
 
@@ -257,6 +262,114 @@ int launch_cloud_map(chi_handle* h, Lane& L, int64_t B, const double* theta, dou
   return CHI_OK;
 }
 
+// ---- small batches: one launch per evaluation (small.cuh) ----------------------------------------
+// A batch is "small" when its evaluation is bound by dependent latency rather than throughput (a few
+// dozen chains).  The choice follows the size of the caller's batch, not of a pipeline piece.
+bool batch_is_small(const chi_handle* h, int64_t B) {
+  const int N = h->cfg.n_clouds;
+  const int K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
+  const int64_t B_call = std::max<int64_t>(B, h->call_draws);
+  return B_call * N * K <= (int64_t)h->n_sm * 1024 && N * K <= 128;
+}
+// k_eval_small (one launch: map + channels + Jacobian + contraction) against the pipeline
+// (map -> channel kernel || Jacobian -> contraction), measured on B200 (tools/small_ab.py,
+// profiles/r2_small_batch.txt):
+//   * more than 8 clouds: the pipeline runs on the 12- / 16-cloud instantiations (255 registers,
+//     kilobytes of spills); one launch is 2.4x faster (57.6 -> 23.9 us at 32 chains x 16 clouds);
+//   * launched from the host one call at a time (the Op / Engine path): a call costs what its
+//     launches cost the host, one launch instead of four is 46.6 against 54.3 us at 64 chains x
+//     8 clouds x 2048+2048 channels, 28.6 against 40.8 us at 8 chains x 2 clouds;
+//   * replayed from a CUDA graph (the sampler's ticks): launches are free and the pipeline's channel
+//     kernel executes fewer instructions per channel (every cloud in one thread): 29.2 against
+//     31.6 us -> the sampler keeps the pipeline (graph_path).
+// CHI_OPT_SMALL_PATH overrides (tests run both paths).
+bool use_eval_small(const chi_handle* h, int64_t B, bool vjp) {
+  if (vjp || h->epilogue_on_hi || h->cfg.n_clouds * CHI_NSLOT > CHI_SM_THREADS - 96) return false;
+  const int64_t mode = h->opt[CHI_OPT_SMALL_PATH];
+  if (mode == 1) return false;
+  if (mode == 2) return true;
+  if (!batch_is_small(h, B)) return false;
+  if (h->cfg.n_clouds > 8) return true;
+  return !h->graph_path && std::max<int64_t>(B, h->call_draws) <= 128;
+}
+
+int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const double* ce, const double* ca,
+              const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model) {
+  const int N = h->cfg.n_clouds;
+  const bool pv = h->cfg.lorentzian != 0;
+  cudaEvent_t* evs = h->ring[h->stage_calls % CHI_STAGE_RING];
+  SmallArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
+  a.rm = h->rm; a.prior = model ? 1 : 0; a.want_grad = grad ? 1 : 0;
+  a.fused = h->shared_axis ? 1 : 0;
+  a.has_e = h->has_e ? 1 : 0; a.has_a = h->has_a ? 1 : 0;
+  a.S_e = h->has_e ? h->e.S : 0; a.S_a = h->has_a ? h->a.S : 0;
+  a.nb_e = h->has_e ? h->e.nb : 0; a.nb_a = h->has_a ? h->a.nb : 0;
+  a.bg = h->cfg.bg_temp;
+  // clouds per thread (NL) and lane groups (2^lgG) of a channel: one cloud per thread, two for 5..8
+  // clouds (measured: 31.6 us against 36.1 at configs[2] shape; more clouds per thread need more
+  // registers than two resident blocks per SM leave)
+  const int force_nl = (int)h->opt[CHI_OPT_SMALL_NL];
+  const int S_max = std::max(a.S_e, a.S_a);
+  int NL = (N >= 5 && N <= 8) ? 2 : 1;
+  if (force_nl >= 1 && force_nl <= 2 && force_nl * 16 >= N) NL = force_nl;
+  int lgG = 0;
+  while ((NL << lgG) < N) ++lgG;
+  a.lgG = lgG;
+  const int NP = NL << lgG, cpw = 32 >> lgG;
+  // blocks per draw: fill the resident block slots once, at least one warp tile per channel warp
+  const int force_chunks = (int)h->opt[CHI_OPT_SMALL_CHUNKS];
+  int64_t want = std::max<int64_t>(1, ((int64_t)h->n_sm * eval_small_blocks_per_sm(NL)) / B);
+  if (force_chunks > 0) want = force_chunks;
+  const int max_chunks = std::max(1, S_max / (cpw * 7));
+  int nc = (int)std::min<int64_t>(want, max_chunks);
+  auto chunk_len = [&](int S) { int len = (S + nc - 1) / nc; return std::max(cpw, (len + cpw - 1) / cpw * cpw); };
+  a.chunk_e = a.S_e ? chunk_len(a.S_e) : 0;
+  a.chunk_a = a.S_a ? chunk_len(a.S_a) : 0;
+  nc = std::max(a.S_e ? (a.S_e + a.chunk_e - 1) / a.chunk_e : 1, a.S_a ? (a.S_a + a.chunk_a - 1) / a.chunk_a : 1);
+  a.n_chunks = nc;
+  // (the same warps are set aside whether or not this call wants the gradient: a logp-only call
+  // then sums its channels in the same order and returns the same bits)
+  a.jac_warps = ((N * a.K + nc - 1) / nc + 31) / 32;
+  const int per_cloud = a.fused ? (pv ? 10 : 6) : (a.has_e ? (pv ? 8 : 5) : 0) + (a.has_a ? (pv ? 6 : 3) : 0);
+  a.stride = 1 + a.nb_e + a.nb_a + NP * per_cloud;
+  CK(L.mom_e.ensure((size_t)B * nc * a.stride * sizeof(double)));
+  CK(L.jacbuf.ensure((size_t)B * N * a.K * CHI_JAC_W * sizeof(double)));
+  CK(L.prior.ensure((size_t)B * N * sizeof(double)));
+  CK(L.cnt.ensure((size_t)B * sizeof(unsigned)));
+  if (L.cnt_zeroed != L.cnt.cap) {  // fresh allocation: the kernel leaves the counters at zero afterwards
+    CK(cudaMemsetAsync(L.cnt.p, 0, L.cnt.cap, L.st));
+    L.cnt_zeroed = L.cnt.cap;
+  }
+  a.chan = h->chan.d(); a.chan_e = h->e.chan.d(); a.chan_a = h->a.chan.d();
+  a.basis_e = h->e.basis.d(); a.basis_a = h->a.basis.d();
+  a.theta = theta; a.coeff_e = ce; a.coeff_a = ca; a.sl = sl; a.lconst = h->lconst.d();
+  a.mom = L.mom_e.d(); a.jac = L.jacbuf.d(); a.prior_buf = L.prior.d(); a.counter = (unsigned*)L.cnt.p;
+  a.logp = logp; a.grad = grad; a.gce = gce; a.gca = gca;
+  memcpy(a.bsig_e, h->bsig_e, sizeof(a.bsig_e));
+  memcpy(a.bsig_a, h->bsig_a, sizeof(a.bsig_a));
+  a.stamps = (long long*)(uintptr_t)h->opt[CHI_OPT_SMALL_STAMPS];
+  for (int i = 0; i < a.nb_e && model; ++i) a.bprior_const += -log(h->bsig_e[i]) - CHI_HALF_LOG_2PI;
+  for (int i = 0; i < a.nb_a && model; ++i) a.bprior_const += -log(h->bsig_a[i]) - CHI_HALF_LOG_2PI;
+  const int n_gb = (a.nb_e > 1 ? a.nb_e - 1 : 0) + (a.nb_a > 1 ? a.nb_a - 1 : 0);
+  if (!h->capturing) {
+    CK(cudaEventRecord(evs[0], L.st));
+    CK(cudaEventRecord(evs[1], L.st));
+  }
+  if (launch_eval_small(NL, pv, h->map, a, (size_t)n_gb * CHI_SM_THREADS * sizeof(double), L.st))
+    return fail(h, CHI_EINVAL, "unsupported small-batch configuration");
+  h->launches++;
+  CK(cudaGetLastError());
+  if (!h->capturing) {
+    CK(cudaEventRecord(evs[2], L.st));
+    CK(cudaEventRecord(evs[3], L.st));
+    CK(cudaEventRecord(evs[4], L.st));
+    h->stage_calls++;
+  }
+  return CHI_OK;
+}
+
 // moments (+ optional logp) + epilogue; gbar_* != null selects the VJP mode
 // `model` = true: theta holds unconstrained values; priors and Jacobians are added (chi_model_logp_grad)
 enum { PHASE_ALL = 0, PHASE_MAP = 1, PHASE_REST = 2 };
@@ -268,6 +381,10 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   // stage-ring slot further on) before the channel kernels of sub-batch k (PHASE_REST), so that the
   // map is not queued behind the previous sub-batch's channel kernel and the channel kernels of
   // consecutive sub-batches run back to back
+  if (use_eval_small(h, B, vjp)) {
+    if (phase == PHASE_MAP) return CHI_OK;  // the map is part of the one launch
+    return run_small(h, L, B, theta, ce, ca, sl, logp, grad, gce, gca, model);
+  }
   const int N = h->cfg.n_clouds;
   const bool pv = h->cfg.lorentzian != 0;
   const int ahead = (phase == PHASE_MAP) ? h->map_ahead : 0;
@@ -309,8 +426,7 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
   // the size of the caller's batch, not of a pipeline piece: every draw of a call goes through the
   // same arithmetic whatever piece it lands in.)
   const int K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
-  const int64_t B_call = std::max<int64_t>(B, h->call_draws);
-  const bool small = B_call * N * K <= (int64_t)h->n_sm * 1024 && N * K <= 128;
+  const bool small = batch_is_small(h, B);
   static const bool old_split = getenv("CHI_OLD_SPLIT") != nullptr;  // A/B knob: split epilogue on the main stream
   const bool side_jac = small && !old_split && !h->epilogue_on_hi;
   if (side_jac && (grad || model)) {
@@ -1155,6 +1271,19 @@ int chi_radiative_transfer_vjp(chi_handle* h, int S, int N, const double* tau, c
 }
 
 // ---- model-level, device pointers ------------------------------------------------
+// The *_dev entry points may be called while the caller captures the handle's stream into a CUDA
+// graph (after one un-captured call of the same size, which allocates the workspace): no timing
+// events are recorded then.
+struct CaptureAware {
+  chi_handle* h;
+  bool was;
+  explicit CaptureAware(chi_handle* h_) : h(h_), was(h_->capturing) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(h->stream, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) h->capturing = true;
+  }
+  ~CaptureAware() { h->capturing = was; }
+};
+
 int chi_logp_grad_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
                       const int32_t* sl, double* logp, double* grad, double* gce, double* gca) {
   int rc = check_model_call(h, B, theta);
@@ -1162,6 +1291,7 @@ int chi_logp_grad_dev(chi_handle* h, int64_t B, const double* theta, const doubl
   if (!logp) return fail(h, CHI_EINVAL, "chi_logp_grad: logp_out is NULL");
   if (B == 0) return CHI_OK;
   CK(cudaSetDevice(h->device));
+  CaptureAware cap_aware(h);
   h->call_first_stage = h->stage_calls;
   h->kernel_ms = 0.f;
   return run_backward(h, h->lanes[0], B, theta, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca);
@@ -1450,6 +1580,7 @@ int chi_model_logp_grad_dev(chi_handle* h, int64_t B, const double* u, const dou
   if (!logp) return fail(h, CHI_EINVAL, "chi_model_logp_grad: logp_out is NULL");
   if (B == 0) return CHI_OK;
   CK(cudaSetDevice(h->device));
+  CaptureAware cap_aware(h);
   h->call_first_stage = h->stage_calls;
   h->kernel_ms = 0.f;
   return run_backward(h, h->lanes[0], B, u, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca, true);
@@ -1655,6 +1786,13 @@ int chi_stage_ms(chi_handle* h, int n, float* ms_out) {
 }
 
 int64_t chi_launch_count(const chi_handle* h) { return h ? h->launches : 0; }
+
+int chi_set_option(chi_handle* h, int option, int64_t value) {
+  if (!h) return CHI_EINVAL;
+  if (option < 0 || option >= CHI_OPT_COUNT) return fail(h, CHI_EINVAL, "chi_set_option: unknown option");
+  h->opt[option] = value;
+  return CHI_OK;
+}
 int64_t chi_stage_count(const chi_handle* h) { return h ? h->stage_calls : 0; }
 
 int chi_microbench_fp64(chi_handle* h, double* tflops_out) {
@@ -1699,6 +1837,11 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   const bool lock_step = cfg->lock_step != 0 || pool_mass;  // pooled windows close for all chains at once
   const double target = cfg->target_accept > 0.0 ? cfg->target_accept : 0.8;
   CK(cudaSetDevice(h->device));
+  struct GraphPath {  // every evaluation of the sampler takes the path that is best inside a graph
+    chi_handle* h;
+    explicit GraphPath(chi_handle* h_) : h(h_) { h->graph_path = true; }
+    ~GraphPath() { h->graph_path = false; }
+  } graph_path(h);
   const int64_t B = cfg->chains;
   const int N = h->cfg.n_clouds, nu = CHI_NSLOT * N;
   const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
@@ -1832,6 +1975,9 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     cudaGraph_t& tg = tgs.g;
     cudaGraphExec_t& tgx = tgs.x;
     size_t tn = 0;
+    // workspace of the tick is allocated before the capture starts
+    CK(h->lanes[0].xcon.ensure((size_t)B * CHI_NSLOT * N * sizeof(double)));
+    CK(h->lanes[0].cc.ensure((size_t)B * N * CHI_CC_STRIDE * sizeof(double)));
     CaptureGuard cap(h, st);
     CK(cap.begin());
     if (getenv("CHI_NUTS_THREAD")) {  // A/B: one thread per chain, separate map kernel
@@ -1839,9 +1985,9 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
       rc = evaluate();
     } else {  // one warp per chain; the tick also maps the new evaluation point
       Lane& L0 = h->lanes[0];
-      CK(L0.xcon.ensure((size_t)B * CHI_NSLOT * N * sizeof(double)));
+      double* tick_cc = use_eval_small(h, B, false) ? nullptr : L0.cc.d();
       MODEL_SWITCH(h->cfg.model, (k_nuts_tick_w<M><<<(unsigned)((B + 3) / 4), 128, 0, st>>>(s, A, h->map, h->rm,
-                                                                                        L0.cc.d(), L0.xcon.d())));
+                                                                                        tick_cc, L0.xcon.d())));
       CK(cudaEventRecord(L0.ev_fork, L0.st));  // the cloud constants are ready from here on
       h->call_first_stage = h->stage_calls;
       rc = run_backward(h, L0, B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, nullptr, nullptr, false,

@@ -32,10 +32,7 @@ namespace chi {
 // s, -1 = the caller does not carry that slot (reads as 0, its gradient is dropped).  The slot
 // layout [B][CHI_NSLOT][N] is the identity map; the packed form carries only the free RVs a
 // model kind has (chi_logp_grad_rows: fewer bytes over PCIe).
-struct RowMap {
-  int n_rows;
-  signed char row[CHI_NSLOT];
-};
+// (struct RowMap: launch.cuh)
 
 // the map of one (draw, cloud); also called from the sampler's tick kernel (nuts_warp.cuh)
 template <int MODEL>
@@ -333,7 +330,6 @@ __global__ void __launch_bounds__(128, (!SPLIT && !PRIOR) ? 4 : 1) k_epilogue(Ma
 // Same arithmetic as k_epilogue<MODEL, true, PRIOR>; record per (draw, cloud, direction):
 //   [dk_e, dAG_e, dAL_e, dh_e, dk_a, dAG_a, dAL_a, dh_a, dTs, df, dc, d(prior density), dx/du, w dlogJ/du]
 // ---------------------------------------------------------------------------
-#define CHI_JAC_W 14
 struct JacArgs {
   int64_t B;
   int N;

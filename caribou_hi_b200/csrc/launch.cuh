@@ -6,6 +6,14 @@
 #include "moments.cuh"
 
 namespace chi {
+// layout of a caller's theta / grad block (see k_cloud_map in kernels.cuh)
+struct RowMap {
+  int n_rows;
+  signed char row[CHI_NSLOT];
+};
+// doubles per record of the Jacobian of the parameter maps (k_jacobian, small.cuh)
+#define CHI_JAC_W 14
+
 // argument block of the spectra-only kernels
 struct SpecArgs {
   int64_t B;
@@ -54,6 +62,53 @@ struct FusedArgs;
 int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st);
 int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st);
 int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st);
+// ---- argument block of k_eval_small (small.cuh) ----
+#define CHI_SM_THREADS 256
+#define CHI_SM_WARPS (CHI_SM_THREADS / 32)
+#define CHI_SM_CCS 17  // doubles per cloud in shared memory: odd stride, lanes of different clouds hit different banks
+#define CHI_SM_MAXREC (1 + 2 * CHI_MAX_BASELINE + CHI_MAX_CLOUDS * 14)
+
+struct SmallArgs {
+  int64_t B;
+  int N;         // clouds of the model
+  int lgG;       // log2 of the lane groups a channel's clouds are spread over (NL * 2^lgG >= N)
+  int K;         // tangent directions per cloud (free RVs; 7 for CHI_MODEL_PHYSICS)
+  RowMap rm;     // layout of theta and grad
+  int prior;     // 1: theta holds unconstrained values, priors and Jacobians are added
+  int want_grad;
+  int fused, has_e, has_a;
+  int S_e, S_a, nb_e, nb_a;
+  int n_chunks;          // blocks per draw
+  int chunk_e, chunk_a;  // channels per chunk
+  int stride;            // doubles per (draw, chunk) record
+  int jac_warps;         // last warps of a block that evaluate Jacobian records instead of channels
+  double bg;
+  const double* __restrict__ chan;    // shared axis: [n_sl][ceil(S/32)][8][32] (moments_ea.cuh)
+  const double* __restrict__ chan_e;  // else per dataset [n_sl][ceil(S/32)][4][32] (moments.cuh)
+  const double* __restrict__ chan_a;
+  const double* __restrict__ basis_e;
+  const double* __restrict__ basis_a;
+  const double* __restrict__ theta;   // [B][n_rows][N]
+  const double* __restrict__ coeff_e;
+  const double* __restrict__ coeff_a;
+  const int32_t* __restrict__ sl;
+  const double* __restrict__ lconst;
+  double* __restrict__ mom;           // [B][n_chunks][stride]
+  double* __restrict__ jac;           // [B][N][K][CHI_JAC_W]
+  double* __restrict__ prior_buf;     // [B][N]
+  unsigned* __restrict__ counter;     // [B], zero between launches
+  double* __restrict__ logp;
+  double* __restrict__ grad;
+  double* __restrict__ gce;
+  double* __restrict__ gca;
+  double bsig_e[CHI_MAX_BASELINE], bsig_a[CHI_MAX_BASELINE];
+  double bprior_const;  // sum over the baseline coefficients in use of -log sigma_i - .5 log 2 pi
+  long long* stamps;  // development aid (CHI_OPT_SMALL_STAMPS): SM-clock offsets of block 0's phases, else null
+};
+
+// one-launch evaluation of a small batch (small.cuh); NL = clouds per thread (1 or 2)
+int launch_eval_small(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, size_t dyn_smem, cudaStream_t st);
+int eval_small_blocks_per_sm(int NL);
 
 // cloud count of the instantiation that serves a model with N clouds
 inline int padded_clouds(int N) { return N <= 8 ? N : (N <= 12 ? 12 : 16); }

@@ -1,0 +1,33 @@
+// k_eval_small<NL, PV> instantiations: the one-launch logp + gradient evaluation of small batches
+// (small.cuh).  The O(N) parameter maps are compiled once per unit, not per instantiation.  Built twice
+// (launch_small.cu: Gaussian, launch_small_pv.cu: pseudo-Voigt) so the halves compile in parallel.
+#include "launch.cuh"
+#include "small.cuh"
+
+#ifndef CHI_SMALL_PV
+#define CHI_SMALL_PV 0
+#endif
+
+namespace chi {
+#if CHI_SMALL_PV
+int launch_eval_small_pv(int NL, const MapCfg& cfg, const SmallArgs& a, size_t dyn_smem, cudaStream_t st) {
+#else
+int launch_eval_small_pv(int NL, const MapCfg& cfg, const SmallArgs& a, size_t dyn_smem, cudaStream_t st);
+static int launch_eval_small_g(int NL, const MapCfg& cfg, const SmallArgs& a, size_t dyn_smem, cudaStream_t st) {
+#endif
+  constexpr bool PV = CHI_SMALL_PV != 0;
+  const unsigned grid = (unsigned)(a.B * a.n_chunks);
+  switch (NL) {
+    case 1: k_eval_small<1, PV><<<grid, CHI_SM_THREADS, dyn_smem, st>>>(cfg, a); return 0;
+    case 2: k_eval_small<2, PV><<<grid, CHI_SM_THREADS, dyn_smem, st>>>(cfg, a); return 0;
+  }
+  return -1;
+}
+#if !CHI_SMALL_PV
+int launch_eval_small(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, size_t dyn_smem, cudaStream_t st) {
+  return pv ? launch_eval_small_pv(NL, cfg, a, dyn_smem, st) : launch_eval_small_g(NL, cfg, a, dyn_smem, st);
+}
+// resident blocks per SM of the instantiation (its launch bounds)
+int eval_small_blocks_per_sm(int NL) { return NL <= 2 ? 2 : 1; }
+#endif
+}  // namespace chi

@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A, M
     nw_begin_subtree(s, b, lane);
   }
   nw_leap_a(s, b, lane);
-  if (lane < s.N) cloud_map_one<MODEL>(cfg, rm, s.N, s.eu, cc, xcon, b, lane);
+  // cc == null: the evaluation kernel maps the point itself (k_eval_small)
+  if (cc && lane < s.N) cloud_map_one<MODEL>(cfg, rm, s.N, s.eu, cc, xcon, b, lane);
 }
 
 #undef CHI_FOR_D

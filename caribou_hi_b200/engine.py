@@ -698,6 +698,14 @@ class Engine:
     def launch_count(self):
         return int(self._lib.chi_launch_count(self._h))
 
+    def set_option(self, name, value):
+        """Tuning / test knobs (``chi_set_option``): ``small_path`` 0 by batch size, 1 never, 2 always
+        (the one-launch evaluation of small batches); ``small_nl`` clouds per thread of that kernel;
+        ``small_chunks`` its blocks per draw."""
+        opts = {"small_path": _lib.OPT_SMALL_PATH, "small_nl": _lib.OPT_SMALL_NL, "small_chunks": _lib.OPT_SMALL_CHUNKS,
+                "small_stamps": _lib.OPT_SMALL_STAMPS}
+        self._check(self._lib.chi_set_option(self._h, opts[name], int(value)))
+
     def microbench_fp64(self):
         v = C.c_double()
         self._check(self._lib.chi_microbench_fp64(self._h, C.byref(v)))

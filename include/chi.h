@@ -405,6 +405,20 @@ int chi_stage_ms(chi_handle* h, int n, float* ms_out);
 int64_t chi_stage_count(const chi_handle* h);
 /* Number of kernel launches issued by this handle since creation. */
 int64_t chi_launch_count(const chi_handle* h);
+/* Tuning / test knobs of a handle (no reference counterpart; results stay within the parity
+ * tolerance whatever the setting, which is what the tests use them for).
+ *   CHI_OPT_SMALL_PATH    0 = by batch size (default), 1 = never, 2 = always: the one-launch
+ *                         evaluation of small batches (csrc/small.cuh) instead of the
+ *                         map -> channel kernels -> epilogue pipeline
+ *   CHI_OPT_SMALL_NL      clouds per thread of that kernel (0 = automatic, 1, 2)
+ *   CHI_OPT_SMALL_CHUNKS  its blocks per draw (0 = automatic) */
+#define CHI_OPT_SMALL_PATH 0
+#define CHI_OPT_SMALL_NL 1
+#define CHI_OPT_SMALL_CHUNKS 2
+#define CHI_OPT_SMALL_STAMPS 3 /* development aid: device pointer to 16 int64 receiving SM-clock offsets
+                                  of block 0's phases (0 = off) */
+#define CHI_OPT_COUNT 8
+int chi_set_option(chi_handle* h, int option, int64_t value);
 /* Own-microbenchmark peaks of the device the handle is on (the driver's
  * MEASURED_PEAKS.json has no CUDA-core FP64 figure): dependent-free DFMA chains. */
 int chi_microbench_fp64(chi_handle* h, double* tflops_out);

@@ -8,7 +8,7 @@ against the oracle at the 1e-10 bar."""
 import numpy as np
 import pytest
 
-from helpers import assert_close, make_case, oracle_logp_grad
+from helpers import assert_close, assert_grad_close, make_case, oracle_logp_grad
 from oracle import models_ref as mr
 
 pytestmark = pytest.mark.gpu
@@ -41,12 +41,6 @@ def test_random_configuration(cuda_device, i):
     c = _config(i)
     spec, data, free, baseline = make_case(c["kind"], c["N"], c["S_e"], c["S_a"], c["B"], c["seed"], lorentzian=c["lor"],
                                            baseline_degree=c["deg"], shared_axis=c["shared"])
-    # Chi-square draws below 1e-3 (2.5 % of the prior mass) give FWHM^2 of 1e-6 km2/s2 and kinetic
-    # temperatures of 1e-5 K: there the gradient itself is so ill-conditioned (fwhm2 - fwhm2_thermal
-    # cancels) that fp64 autograd and the CUDA path are both 4-6e-8 off the 60-digit value
-    # (configurations 51 and 69 before this floor, arbitrated with mpmath like
-    # tests/test_oracle_arbiter.py); such draws are floored rather than compared at 1e-10.
-    free["fwhm2_norm"] = np.maximum(free["fwhm2_norm"], 1e-3)
     rng = np.random.default_rng(c["seed"] + 1)
     n_sl, B = c["n_sl"], c["B"]
     # per-sightline spectra: the case's data plus independent perturbations
@@ -91,14 +85,15 @@ def test_random_configuration(cuda_device, i):
                                          {k: v[sel] for k, v in baseline.items()})
         assert_close(lp[sel], ref_lp, what=f"{c} logp", axis=None)
         fin = np.isfinite(ref_lp)
-        x = [got[n][sel][fin] for n in names]
-        r = [ref_g[n][fin] for n in names]
+        g_sel = {n: got[n][sel] for n in names}
         if gce is not None:
-            x.append(gce[sel][fin]); r.append(ref_g["baseline_emission_norm"][fin])
+            g_sel["baseline_emission_norm"] = gce[sel]
         if gca is not None:
-            x.append(gca[sel][fin]); r.append(ref_g["baseline_absorption_norm"][fin])
-        if fin.any():
-            assert_close(np.concatenate(x, axis=1), np.concatenate(r, axis=1), what=f"{c} gradient")
+            g_sel["baseline_absorption_norm"] = gca[sel]
+        # per RV vector; components that miss 1e-10 against autograd (tiny chi-square draws give kinetic
+        # temperatures of 1e-5 K where fwhm2 - fwhm2_thermal cancels) go to the 60-digit arbiter
+        case = (spec, per_sl[j], {k: v[sel] for k, v in free.items()}, {k: v[sel] for k, v in baseline.items()})
+        assert_grad_close(g_sel, ref_g, fin, case=case, what=f"{c} gradient", max_arbitrations=60)
     if n_sl == 1:  # predicted spectra (fused forward kernel on a shared axis, one kernel per dataset otherwise)
         ref_mu = mr.predict(spec, per_sl[0], free, baseline)
         mu_e, mu_a = eng.spectra(eng.pack(free), ce, ca)
