@@ -101,30 +101,93 @@ __device__ __forceinline__ double chi_exp(double x) { return chi_exp<true>(x, lo
 __device__ const double g_exp2_table[1024] = {
 #include "exp2_table.inc"
 };
+#define CHI_LOG2E 1.4426950408889634074
+// CHI_LN2: cloud_map.cuh
+#ifndef CHI_EXP_REPL
+#define CHI_EXP_REPL 0
+#endif
+#if CHI_EXP_REPL
+// A/B variant (tools/exp_variants.sh), REJECTED: 128 table entries (2^(j/128)), each replicated 16 times
+// so that lane l reads bank pair l % 16 whatever its index -- no bank conflicts -- and a cubic q (one
+// more FMA per exponential) for the 8x wider remainder |r| <= 2^-8.  Measured at configs[1]: fused
+// kernel 1.480 -> 1.566 ms (Gaussian), 2.155 -> 2.233 ms (pseudo-Voigt): the extra FP64 instruction
+// costs more than the 25 % of shared-memory wavefronts that were conflicts; the kernel is bound by
+// FP64 issue, not by the LSU (profiles/r2_exp_variants.txt).
+__constant__ double c_expt[5] = {
+    52776558133248.0,       // 0  1.5 * 2^45: rounds to multiples of 2^-7
+    0x1.62e42fefa3900p-1,   // 1..4 least-squares cubic of (2^r - 1)/r on |r| <= 2^-8
+    0x1.ebfbdff82c45bp-3, 0x1.c6b096cd133cfp-5, 0x1.3b2abc975b807p-7};
+#define CHI_EXP_BITS 7
+#define CHI_EXP_TABLE (128 * 16)
+#define CHI_EXP_NK 5
+#else
 __constant__ double c_expt[4] = {
     6597069766656.0,        // 0  1.5 * 2^42
     0x1.62e42fefa39efp-1,   // 1  q0 = ln2
     0x1.ebfbe02772c13p-3,   // 2  q1
     0x1.c6b08d95bd306p-5};  // 3  q2
-#define CHI_LOG2E 1.4426950408889634074
-// CHI_LN2: cloud_map.cuh
+#define CHI_EXP_BITS 10
 #define CHI_EXP_TABLE 1024
+#define CHI_EXP_NK 4
+#endif
 
 struct ExpT {
-  double k[4];
-  unsigned T;  // shared-memory address of the table
+  double k[CHI_EXP_NK];
+  unsigned T;  // shared-memory address of the table (of this lane's replica in the replicated form)
 };
 __device__ __forceinline__ ExpT load_expt(const double* shared_table) {
   ExpT e;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) e.k[i] = c_expt[i];
+  for (int i = 0; i < CHI_EXP_NK; ++i) e.k[i] = c_expt[i];
   e.T = (unsigned)__cvta_generic_to_shared(shared_table);
+#if CHI_EXP_REPL
+  e.T += (threadIdx.x & 15) * 8;
+#endif
   return e;
 }
 // every thread of the block must call this before any early exit (block barrier inside)
 __device__ __forceinline__ void fill_exp_table(double* shared_table) {
+#if CHI_EXP_REPL
+  for (int i = threadIdx.x; i < CHI_EXP_TABLE; i += blockDim.x) shared_table[i] = g_exp2_table[(i >> 4) << 3];
+#else
   for (int i = threadIdx.x; i < CHI_EXP_TABLE; i += blockDim.x) shared_table[i] = g_exp2_table[i];
+#endif
   __syncthreads();
+}
+// table look-up and polynomial shared by the two entry points: n = lo32(t), r the remainder
+__device__ __forceinline__ double chi_exp2_core(int n, double r, const ExpT& c, int& m) {
+  unsigned addr;
+#if CHI_EXP_REPL
+  asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(addr) : "r"(n & 127), "r"(c.T));
+#else
+  asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(n & (CHI_EXP_TABLE - 1)), "r"(c.T));
+#endif
+  double Tj;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(Tj) : "r"(addr));
+#if CHI_EXP_REPL
+  double q = fma(c.k[4], r, c.k[3]);
+  q = fma(q, r, c.k[2]);
+#else
+  double q = fma(c.k[3], r, c.k[2]);
+#endif
+  q = fma(q, r, c.k[1]);
+  const double Tr = Tj * r;
+  m = n >> CHI_EXP_BITS;
+  return fma(Tr, q, Tj);
+}
+// y < -1022 (result below 2^-1042): negative doubles order like unsigned ints on the high word.
+// CHI_EXP_U: one unsigned compare -- everything at or beyond the threshold, -inf included, has a high
+// word >= 0xC08FF001, positive numbers and the canonical (positive) NaN of an arithmetic result lie below
+// it; the two-sided form also lets NaNs with the sign bit set through.
+#ifndef CHI_EXP_U
+#define CHI_EXP_U 1  // measured: fused kernel 1.480 -> 1.471 ms at configs[1] (profiles/r2_exp_variants.txt)
+#endif
+__device__ __forceinline__ bool chi_exp2_underflow(int hi) {
+#if CHI_EXP_U
+  return (unsigned)hi >= 0xC08FF001u;
+#else
+  return (unsigned)(hi - 0xC08FF001) <= (0xFFF00000u - 0xC08FF001u);
+#endif
 }
 
 // 2^y
@@ -134,21 +197,12 @@ __device__ __forceinline__ double chi_exp2(double y, const ExpT& c) {
   const double t = y + c.k[0];
   const double nf = t - c.k[0];
   const double r = y - nf;
-  const int n = __double2loint(t);
-  unsigned addr;
-  asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(n & (CHI_EXP_TABLE - 1)), "r"(c.T));
-  double Tj;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(Tj) : "r"(addr));
-  double q = fma(c.k[3], r, c.k[2]);
-  q = fma(q, r, c.k[1]);
-  const double Tr = Tj * r;
-  const double p = fma(Tr, q, Tj);
+  int m;
+  const double p = chi_exp2_core(__double2loint(t), r, c, m);
   int ph;
-  asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(ph) : "r"(n >> 10), "r"(__double2hiint(p)));
-  // -1022 = 0xC08FF00000000000; negative doubles order like unsigned ints on the high word; the
-  // range stops at -inf (0xFFF00000) so that NaNs still propagate through r and p
-  const bool underflow = (unsigned)(hi - 0xC08FF001) <= (0xFFF00000u - 0xC08FF001u);
-  ph = underflow ? 0 : ph;
+  asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(ph) : "r"(m), "r"(__double2hiint(p)));
+  // the range stops at -inf (0xFFF00000) so that NaNs still propagate through r and p
+  ph = chi_exp2_underflow(hi) ? 0 : ph;
   double out = __hiloint2double(ph, __double2loint(p));
   if (OVERFLOW) {
     // y >= 1024 (0x4090000000000000) up to and including +inf gives +inf
@@ -167,19 +221,11 @@ __device__ __forceinline__ double chi_exp2_prod(double a, double b, const ExpT& 
   const double nf = t - c.k[0];
   const double r = fma(a, b, -nf);
   const int hi = __double2hiint(nf);
-  const int n = __double2loint(t);
-  unsigned addr;
-  asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(n & (CHI_EXP_TABLE - 1)), "r"(c.T));
-  double Tj;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(Tj) : "r"(addr));
-  double q = fma(c.k[3], r, c.k[2]);
-  q = fma(q, r, c.k[1]);
-  const double Tr = Tj * r;
-  const double p = fma(Tr, q, Tj);
+  int m;
+  const double p = chi_exp2_core(__double2loint(t), r, c, m);
   int ph;
-  asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(ph) : "r"(n >> 10), "r"(__double2hiint(p)));
-  const bool underflow = (unsigned)(hi - 0xC08FF001) <= (0xFFF00000u - 0xC08FF001u);
-  ph = underflow ? 0 : ph;
+  asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(ph) : "r"(m), "r"(__double2hiint(p)));
+  ph = chi_exp2_underflow(hi) ? 0 : ph;
   double out = __hiloint2double(ph, __double2loint(p));
   if (OVERFLOW) {
     const bool overflow = (unsigned)(hi - 0x40900000) <= (0x7FF00000u - 0x40900000u);

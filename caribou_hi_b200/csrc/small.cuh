@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(
   const int nbe = a.nb_e, nba = a.nb_a;
 
   if (tid == 0) { s_cfg = cfg; s_rm = a.rm; }
-  for (int i = tid; i < CHI_EXP_TABLE; i += CHI_SM_THREADS) s_T[i] = g_exp2_table[i];
+  for (int i = tid; i < CHI_EXP_TABLE; i += CHI_SM_THREADS) s_T[i] = g_exp2_table[CHI_EXP_REPL ? (i >> 4) << 3 : i];
   // null clouds pad the lane groups: tau = 0, f = 0
   for (int i = tid; i < NP * CHI_SM_CCS; i += CHI_SM_THREADS) {
     const int k = i % CHI_SM_CCS;
