@@ -271,7 +271,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from caribou_hi_b200 import Engine, PinnedArray
+    from caribou_hi_b200 import Engine, PinnedArray, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -285,6 +285,9 @@ def run_b200(args):
     N = N_CLOUDS
 
     eng = Engine(KIND, N, device=local, prior_amplitude=1.0e21)
+    # the library's own NCCL communicator (chi_comm_init); torch.distributed only ships its 128-byte id,
+    # provides the barriers around the timed region and the max-over-ranks of the timings
+    sharding.init_engine_comm(eng)
     thetas = build_inputs(eng, draws, rank, N_SETS)
     dev = torch.device("cuda", local)
     th_d = [torch.from_numpy(t).to(dev) for t in thetas]
@@ -295,12 +298,15 @@ def run_b200(args):
     gce_d = torch.empty((draws, 1), dtype=torch.float64, device=dev)
     gca_d = torch.empty((draws, 1), dtype=torch.float64, device=dev)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
-    gathered = torch.empty((world, 1 + 10 * N), dtype=torch.float64, device=dev) if world > 1 else None
+    width = 10 * N
+    sums_d = [torch.empty(width + 2, dtype=torch.float64, device=dev) for _ in range(N_SETS)]
+    gathered = torch.empty((world, width + 2), dtype=torch.float64, device=dev) if world > 1 else None
     torch.cuda.synchronize()
 
-    # the exchange of step i runs on its own stream next to the kernels of step i+1
-    side = torch.cuda.Stream(device=dev) if world > 1 else None
-    ev_done = [torch.cuda.Event() for _ in range(N_SETS)]   # kernels of buffer set k finished
+    # the exchange of step i -- the shard's sums of logp and gradient (chi_shard_sums_dev) and their
+    # all-gather over the ranks (chi_allgather_dev: NCCL) -- runs on the library's communication
+    # stream next to the kernels of step i+1
+    side = torch.cuda.ExternalStream(eng.comm_stream, device=dev) if world > 1 else None
     ev_read = [torch.cuda.Event() for _ in range(N_SETS)]   # exchange has read buffer set k
     read_pending = [False] * N_SETS
 
@@ -312,18 +318,14 @@ def run_b200(args):
         eng.logp_grad_dev(draws, th_d[k], lp_d[k], gr_d[k], coeff_e=ce_d, coeff_a=ca_d, gcoeff_e=gce_d, gcoeff_a=gca_d)
         if world > 1 and exchange:
             # the only collective of the path: gather per-shard logp and gradient sums
-            ev_done[k].record(stream)
-            with torch.cuda.stream(side):
-                side.wait_event(ev_done[k])
-                summary = torch.cat([torch.nan_to_num(lp_d[k]).sum().reshape(1),
-                                     torch.nan_to_num(gr_d[k]).sum(dim=0).reshape(-1)])
-                dist.all_gather_into_tensor(gathered, summary)
-                ev_read[k].record(side)
+            eng.shard_sums_dev(draws, width, lp_d[k], gr_d[k], sums_d[k])
+            eng.allgather_dev(sums_d[k], gathered, width + 2)
+            ev_read[k].record(side)
             read_pending[k] = True
 
     def join_side():
         if side is not None:
-            stream.wait_stream(side)  # the timed region ends after the last exchange
+            eng.comm_join()  # the timed region ends after the last exchange
 
     def barrier():
         eng.synchronize()
@@ -456,7 +458,7 @@ def run_b200(args):
             "config": {"workload": workload_name(draws), "units_per_step_per_gpu": units_step,
                        "l2": f"inputs/outputs rotated over {N_SETS} buffer sets ({N_SETS * 65} MB > 126 MB L2)",
                        "parallelism": f"draws sharded over {world} GPU(s), one process per GPU"
-                                      + ("; per-step NCCL all_gather of per-shard logp/grad sums on a side stream, overlapping the next step" if world > 1 else "")},
+                                      + ("; per step the shard's logp/gradient sums (chi_shard_sums_dev) are all-gathered by the library's own NCCL communicator (chi_allgather_dev) on its communication stream, next to the following step's kernels" if world > 1 else "")},
             "clocks": clocks,
             "e2e": {"value": world * units_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,

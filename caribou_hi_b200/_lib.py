@@ -18,6 +18,7 @@ CHI_NSLOT = 10
 CHI_NDET = 20
 CHI_MAX_CLOUDS = 16
 CHI_MAX_BASELINE = 8
+CHI_COMM_ID_BYTES = 128
 
 MODEL_PHYSICS = 0
 MODEL_ABSORPTION = 1
@@ -149,6 +150,17 @@ SYMBOLS = {
     "chi_stage_ms": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float)]),
     "chi_launch_count": (C.c_int64, [_H]),
     "chi_set_option": (C.c_int, [_H, C.c_int, C.c_int64]),
+    "chi_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "chi_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
+    "chi_comm_destroy": (C.c_int, [_H]),
+    "chi_comm_rank": (C.c_int, [_H]),
+    "chi_comm_size": (C.c_int, [_H]),
+    "chi_shard_sums_dev": (C.c_int, [_H, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chi_allgather_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64]),
+    "chi_allreduce_sum_dev": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "chi_comm_join": (C.c_int, [_H]),
+    "chi_comm_synchronize": (C.c_int, [_H]),
+    "chi_comm_stream": (C.c_void_p, [_H]),
     "chi_microbench_fp64": (C.c_int, [_H, C.POINTER(C.c_double)]),
 }
 

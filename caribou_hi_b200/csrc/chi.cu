@@ -19,6 +19,7 @@
 #include "launch.cuh"
 #include "moments_ea.cuh"
 #include "nuts.cuh"
+#include "comm.cuh"
 #include "nuts_warp.cuh"
 
 #define CHI_STAGE_RING 64
@@ -153,6 +154,12 @@ struct chi_handle {
   int64_t call_first_stage = 0;  // stage_calls at the start of the current model-level call
   int64_t launches = 0;
   int64_t opt[CHI_OPT_COUNT] = {};  // chi_set_option
+  // multi-GPU (comm.cuh): communicator, its stream, and the workspace of k_shard_sums
+  NcclComm comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_comm_in = nullptr, ev_comm_out = nullptr;
+  Buf sums_partial, sums_counter;
   std::string err;
 };
 
@@ -920,9 +927,20 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
   return CHI_OK;
 }
 
+int chi_comm_destroy(chi_handle* h);
+
 void chi_destroy(chi_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  chi_comm_destroy(h);
+  if (h->comm_stream) {
+    cudaStreamSynchronize(h->comm_stream);
+    cudaStreamDestroy(h->comm_stream);
+    cudaEventDestroy(h->ev_comm_in);
+    cudaEventDestroy(h->ev_comm_out);
+  }
+  h->sums_partial.release();
+  h->sums_counter.release();
   for (Lane& L : h->lanes) {
     if (L.st) cudaStreamSynchronize(L.st);
     if (L.hi) cudaStreamSynchronize(L.hi);
@@ -1786,6 +1804,161 @@ int chi_stage_ms(chi_handle* h, int n, float* ms_out) {
 }
 
 int64_t chi_launch_count(const chi_handle* h) { return h ? h->launches : 0; }
+
+// ---- multi-GPU: shard sums and the NCCL collectives that gather them (comm.cuh) --------------------
+static NcclApi g_nccl;
+
+static int nccl_fail(chi_handle* h, const char* what, int rc) {
+  return fail(h, CHI_ECUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error"));
+}
+
+int chi_comm_unique_id(void* id_out) {
+  if (!id_out) return CHI_EINVAL;
+  const char* why = "";
+  if (!g_nccl.load(&why)) { g_create_error = why; return CHI_ESTATE; }
+  NcclId id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc); return CHI_ECUDA; }
+  memcpy(id_out, &id, sizeof(id));
+  return CHI_OK;
+}
+
+int chi_comm_init(chi_handle* h, const void* id, int rank, int n_ranks) {
+  if (!h) return CHI_EINVAL;
+  if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(h, CHI_EINVAL, "chi_comm_init: bad rank / n_ranks / id");
+  if (h->comm) return fail(h, CHI_ESTATE, "chi_comm_init: the handle already has a communicator");
+  const char* why = "";
+  if (!g_nccl.load(&why)) return fail(h, CHI_ESTATE, why);
+  CK(cudaSetDevice(h->device));
+  NcclId nid;
+  memcpy(&nid, id, sizeof(nid));
+  const int rc = g_nccl.CommInitRank(&h->comm, n_ranks, nid, rank);
+  if (rc) { h->comm = nullptr; return nccl_fail(h, "ncclCommInitRank", rc); }
+  h->comm_rank = rank;
+  h->comm_size = n_ranks;
+  return CHI_OK;
+}
+
+int chi_comm_destroy(chi_handle* h) {
+  if (!h) return CHI_EINVAL;
+  if (h->comm) {
+    cudaSetDevice(h->device);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  h->comm_rank = 0;
+  h->comm_size = 1;
+  return CHI_OK;
+}
+
+int chi_comm_rank(const chi_handle* h) { return h ? h->comm_rank : 0; }
+int chi_comm_size(const chi_handle* h) { return h ? h->comm_size : 1; }
+
+// stream the shard sums and the collectives run on: the communication stream once a communicator (or a
+// previous call) created it, else the handle's stream
+static int comm_stream_of(chi_handle* h, cudaStream_t* st) {
+  if (!h->comm_stream) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&h->ev_comm_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_comm_out, cudaEventDisableTiming));
+  }
+  // everything enqueued on the handle's stream so far is visible to the communication stream
+  CK(cudaEventRecord(h->ev_comm_in, h->stream));
+  CK(cudaStreamWaitEvent(h->comm_stream, h->ev_comm_in, 0));
+  *st = h->comm_stream;
+  return CHI_OK;
+}
+
+int chi_shard_sums_dev(chi_handle* h, int64_t B, int32_t width, const double* logp, const double* grad, double* sums_out) {
+  if (!h) return CHI_EINVAL;
+  if (B < 0 || width < 1 || width > CHI_SUMS_MAXW || !logp || !grad || !sums_out)
+    return fail(h, CHI_EINVAL, "chi_shard_sums: bad arguments (1 <= width <= 256)");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st;
+  int rc = comm_stream_of(h, &st);
+  if (rc) return rc;
+  if (B == 0) {
+    CK(cudaMemsetAsync(sums_out, 0, (size_t)(width + 2) * sizeof(double), st));
+    return CHI_OK;
+  }
+  // enough blocks to stream at HBM speed, few enough that the last block's pass over the partials is short
+  const int grid = (int)std::min<int64_t>((B + 63) / 64, (int64_t)h->n_sm * 2);
+  const int per = (int)((B + grid - 1) / grid);
+  const int grid2 = (int)((B + per - 1) / per);
+  CK(h->sums_partial.ensure((size_t)grid2 * (width + 2) * sizeof(double)));
+  if (!h->sums_counter.p) {
+    CK(h->sums_counter.ensure(sizeof(unsigned)));
+    CK(cudaMemsetAsync(h->sums_counter.p, 0, sizeof(unsigned), st));
+  }
+  k_shard_sums<<<grid2, CHI_SUMS_THREADS, 0, st>>>(B, width, per, logp, grad, h->sums_partial.d(),
+                                                   (unsigned*)h->sums_counter.p, sums_out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return CHI_OK;
+}
+
+int chi_allgather_dev(chi_handle* h, const double* send, double* recv, int64_t count) {
+  if (!h) return CHI_EINVAL;
+  if (!send || !recv || count < 1) return fail(h, CHI_EINVAL, "chi_allgather: bad arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st;
+  int rc = comm_stream_of(h, &st);
+  if (rc) return rc;
+  if (!h->comm) {  // one rank: the gather is a copy
+    if (recv != send) CK(cudaMemcpyAsync(recv, send, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return CHI_OK;
+  }
+  rc = g_nccl.AllGather(send, recv, (size_t)count, CHI_NCCL_FLOAT64, h->comm, st);
+  if (rc) return nccl_fail(h, "ncclAllGather", rc);
+  return CHI_OK;
+}
+
+int chi_allreduce_sum_dev(chi_handle* h, double* buf, int64_t count) {
+  if (!h) return CHI_EINVAL;
+  if (!buf || count < 1) return fail(h, CHI_EINVAL, "chi_allreduce_sum: bad arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st;
+  int rc = comm_stream_of(h, &st);
+  if (rc) return rc;
+  if (!h->comm) return CHI_OK;
+  rc = g_nccl.AllReduce(buf, buf, (size_t)count, CHI_NCCL_FLOAT64, CHI_NCCL_SUM, h->comm, st);
+  if (rc) return nccl_fail(h, "ncclAllReduce", rc);
+  return CHI_OK;
+}
+
+// the handle's stream waits for the communication stream (before the caller reuses a buffer a
+// collective still reads, or reads one it writes)
+int chi_comm_join(chi_handle* h) {
+  if (!h) return CHI_EINVAL;
+  if (!h->comm_stream) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->ev_comm_out, h->comm_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_comm_out, 0));
+  return CHI_OK;
+}
+
+// the communication stream (cudaStream_t as void*; created on first use) for callers that order their
+// own work against the collectives with events
+void* chi_comm_stream(chi_handle* h) {
+  if (!h) return nullptr;
+  if (!h->comm_stream) {
+    cudaStream_t st;
+    if (comm_stream_of(h, &st) != CHI_OK) return nullptr;
+  }
+  return (void*)h->comm_stream;
+}
+
+// host-blocking wait for the communication stream
+int chi_comm_synchronize(chi_handle* h) {
+  if (!h) return CHI_EINVAL;
+  if (!h->comm_stream) return CHI_OK;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->comm_stream));
+  return CHI_OK;
+}
 
 int chi_set_option(chi_handle* h, int option, int64_t value) {
   if (!h) return CHI_EINVAL;

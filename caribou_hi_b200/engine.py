@@ -698,6 +698,59 @@ class Engine:
     def launch_count(self):
         return int(self._lib.chi_launch_count(self._h))
 
+    # ---- multi-GPU: the library's own communicator (chi_comm_*, csrc/comm.cuh) -----------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes identifying a new communicator (``chi_comm_unique_id``): rank 0 creates it, the caller
+        ships it to every rank (e.g. ``torch.distributed.broadcast_object_list``), every rank calls
+        :meth:`comm_init`."""
+        lib = _lib.load()
+        buf = C.create_string_buffer(_lib.CHI_COMM_ID_BYTES)
+        rc = lib.chi_comm_unique_id(buf)
+        if rc != 0:
+            raise _lib.ChiError(rc, lib.chi_last_error(None).decode())
+        return bytes(buf.raw)
+
+    def comm_init(self, unique_id, rank, n_ranks):
+        if len(unique_id) != _lib.CHI_COMM_ID_BYTES:
+            raise ValueError("unique_id: expected the 128 bytes of Engine.comm_unique_id()")
+        self._check(self._lib.chi_comm_init(self._h, C.c_char_p(unique_id), int(rank), int(n_ranks)))
+
+    def comm_destroy(self):
+        self._check(self._lib.chi_comm_destroy(self._h))
+
+    @property
+    def comm_size(self):
+        return int(self._lib.chi_comm_size(self._h))
+
+    @property
+    def comm_rank(self):
+        return int(self._lib.chi_comm_rank(self._h))
+
+    def shard_sums_dev(self, B, width, logp, grad, sums):
+        """``sums[0]`` = sum of ``logp`` over the finite draws, ``sums[1:1+width]`` = sum of their gradient
+        rows, ``sums[1+width]`` = number of non-finite draws (``chi_shard_sums_dev``; device tensors)."""
+        p = self._ptr
+        self._check(self._lib.chi_shard_sums_dev(self._h, int(B), int(width), p(logp), p(grad), p(sums)))
+
+    def allgather_dev(self, send, recv, count):
+        p = self._ptr
+        self._check(self._lib.chi_allgather_dev(self._h, p(send), p(recv), int(count)))
+
+    def allreduce_sum_dev(self, buf, count):
+        self._check(self._lib.chi_allreduce_sum_dev(self._h, self._ptr(buf), int(count)))
+
+    @property
+    def comm_stream(self):
+        """The library's communication stream (``cudaStream_t`` as int) for ``torch.cuda.ExternalStream``."""
+        return int(self._lib.chi_comm_stream(self._h) or 0)
+
+    def comm_join(self):
+        self._check(self._lib.chi_comm_join(self._h))
+
+    def comm_synchronize(self):
+        self._check(self._lib.chi_comm_synchronize(self._h))
+
     def set_option(self, name, value):
         """Tuning / test knobs (``chi_set_option``): ``small_path`` 0 by batch size, 1 never, 2 always
         (the one-launch evaluation of small batches); ``small_nl`` clouds per thread of that kernel;

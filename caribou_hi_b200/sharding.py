@@ -2,8 +2,11 @@
 evaluations (draws x chains x sightlines) split contiguously across ranks.
 
 The arithmetic has no exchange step: every draw is independent, so shards never talk to
-each other while computing.  ``torch.distributed`` (NCCL over NVLink on GPUs, gloo on CPU
-in the tests) is used only to *collect* results:
+each other while computing; results are only *collected*.  On GPUs the library owns the NCCL
+communicator and the reductions (``chi_comm_*``, ``chi_shard_sums_dev``, csrc/comm.cuh):
+:func:`init_engine_comm` creates it from the ``torch.distributed`` world (used only to ship the
+128-byte id) and :class:`ShardedEngine` is the device-resident front end.  The functions below it
+are the same logic on ``torch.distributed`` tensors (gloo on CPU in the tests):
 
 * ``gather_rows``      all-gather per-draw ``logp[B_local]`` / ``grad[B_local, ...]`` back
                        into batch order (uneven shards are padded for the collective)
@@ -133,3 +136,68 @@ class ShardedLikelihood:
         packed = reduce_sum(packed).cpu().numpy()
         self.n_bad = int(packed[-1])
         return packed[0], packed[1:-1].reshape(grad.shape[1:])
+
+
+# ---- the library's own communicator (NCCL inside the handle) --------------------------------------
+def init_engine_comm(engine):
+    """Create ``engine``'s NCCL communicator for the current ``torch.distributed`` world: rank 0 makes
+    the id (``chi_comm_unique_id``), the process group ships it, every rank calls ``chi_comm_init``.
+    A world of one needs no communicator (the collectives degenerate to copies)."""
+    ws, rank = world()
+    if ws == 1:
+        return
+    dist = _dist()
+    box = [type(engine).comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    engine.comm_init(box[0], rank, ws)
+
+
+class ShardedEngine:
+    """This rank's shard of a batch on its own GPU, results collected by the library: per-shard sums of
+    logp and gradient (``chi_shard_sums_dev``) gathered or reduced over the ranks with NCCL on the
+    handle's communication stream (``chi_allgather_dev`` / ``chi_allreduce_sum_dev``).  Tensors are
+    ``torch`` CUDA tensors on the engine's device (device memory is all torch is used for)."""
+
+    def __init__(self, engine):
+        import torch
+
+        self.engine = engine
+        self.torch = torch
+        self.device = torch.device("cuda", engine.device)
+        self._buf = {}
+
+    def _tensor(self, key, shape):
+        t = self._buf.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = self.torch.empty(shape, dtype=self.torch.float64, device=self.device)
+            self._buf[key] = t
+        return t
+
+    def shard(self, n_items):
+        """``(start, stop)`` of this rank's contiguous shard of ``n_items``."""
+        return shard_bounds(n_items, self.engine.comm_size, self.engine.comm_rank)
+
+    def sums(self, rows_dev, coeff_e=None, coeff_a=None, sightline=None, reduce=True):
+        """Evaluate the local packed rows ``[B_local, n_rows, N]`` (device) and return, on the host,
+        ``(sum logp, sum grad [n_rows, N], non-finite draws)`` over ALL ranks (``reduce=True``:
+        all-reduce) or the per-rank table ``[n_ranks, 2 + n_rows N]`` (``reduce=False``: all-gather)."""
+        eng = self.engine
+        B, n_rows, N = rows_dev.shape
+        width = n_rows * N
+        lp = self._tensor("lp", (B,))
+        gr = self._tensor("gr", (B, n_rows, N))
+        gce = self._tensor("gce", (B, max(eng.nb_e, 1)))
+        gca = self._tensor("gca", (B, max(eng.nb_a, 1)))
+        eng.logp_grad_rows_dev(B, rows_dev, lp, gr, coeff_e=coeff_e, coeff_a=coeff_a, sightline=sightline,
+                               gcoeff_e=gce if eng.nb_e else None, gcoeff_a=gca if eng.nb_a else None)
+        s = self._tensor("sums", (width + 2,))
+        eng.shard_sums_dev(B, width, lp, gr, s)
+        if reduce:
+            eng.allreduce_sum_dev(s, width + 2)
+            eng.comm_synchronize()
+            h = s.cpu().numpy()
+            return float(h[0]), h[1 : 1 + width].reshape(n_rows, N), int(round(h[1 + width]))
+        table = self._tensor("table", (eng.comm_size, width + 2))
+        eng.allgather_dev(s, table, width + 2)
+        eng.comm_synchronize()
+        return table.cpu().numpy()

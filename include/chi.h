@@ -391,6 +391,39 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
                     double* draws_ca, double* stat_accept, int32_t* stat_depth, int32_t* stat_diverged,
                     double* stat_logp, double* stat_step);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink only to COLLECT ---------------
+ * The path has no exchange step (draws, chains and sightlines are independent: SURVEY 8e; the
+ * reference parallelises over chains with one process each, optimization.ipynb cell 12).  A sharded
+ * job evaluates its shard with the entry points above and then gathers the per-shard sums of logp and
+ * gradient (or rows of per-draw results) with the calls below.  The handle owns the communicator
+ * and a communication stream: a collective waits for what the handle's stream has enqueued so far and
+ * runs next to whatever is enqueued afterwards; chi_comm_join makes the handle's stream wait for it.
+ * NCCL is loaded at run time (libnccl.so.2), so single-GPU use has no dependency on it.
+ *   rank 0: chi_comm_unique_id(id) -> the caller ships the 128 bytes to every rank (any side
+ *   channel: torch.distributed, MPI, a file) -> every rank: chi_comm_init(h, id, rank, n_ranks). */
+#define CHI_COMM_ID_BYTES 128
+int chi_comm_unique_id(void* id_out);
+int chi_comm_init(chi_handle* h, const void* id, int rank, int n_ranks);
+int chi_comm_destroy(chi_handle* h);
+int chi_comm_rank(const chi_handle* h);
+int chi_comm_size(const chi_handle* h);
+/* Sums over the FINITE draws of this shard (device pointers): sums_out[0] = sum logp,
+ * sums_out[1 .. width] = sum over draws of grad[b][0 .. width) (width = n_rows * N of the block the
+ * gradient came in, <= 256), sums_out[1 + width] = number of draws with a non-finite logp (their
+ * gradients are left out too).  Deterministic (fixed summation order).  Runs on the communication
+ * stream behind everything enqueued on the handle's stream. */
+int chi_shard_sums_dev(chi_handle* h, int64_t B, int32_t width, const double* logp, const double* grad,
+                       double* sums_out);
+/* recv[n_ranks][count] <- every rank's send[count] (ncclAllGather); buf[count] <- sum over ranks
+ * (ncclAllReduce).  Device pointers; with one rank / no communicator the gather is a copy. */
+int chi_allgather_dev(chi_handle* h, const double* send, double* recv, int64_t count);
+int chi_allreduce_sum_dev(chi_handle* h, double* buf, int64_t count);
+/* The handle's stream waits for the communication stream / the host waits for it; the stream itself
+ * (cudaStream_t as void*) for callers that order their own work with events. */
+int chi_comm_join(chi_handle* h);
+int chi_comm_synchronize(chi_handle* h);
+void* chi_comm_stream(chi_handle* h);
+
 /* ---- measurement helpers --------------------------------------------------- */
 /* Milliseconds spent in the kernels of the last model-level call on this handle
  * (CUDA events on the handle's stream; synchronises). */

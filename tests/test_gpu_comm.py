@@ -1,0 +1,65 @@
+"""The library's multi-GPU layer (include/chi.h "multi-GPU", csrc/comm.cuh): shard sums on the device and
+the NCCL collectives behind the handle.  The two-rank test needs two GPUs (`gpurun --gpus 2`)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import engine_for, make_case
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_sums_match_numpy_and_skip_nan_draws(cuda_device):
+    import torch
+
+    spec, data, free, baseline = make_case("emission_absorption_physical", 4, 200, 200, 5000, seed=21, shared_axis=True)
+    eng = engine_for(spec, data, 0)
+    rows = eng.pack_rows(free)
+    ce, ca = baseline["baseline_emission_norm"], baseline["baseline_absorption_norm"]
+    lp, gr, _, _ = eng.logp_grad_rows(rows, ce, ca)
+    fin = np.isfinite(lp)
+    assert 0 < (~fin).sum() < lp.size  # the prior of the physical models produces NaN draws, as the reference does
+    dev = torch.device("cuda", 0)
+    lp_d, gr_d = torch.from_numpy(lp).to(dev), torch.from_numpy(gr).to(dev)
+    width = gr.shape[1] * gr.shape[2]
+    out = [torch.zeros(width + 2, dtype=torch.float64, device=dev) for _ in range(2)]
+    for o in out:
+        eng.shard_sums_dev(lp.size, width, lp_d, gr_d, o)
+    eng.comm_synchronize()
+    a, b = out[0].cpu().numpy(), out[1].cpu().numpy()
+    assert np.array_equal(a, b)  # fixed summation order: deterministic
+    assert a[-1] == (~fin).sum()
+    assert abs(a[0] - lp[fin].sum()) <= 1e-13 * abs(lp[fin].sum())
+    ref = gr[fin].sum(axis=0).reshape(-1)
+    assert np.all(np.abs(a[1:-1] - ref) <= 1e-12 * np.abs(ref).max())
+    # one rank, no communicator: the gather is a copy, the reduction the identity
+    rec = torch.zeros_like(out[0])
+    eng.allgather_dev(out[0], rec, width + 2)
+    eng.allreduce_sum_dev(out[1], width + 2)
+    eng.comm_join()
+    eng.synchronize()
+    assert np.array_equal(rec.cpu().numpy(), a) and np.array_equal(out[1].cpu().numpy(), a)
+    assert eng.comm_size == 1 and eng.comm_rank == 0
+    # edge: a shard with no draws
+    eng.shard_sums_dev(0, width, lp_d, gr_d, rec)
+    eng.comm_synchronize()
+    assert not rec.cpu().numpy().any()
+    eng.close()
+
+
+def test_nccl_two_ranks(cuda_device):
+    """Two processes, two GPUs: chi_comm_init from an id shipped over a gloo group, shard sums reduced and
+    gathered with the library's NCCL calls (tests/comm_worker.py)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "tests", "comm_worker.py")]
+    env = dict(os.environ, NCCL_DEBUG="WARN")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0 and "COMM_WORKER_OK 2" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
