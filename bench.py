@@ -425,10 +425,47 @@ def run_b200(args):
     checksum += float(np.nansum(outs[(e2e_steps - 1) % 2]["logp"][:16]))
     t_async = (time.perf_counter() - t0) / e2e_steps
     t_e2e = min(t_sync, t_async)
+    # (c) the same steps for a consumer of TOTALS (what a sharded job gathers): chi_logp_sums_rows_async
+    # uploads the same inputs, computes logp and the full gradient, and downloads logp per draw plus
+    # the shard's gradient sums -- the per-draw gradient stays on the device
+    pin_lp2 = [PinnedArray((draws,)) for _ in range(2)]
+    outs_s = [{"logp": pin_lp2[k].array, "sums": np.empty(2 + rows.size * N)} for k in range(2)]
+    eng.wait(eng.logp_sums_rows_async(pin_th[0].array, ce_h, ca_h, outs_s[1]))  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    prev = None
+    for i in range(e2e_steps):
+        tk = eng.logp_sums_rows_async(pin_th[i % 2].array, ce_h, ca_h, outs_s[i % 2])
+        if prev is not None:
+            eng.wait(prev)
+            checksum += float(outs_s[(i - 1) % 2]["sums"][0])  # the host reads the result
+        prev = tk
+    eng.wait(prev)
+    checksum += float(outs_s[(e2e_steps - 1) % 2]["sums"][0])
+    t_sums = (time.perf_counter() - t0) / e2e_steps
+    # (d) what the host lets through: the copies of (b) alone, every rank at the same time, no kernels
+    h_in = torch.from_numpy(pin_th[0].array)
+    h_out = torch.from_numpy(pin_gr.array)
+    d_tmp = [torch.empty((draws, rows.size, N), dtype=torch.float64, device=dev) for _ in range(2)]
+    cs = [torch.cuda.Stream(device=dev) for _ in range(2)]
+
+    def copies():
+        with torch.cuda.stream(cs[0]):
+            d_tmp[0].copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(cs[1]):
+            h_out.copy_(d_tmp[1], non_blocking=True)
+
+    copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copies()
+    torch.cuda.synchronize()
+    t_copy = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([t_e2e, t_sums, t_copy, t_sync, t_async], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
+        t_e2e, t_sums, t_copy, t_sync, t_async = (float(x) for x in t.tolist())
     h2d = (draws * rows.size * N + 2 * draws) * 8
     d2h = (draws + draws * rows.size * N + 2 * draws) * 8
 
@@ -467,7 +504,18 @@ def run_b200(args):
                              if t_async <= t_sync else
                              "Engine.logp_grad_rows (C ABI chi_logp_grad_rows) with pinned host buffers"),
                     "blocking_call_value": world * units_step / t_sync, "blocking_call_ms_per_step": t_sync * 1e3,
-                    "async_ms_per_step": t_async * 1e3},
+                    "async_ms_per_step": t_async * 1e3,
+                    # the host's ceiling for these bytes: the same uploads and downloads with no kernels at
+                    # all, every rank at once (on the 8-GPU bench host the ranks share ~150 GB/s: 8-11 GB/s
+                    # each way per rank against 55 GB/s for one rank alone, profiles/r2_e2e_diag_n8.txt)
+                    "copies_alone_ms_per_step": t_copy * 1e3, "copies_alone_value": world * units_step / t_copy,
+                    "frac_of_copy_ceiling": min(1.0, t_copy / t_e2e)},
+            # the same steps returning totals: logp per draw + the shard's gradient sums come back, the
+            # per-draw gradient stays on the device (C ABI chi_logp_sums_rows_async)
+            "e2e_logp_and_gradient_sums": {
+                "value": world * units_step / t_sums, "unit": UNIT, "ms_per_step": t_sums * 1e3,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (draws + 2 + rows.size * N) * 8,
+                "path": "Engine.logp_sums_rows_async + wait (C ABI chi_logp_sums_rows_async / chi_wait), two calls in flight"},
             "gpu_launches": launches,
             "stage_ms": {"cloud_map": float(stage[0]), "moments_emission": float(stage[1]),
                          "moments_absorption": float(stage[2]), "epilogue": float(stage[3]),
@@ -489,7 +537,7 @@ def run_b200(args):
                                  "frac": bytes_em / t_em / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
             v, s_step, done, cores = time_c_oracle(4096, 3, 1, min_seconds=10.0)
             result["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                       "sample": f"4096 of the {draws} draws x {done} steps "
@@ -497,32 +545,67 @@ def run_b200(args):
             vt, st_step, dn, ct = time_oracle(256, 2, 1, min_seconds=4.0)
             result["cpu_baseline_torch"] = {"value": vt, "unit": UNIT, "cores": ct, "kind": "port",
                                             "sample": f"256 draws x {dn} steps, torch-CPU fp64 autograd oracle"}
-        if world == 1 and not args.no_extras:
-            try:
-                result["other_configs"] = other_configs(local)
-            except Exception as exc:  # secondary numbers never break the bench line
-                result["other_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
-        print(json.dumps(result))
-    barrier()
+        result["roofline"]["traffic_source"] = "profiles/r1g_ncu_full_summary.txt (ncu --set full, scaled to this launch's draws)" if fused else None
+    else:
+        result = None
     eng.close()
+    # secondary numbers (every BASELINE config, each with its roofline block); never break the bench line.
+    # configs[3] runs on all ranks (sightlines sharded), the others on rank 0 while the rest wait.
+    if not args.no_extras:
+        try:
+            extras = other_configs(local, world, rank, peak if rank == 0 else None)
+        except Exception as exc:
+            extras = {"error": f"{type(exc).__name__}: {exc}"}
+        if rank == 0:
+            result["other_configs"] = extras
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
     if world > 1:
         dist.destroy_process_group()
 
 
-def other_configs(local):
-    """Secondary, device-timed numbers beside the headline (not part of `value`): BASELINE configs[2]
-    shape (64 chains x 8 clouds x 2048+2048 channels, pseudo-Voigt: latency per logp+grad evaluation)
-    and configs[4] per-draw shape (8 clouds x 4096+4096 channels, pseudo-Voigt: spectra only, fp64 and
-    the optional fp32 path, 8000 draws)."""
+def _ess(x):
+    """Effective sample size of draws x[n_draws, n_chains] (Geyer's initial positive sequence on the
+    chain-averaged autocorrelation, as ArviZ / Stan do without the rank-normalisation)."""
+    x = np.asarray(x, dtype=np.float64)
+    n, m = x.shape
+    if n < 8:
+        return float(n * m)
+    xc = x - x.mean(axis=0, keepdims=True)
+    f = np.fft.rfft(xc, n=2 * n, axis=0)
+    acov = np.fft.irfft(f * np.conj(f), axis=0)[:n].real / n
+    w = acov[0].mean()
+    var_plus = w * (n - 1) / n + (x.mean(axis=0).var(ddof=1) if m > 1 else 0.0)
+    rho = 1.0 - (w - acov.mean(axis=1)) / var_plus
+    tau = -1.0
+    for t in range(0, n - 1, 2):
+        pair = rho[t] + rho[t + 1]
+        if pair < 0:
+            break
+        tau += 2.0 * pair
+    return float(n * m / max(tau, 1.0 / np.log10(max(n * m, 10))))
+
+
+def other_configs(local, world, rank, peak64):
+    """Secondary numbers beside the headline (not part of `value`), one entry per remaining BASELINE
+    config, each with the roofline of its dominant kernel (canonical flops per unit: SURVEY 8d):
+      configs[0]  NUTS on EmissionAbsorptionModel, 2 clouds, ~500 channels, 8 chains (rank 0)
+      configs[2]  64 chains x 8 clouds x 2048+2048 channels, pseudo-Voigt: one logp+grad evaluation (rank 0)
+      configs[3]  survey: 10^4 sightlines x 5 clouds x 1000+1000 channels, 10 draws each; at N > 1 the
+                  sightlines are sharded over the ranks (strong scaling), sums gathered by the library's NCCL
+      configs[4]  8 clouds x 4096+4096 channels, pseudo-Voigt, spectra only, per-GPU shard, fp64 and fp32 (rank 0)"""
     import torch
-    from caribou_hi_b200 import Engine, synthetic
+    import torch.distributed as dist
+    from caribou_hi_b200 import Engine, sharding, synthetic
 
     out = {}
     dev = torch.device("cuda", local)
     kind = "emission_absorption_physical"
 
-    def engine(N, S):
-        e = Engine(kind, N, device=local, lorentzian=True, prior_fwhm_L=1.0, prior_amplitude=1e21)
+    def engine(N, S, lorentzian=True):
+        e = Engine(kind, N, device=local, lorentzian=lorentzian, prior_fwhm_L=1.0 if lorentzian else 0.0, prior_amplitude=1e21)
         v = np.linspace(-100.0, 100.0, S)
         rng = np.random.default_rng(0)
         e.set_spectra(emission=dict(spectral=v, brightness=rng.normal(10, 5, S), noise=0.1, basis=np.full((1, S), 0.1)),
@@ -542,7 +625,56 @@ def other_configs(local):
         e.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    # configs[2] shape
+    def roof(units_per_s, flops_per_unit, peak, unit="TFLOP/s", **kw):
+        a = units_per_s * flops_per_unit / 1e12
+        return dict({"bound": "fp64", "achieved": a, "peak": peak, "unit": unit, "frac": a / peak if peak else None,
+                     "flops_per_unit": flops_per_unit}, **kw)
+
+    # ---- configs[3]: survey, every rank takes part ----
+    N, S, n_sl, per = 5, 1000, 10_000, 10
+    lo, hi = sharding.shard_bounds(n_sl, world, rank)
+    rng = np.random.default_rng(8 + rank)
+    v = np.linspace(-100.0, 100.0, S)
+    e = Engine(kind, N, device=local, prior_amplitude=1e21)
+    e.set_spectra(emission=dict(spectral=v, brightness=rng.normal(10, 5, (hi - lo, S)), noise=0.1),
+                  absorption=dict(spectral=v, brightness=rng.normal(0.3, 0.1, (hi - lo, S)), noise=0.01), n_sightlines=hi - lo)
+    sharding.init_engine_comm(e)
+    B = (hi - lo) * per
+    th = lambda trial: e.deterministics(e.pack(trial))["fwhm2_thermal"]
+    theta = torch.from_numpy(e.pack(synthetic.draw_free(kind, N, B, rng, thermal_fn=th))).to(dev)
+    sl_d = torch.from_numpy(np.repeat(np.arange(hi - lo, dtype=np.int32), per)).to(dev)
+    lp = torch.empty(B, dtype=torch.float64, device=dev)
+    gr = torch.empty_like(theta)
+    sums = torch.empty(10 * N + 2, dtype=torch.float64, device=dev)
+    table = torch.empty((world, 10 * N + 2), dtype=torch.float64, device=dev)
+
+    def sweep():
+        e.logp_grad_dev(B, theta, lp, gr, sightline=sl_d)
+        if world > 1:
+            e.shard_sums_dev(B, 10 * N, lp, gr, sums)
+            e.allgather_dev(sums, table, 10 * N + 2)
+            e.comm_join()
+
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([timed(e, sweep, 20)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    units = n_sl * per * N * 2 * S
+    if rank == 0:
+        bytes_spectra = n_sl * ((S + 31) // 32) * 8 * 32 * 8  # packed planes of both datasets, read once per sweep
+        out["configs[3]: survey, 10^4 sightlines x 5 clouds x 1000+1000 channels x 10 draws, logp+grad"] = {
+            "ms_per_sweep": ms, "units_per_s": units / (ms * 1e-3), "n_gpus": world,
+            "scaling": "strong (sightlines sharded over the ranks; per-sweep NCCL all-gather of the shard sums by the library)",
+            "roofline": roof(units / (ms * 1e-3), 22.0, (peak64 or 0) * world,
+                             kernel="k_moments_ea<5,false,true,STAGED> (bulk-async staged channels)",
+                             hbm_gb_s=bytes_spectra / (ms * 1e-3) / 1e9)}
+    e.close()
+    if rank != 0:
+        return out
+
+    # ---- configs[2]: latency of one evaluation at 64 chains ----
     N, S, B = 8, 2048, 64
     e, rng = engine(N, S)
     th = lambda trial: e.deterministics(e.pack(trial))["fwhm2_thermal"]
@@ -550,11 +682,39 @@ def other_configs(local):
     lp = torch.empty(B, dtype=torch.float64, device=dev); gr = torch.empty((B, 10, N), dtype=torch.float64, device=dev)
     ce = torch.zeros((B, 1), dtype=torch.float64, device=dev); ca = torch.zeros_like(ce)
     ge = torch.empty_like(ce); ga = torch.empty_like(ce)
-    ms = timed(e, lambda: e.logp_grad_dev(B, theta, lp, gr, coeff_e=ce, coeff_a=ca, gcoeff_e=ge, gcoeff_a=ga), 200)
-    out["configs[2] shape: 64 chains x 8 clouds x 2048+2048 channels, pseudo-Voigt, logp+grad"] = {
-        "us_per_evaluation": ms * 1e3, "units_per_s": B * N * 2 * S / (ms * 1e-3)}
+    call = lambda: e.logp_grad_dev(B, theta, lp, gr, coeff_e=ce, coeff_a=ca, gcoeff_e=ge, gcoeff_a=ga)
+    res = {}
+    stream = torch.cuda.ExternalStream(e.stream, device=dev)
+    for label, path in (("pipeline", 1), ("one_launch", 2)):
+        e.set_option("small_path", path)
+        host_ms = timed(e, call, 200)
+        # replayed from a CUDA graph, as the sampler replays its ticks: no host launch cost
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for _ in range(20):
+                call()
+        with torch.cuda.stream(stream):
+            g.replay()
+            e.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(10):
+                g.replay()
+            e1.record(stream)
+        e.synchronize()
+        res[label] = {"us_host_loop": host_ms * 1e3, "us_in_graph": e0.elapsed_time(e1) / 200 * 1e3}
+        del g
+    e.set_option("small_path", 0)
+    best = min(r["us_in_graph"] for r in res.values())
+    units = B * N * 2 * S
+    out["configs[2]: 64 chains x 8 clouds x 2048+2048 channels, pseudo-Voigt, logp+grad"] = {
+        "us_per_evaluation": best, "units_per_s": units / (best * 1e-6),
+        "how": "device time of one evaluation replayed from a CUDA graph (what a sampler tick pays); us_host_loop = "
+               "one Python call per evaluation, bound by the host's launch cost",
+        "paths": res, "roofline": roof(units / (best * 1e-6), 33.0, peak64, kernel="k_moments_ea<8,true> / k_eval_small<2,true>")}
     e.close()
-    # configs[4] per-draw shape
+
+    # ---- configs[4]: spectra only, per-GPU shape ----
     N, S, B = 8, 4096, 8000
     e, rng = engine(N, S)
     th = lambda trial: e.deterministics(e.pack(trial))["fwhm2_thermal"]
@@ -566,10 +726,67 @@ def other_configs(local):
     ok = torch.isfinite(m64[0]).all(dim=1)
     err = float(((m32[0][ok].double() - m64[0][ok]).abs() / m64[0][ok].abs().amax(dim=1, keepdim=True)).max())
     units = B * N * 2 * S
-    out["configs[4] shape: 8000 draws x 8 clouds x 4096+4096 channels, pseudo-Voigt, spectra only"] = {
+    peak32, peak_sfu = e.microbench_fp32()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    pairs32 = B * N * S / (t32 * 1e-3)
+    out["configs[4]: 8000 draws x 8 clouds x 4096+4096 channels, pseudo-Voigt, spectra only (per-GPU shard)"] = {
         "fp64_units_per_s": units / (t64 * 1e-3), "fp32_units_per_s": units / (t32 * 1e-3),
-        "fp32_worst_error_over_peak_vs_fp64": err}
+        "fp32_worst_error_over_peak_vs_fp64": err,
+        "roofline_fp64": roof(units / (t64 * 1e-3), 13.5, peak64, kernel="k_spectra_ea_t<8,true>",
+                              hbm={"achieved": B * 2 * S * 8 / (t64 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                   "frac": B * 2 * S * 8 / (t64 * 1e-3) / 1e9 / hbm}),
+        "roofline_fp32": {"kernel": "k_spectra32_t<8,true,2>", "bound": "sfu",
+                          "achieved": 3.0 * pairs32 / 1e12, "peak": peak_sfu, "unit": "1e12 MUFU/s", "frac": 3.0 * pairs32 / 1e12 / peak_sfu,
+                          "mufu_per_channel_pair": 3.0,
+                          "fp32_fma": {"achieved": 23.0 * pairs32 / 1e12, "peak": peak32, "unit": "TFLOP/s", "frac": 23.0 * pairs32 / 1e12 / peak32},
+                          "hbm": {"achieved": B * 2 * S * 4 / (t32 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "frac": B * 2 * S * 4 / (t32 * 1e-3) / 1e9 / hbm},
+                          "peak_source": "own microbenchmarks chi_microbench_fp32 (FFMA chains, MUFU.EX2 chains)"}}
     e.close()
+
+    # ---- configs[0]: the sampler on the reference's own tutorial shape ----
+    from caribou_hi_b200 import EmissionAbsorptionModel, SpecData
+
+    rng = np.random.default_rng(1)
+    S_e, S_a, chains, tune, draws = 334, 166, 8, 300, 300
+    ve, va = np.linspace(-60, 60, S_e), np.linspace(-30, 30, S_a)
+    sim = EmissionAbsorptionModel({"emission": SpecData(ve, np.zeros(S_e), 0.1), "absorption": SpecData(va, np.zeros(S_a), 0.01)},
+                                  2, baseline_degree=0)
+    sim.add_priors(); sim.add_likelihood()
+    truth = sim.sample_prior(1, np.random.default_rng(7))
+    for _ in range(20):
+        mu = sim.predict(truth)
+        if all(np.all(np.isfinite(m)) for m in mu.values()):
+            break
+        truth = sim.sample_prior(1, rng)
+    data = {"emission": SpecData(ve, mu["emission"][0] + 0.1 * rng.standard_normal(S_e), 0.1),
+            "absorption": SpecData(va, mu["absorption"][0] + 0.01 * rng.standard_normal(S_a), 0.01)}
+    model = EmissionAbsorptionModel(data, 2, baseline_degree=0)
+    model.add_priors(); model.add_likelihood()
+    t0 = time.perf_counter()
+    post, stats = model.sample(draws=draws, tune=tune, chains=chains, seed=2, init_point=truth, jitter=0.05)
+    dt = time.perf_counter() - t0
+    leaps = float((2.0 ** stats["depth"]).sum())  # upper bound on the leapfrog steps of the kept draws
+    ess = None
+    if "velocity_norm" in post:
+        # [chains, draws, clouds]; clouds are exchangeable: the sorted velocities are label-invariant
+        vs = np.sort(np.asarray(post["velocity_norm"]).transpose(1, 0, 2), axis=-1)
+        ess = min(_ess(vs[:, :, k]) for k in range(vs.shape[-1]))
+    units_eval = chains * 2 * (S_e + S_a)
+    frac_kept = draws / float(tune + draws)
+    out["configs[0]: EmissionAbsorptionModel, 2 clouds, 334+166 channels, NUTS, 8 chains x (300 tune + 300 draws)"] = {
+        "iterations_per_s": (tune + draws) / dt, "chain_iterations_per_s": chains * (tune + draws) / dt,
+        "mean_tree_depth": float(stats["depth"].mean()), "mean_accept": float(stats["accept"].mean()),
+        "divergent_fraction": float(stats["diverging"].mean()), "seconds": dt,
+        "ess_per_s_min_over_sorted_velocity": (ess / (dt * frac_kept)) if ess else None,
+        "reference_figure": "optimization.ipynb cell 12: 16000 chain-iterations in 28 s = 571 chain-iterations/s (n_cloud = 2, 8 processes, CPU)",
+        "roofline": roof(leaps / (dt * frac_kept) * units_eval / chains, 22.0, peak64,
+                         note="latency-bound by construction: one tick = the dependent chain leapfrog -> map -> channels -> contraction of 8 chains")}
     return out
 
 

@@ -128,6 +128,9 @@ SYMBOLS = {
     "chi_logp_grad_rows_async": (C.c_int, [_H, C.c_int64, C.c_int32, _ip, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp,
                                            C.POINTER(C.c_int64)]),
     "chi_wait": (C.c_int, [_H, C.c_int64]),
+    "chi_logp_sums_rows": (C.c_int, [_H, C.c_int64, C.c_int32, _ip, _dp, _dp, _dp, _ip, _dp, _dp]),
+    "chi_logp_sums_rows_async": (C.c_int, [_H, C.c_int64, C.c_int32, _ip, _dp, _dp, _dp, _ip, _dp, _dp,
+                                           C.POINTER(C.c_int64)]),
     "chi_stage_count": (C.c_int64, [_H]),
     "chi_spectra": (C.c_int, [_H, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
     "chi_spectra_dev": (C.c_int, [_H, C.c_int64] + [C.c_void_p] * 5),
@@ -162,6 +165,7 @@ SYMBOLS = {
     "chi_comm_synchronize": (C.c_int, [_H]),
     "chi_comm_stream": (C.c_void_p, [_H]),
     "chi_microbench_fp64": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "chi_microbench_fp32": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -3,6 +3,8 @@
 // host<->device copies.  There is no CPU compute path in this file.
 #include <cuda_runtime.h>
 #include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <cctype>
 #include <cstring>
 #include <math.h>
@@ -77,6 +79,7 @@ static RowMap identity_rows() {
 }
 
 #define CHI_TICKETS 8
+#define CHI_SUMS_MAXPIECES 64
 
 struct DevDataset {
   int S = 0, nb = 0;
@@ -99,6 +102,7 @@ struct Lane {
   cudaStream_t jac = nullptr;
   cudaEvent_t ev_jac = nullptr;
   Buf jacbuf;
+  Buf sums_partial, sums_counter, sums_out;  // per-piece shard sums of the host "sums" entry points
   Buf cnt;            // small batches: blocks-done counter per draw (k_eval_small), zero between launches
   size_t cnt_zeroed = 0;
   // pipelined host path: the epilogue and the downloads of a piece run on a high-priority stream, so
@@ -112,7 +116,7 @@ struct Lane {
   Buf w_theta, w_ce, w_ca, w_sl, w_logp, w_grad, w_gce, w_gca;    // staging of the host entry points
   void release() {
     cnt_zeroed = 0;
-    Buf* bufs[] = {&cc, &mom_e, &mom_a, &xcon, &prior, &jacbuf, &cnt, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
+    Buf* bufs[] = {&cc, &mom_e, &mom_a, &xcon, &prior, &jacbuf, &cnt, &sums_partial, &sums_counter, &sums_out, &w_theta, &w_ce, &w_ca, &w_sl, &w_logp, &w_grad, &w_gce, &w_gca};
     for (Buf* b : bufs) b->release();
   }
 };
@@ -160,6 +164,10 @@ struct chi_handle {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_comm_in = nullptr, ev_comm_out = nullptr;
   Buf sums_partial, sums_counter;
+  // host "sums" entry points: per-piece sums land in pinned staging; the host adds them in piece order
+  // when the call (or its ticket) completes
+  double* sums_stage = nullptr;  // [CHI_TICKETS + 1][CHI_SUMS_MAXPIECES][CHI_SUMS_MAXW + 2], pinned
+  struct PendingSums { double* out = nullptr; int pieces = 0, width = 0; } pending[CHI_TICKETS + 1];
   std::string err;
 };
 
@@ -941,6 +949,7 @@ void chi_destroy(chi_handle* h) {
   }
   h->sums_partial.release();
   h->sums_counter.release();
+  if (h->sums_stage) cudaFreeHost(h->sums_stage);
   for (Lane& L : h->lanes) {
     if (L.st) cudaStreamSynchronize(L.st);
     if (L.hi) cudaStreamSynchronize(L.hi);
@@ -974,6 +983,8 @@ void chi_destroy(chi_handle* h) {
 
 void* chi_stream(chi_handle* h) { return h ? (void*)h->stream : nullptr; }
 
+static void finish_pending_sums(chi_handle* h, int slot);
+
 int chi_synchronize(chi_handle* h) {
   if (!h) return CHI_EINVAL;
   CK(cudaSetDevice(h->device));
@@ -982,6 +993,8 @@ int chi_synchronize(chi_handle* h) {
     if (L.hi) CK(cudaStreamSynchronize(L.hi));
     L.tail_pending = false;
   }
+  if (h->sums_stage)
+    for (int i = 0; i <= CHI_TICKETS; ++i) finish_pending_sums(h, i);
   return CHI_OK;
 }
 
@@ -994,6 +1007,9 @@ int chi_wait(chi_handle* h, int64_t ticket) {
   ticket = std::max<int64_t>(ticket, h->next_ticket - CHI_TICKETS);
   CK(cudaSetDevice(h->device));
   for (cudaEvent_t e : h->tickets[ticket % CHI_TICKETS]) CK(cudaEventSynchronize(e));
+  // calls complete in issue order: every older ticket's sums are in the staging buffer too
+  for (int64_t t = std::max<int64_t>(0, h->next_ticket - CHI_TICKETS); t <= ticket; ++t)
+    finish_pending_sums(h, (int)(t % CHI_TICKETS));
   return CHI_OK;
 }
 
@@ -1027,18 +1043,43 @@ static bool gpu_local_cpus(cpu_set_t* set) {
   return n > 0;
 }
 
-// Page-locked host memory on the NUMA node of the current device: the pages are allocated while
-// the calling thread is confined to the GPU's local CPUs (first-touch placement), so H2D reads do
-// not cross the socket interconnect (measured on the bench box: 23 GB/s remote, 55 GB/s local).
+// NUMA node of the current device (sysfs), -1 when unknown
+static int gpu_numa_node() {
+  int dev = 0;
+  char id[32] = {0};
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(id, sizeof(id), dev) != cudaSuccess) return -1;
+  for (char* c = id; *c; ++c) *c = (char)tolower(*c);
+  const std::string path = std::string("/sys/bus/pci/devices/") + id + "/numa_node";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+// Page-locked host memory on the NUMA node of the current device, so that H2D reads and D2H writes do
+// not cross the socket interconnect (measured on the bench box: 23 GB/s remote, 55 GB/s local).  Two
+// mechanisms, both undone before returning: a PREFERRED memory policy for the GPU's node while the
+// pages are allocated and first touched (works even when the process may not run on that node's CPUs
+// -- a container pinned to the other socket, the case of ranks 4..7 of an 8-GPU job), and, where those
+// CPUs are allowed, running the first touch on them.
 int chi_host_alloc(void** out, size_t bytes) {
   if (!out) return CHI_EINVAL;
   cpu_set_t old_set, local;
+  const bool numa = !getenv("CHI_NO_NUMA");
   const bool have_old = sched_getaffinity(0, sizeof(old_set), &old_set) == 0;
-  const bool moved = have_old && !getenv("CHI_NO_NUMA") && gpu_local_cpus(&local) &&
-                     sched_setaffinity(0, sizeof(local), &local) == 0;
+  const int node = numa ? gpu_numa_node() : -1;
+  bool policy = false;
+  if (node >= 0 && node < 64) {
+    unsigned long mask = 1UL << node;
+    policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65UL) == 0;
+  }
+  const bool moved = have_old && numa && gpu_local_cpus(&local) && sched_setaffinity(0, sizeof(local), &local) == 0;
   cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
-  if (e == cudaSuccess && moved) memset(*out, 0, bytes ? bytes : 1);
+  if (e == cudaSuccess && (moved || policy)) memset(*out, 0, bytes ? bytes : 1);
   if (moved) sched_setaffinity(0, sizeof(old_set), &old_set);
+  if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0UL);
   if (e != cudaSuccess) {
     g_create_error = std::string("chi_host_alloc: ") + cudaGetErrorString(e);
     return CHI_ENOMEM;
@@ -1348,22 +1389,67 @@ int chi_spectra_vjp_dev(chi_handle* h, int64_t B, const double* theta, const dou
 }
 
 // ---- model-level, host pointers ---------------------------------------------------
+// k_shard_sums (comm.cuh) of B draws on stream `st` with the given workspace: out[width + 2] on the device
+static int launch_shard_sums(chi_handle* h, cudaStream_t st, Buf& partial, Buf& counter, int64_t B, int width,
+                             const double* logp, const double* grad, double* out) {
+  if (B == 0) {
+    CK(cudaMemsetAsync(out, 0, (size_t)(width + 2) * sizeof(double), st));
+    return CHI_OK;
+  }
+  // enough blocks to stream at HBM speed, few enough that the last block's pass over the partials is short
+  const int grid = (int)std::min<int64_t>((B + 63) / 64, (int64_t)h->n_sm * 2);
+  const int per = (int)((B + grid - 1) / grid);
+  const int grid2 = (int)((B + per - 1) / per);
+  CK(partial.ensure((size_t)grid2 * (width + 2) * sizeof(double)));
+  if (!counter.p) {
+    CK(counter.ensure(sizeof(unsigned)));
+    CK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), st));
+  }
+  k_shard_sums<<<grid2, CHI_SUMS_THREADS, 0, st>>>(B, width, per, logp, grad, partial.d(), (unsigned*)counter.p, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return CHI_OK;
+}
+
+// adds the per-piece sums of a completed "sums" call in piece order (deterministic) into the caller's array
+static void finish_pending_sums(chi_handle* h, int slot) {
+  chi_handle::PendingSums& ps = h->pending[slot];
+  if (!ps.out) return;
+  const int w2 = ps.width + 2;
+  const double* st = h->sums_stage + (size_t)slot * CHI_SUMS_MAXPIECES * (CHI_SUMS_MAXW + 2);
+  for (int t = 0; t < w2; ++t) {
+    double v = 0.0;
+    for (int k = 0; k < ps.pieces; ++k) v += st[(size_t)k * (CHI_SUMS_MAXW + 2) + t];
+    ps.out[t] = v;
+  }
+  ps.out = nullptr;
+}
+
+// `sums` != null: the per-draw gradient stays on the device; what comes back is logp (if asked for)
+// and sums[2 + n_rows N] = {sum logp, sum of every gradient entry over the finite draws, number of
+// non-finite draws} (chi_logp_sums_rows)
 static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,
                           const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model,
-                          int64_t* ticket_out = nullptr) {
+                          int64_t* ticket_out = nullptr, double* sums = nullptr) {
   int rc = check_model_call(h, B, theta);
   if (rc) return rc;
   if (model) {
     rc = check_prior_call(h);
     if (rc) return rc;
   }
-  if (!logp) return fail(h, CHI_EINVAL, "chi_logp_grad: logp_out is NULL");
+  if (!logp && !sums) return fail(h, CHI_EINVAL, "chi_logp_grad: logp_out is NULL");
   CK(cudaSetDevice(h->device));
   if (sl)
     for (int64_t i = 0; i < B; ++i)
       if (sl[i] < 0 || sl[i] >= h->n_sl) return fail(h, CHI_EINVAL, "chi_logp_grad: sightline index out of range");
   const int N = h->cfg.n_clouds;
   const int n_rows = h->rm.n_rows;
+  const int sums_w = n_rows * N;
+  if (sums) {
+    if (sums_w > CHI_SUMS_MAXW) return fail(h, CHI_EINVAL, "chi_logp_sums: n_rows * n_clouds > 256");
+    if (!h->sums_stage)
+      CK(cudaMallocHost(&h->sums_stage, sizeof(double) * (CHI_TICKETS + 1) * CHI_SUMS_MAXPIECES * (CHI_SUMS_MAXW + 2)));
+  }
   const size_t th_b = (size_t)n_rows * N * sizeof(double);
   const int nbe = h->has_e ? h->e.nb : 0, nba = h->has_a ? h->a.nb : 0;
   // Sub-batches rotate over the lanes: while one lane computes, the next one uploads its
@@ -1445,7 +1531,7 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
       CK(cudaMemcpyAsync(L.w_sl.p, sl + b0, nb * sizeof(int32_t), cudaMemcpyHostToDevice, L.st));
       p.d_sl = (int32_t*)L.w_sl.p;
     }
-    if (grad) { CK(L.w_grad.ensure(nb * th_b)); p.d_grad = L.w_grad.d(); }
+    if (grad || sums) { CK(L.w_grad.ensure(nb * th_b)); p.d_grad = L.w_grad.d(); }
     if (gce && nbe) { CK(L.w_gce.ensure(nb * nbe * sizeof(double))); p.d_gce = L.w_gce.d(); }
     if (gca && nba) { CK(L.w_gca.ensure(nb * nba * sizeof(double))); p.d_gca = L.w_gca.d(); }
     return run_backward(h, L, nb, L.w_theta.d(), p.d_ce, p.d_ca, p.d_sl, nullptr, nullptr, false, L.w_logp.d(),
@@ -1455,7 +1541,14 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
     int64_t b0 = 0;
     for (size_t k = 0; k < sizes.size(); ++k) { P[k].b0 = b0; P[k].nb = sizes[k]; b0 += sizes[k]; }
   }
-  if (sizes.empty()) return CHI_OK;  // B == 0
+  if (sizes.empty()) {  // B == 0
+    if (sums) memset(sums, 0, sizeof(double) * (sums_w + 2));
+    return CHI_OK;
+  }
+  if (sums && sizes.size() > CHI_SUMS_MAXPIECES) return fail(h, CHI_EINVAL, "chi_logp_sums: batch needs too many pieces");
+  // staging slot of this call's per-piece sums: the ticket's for asynchronous calls, the last one otherwise
+  const int sums_slot = ticket_out ? (int)(h->next_ticket % CHI_TICKETS) : CHI_TICKETS;
+  if (sums) finish_pending_sums(h, sums_slot);  // a ticket that left the ring without a wait: complete it now
   struct CallScope {  // h->call_draws is only meaningful while this call issues work
     chi_handle* h;
     ~CallScope() { h->call_draws = 0; }
@@ -1481,14 +1574,26 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
     h->epilogue_on_hi = false;
     if (rc) return rc;
     cudaStream_t ds = use_hi ? L.hi : L.st;
-    CK(cudaMemcpyAsync(logp + b0, L.w_logp.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ds));
-    if (p.d_grad) CK(cudaMemcpyAsync(grad + b0 * n_rows * N, p.d_grad, nb * th_b, cudaMemcpyDeviceToHost, ds));
+    if (logp) CK(cudaMemcpyAsync(logp + b0, L.w_logp.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ds));
+    if (sums) {
+      CK(L.sums_out.ensure(sizeof(double) * (CHI_SUMS_MAXW + 2)));
+      rc = launch_shard_sums(h, ds, L.sums_partial, L.sums_counter, nb, sums_w, L.w_logp.d(), p.d_grad, L.sums_out.d());
+      if (rc) return rc;
+      double* dst = h->sums_stage + ((size_t)sums_slot * CHI_SUMS_MAXPIECES + k) * (CHI_SUMS_MAXW + 2);
+      CK(cudaMemcpyAsync(dst, L.sums_out.p, sizeof(double) * (sums_w + 2), cudaMemcpyDeviceToHost, ds));
+    }
+    if (p.d_grad && grad) CK(cudaMemcpyAsync(grad + b0 * n_rows * N, p.d_grad, nb * th_b, cudaMemcpyDeviceToHost, ds));
     if (p.d_gce) CK(cudaMemcpyAsync(gce + b0 * nbe, p.d_gce, nb * nbe * sizeof(double), cudaMemcpyDeviceToHost, ds));
     if (p.d_gca) CK(cudaMemcpyAsync(gca + b0 * nba, p.d_gca, nb * nba * sizeof(double), cudaMemcpyDeviceToHost, ds));
     if (use_hi) {
       CK(cudaEventRecord(L.ev_tail, L.hi));
       L.tail_pending = true;
     }
+  }
+  if (sums) {
+    h->pending[sums_slot].out = sums;
+    h->pending[sums_slot].pieces = (int)sizes.size();
+    h->pending[sums_slot].width = sums_w;
   }
   if (ticket_out) {
     // asynchronous call: completion = everything queued on the lanes' streams so far
@@ -1508,6 +1613,7 @@ static int host_logp_grad(chi_handle* h, int64_t B, const double* theta, const d
     CK(cudaStreamSynchronize(L.hi));
     L.tail_pending = false;
   }
+  if (sums) finish_pending_sums(h, sums_slot);
   if (getenv("CHI_TIMELINE")) {  // development aid: when each piece's stages ran, relative to the first
     const int first = h->call_first_stage, n = h->stage_calls - first;
     cudaEvent_t t0 = h->ring[first % CHI_STAGE_RING][0];
@@ -1571,6 +1677,31 @@ int chi_logp_grad_rows_async(chi_handle* h, int64_t B, int32_t n_rows, const int
   return rc;
 }
 
+int chi_logp_sums_rows(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* slot_of_row, const double* rows,
+                       const double* ce, const double* ca, const int32_t* sl, double* logp, double* sums) {
+  if (!h) return CHI_EINVAL;
+  if (!sums) return fail(h, CHI_EINVAL, "chi_logp_sums_rows: sums_out is NULL");
+  RowMap m;
+  int rc = make_row_map(h, n_rows, slot_of_row, &m);
+  if (rc) return rc;
+  h->rm = m;
+  rc = host_logp_grad(h, B, rows, ce, ca, sl, logp, nullptr, nullptr, nullptr, false, nullptr, sums);
+  h->rm = identity_rows();
+  return rc;
+}
+int chi_logp_sums_rows_async(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* slot_of_row, const double* rows,
+                             const double* ce, const double* ca, const int32_t* sl, double* logp, double* sums,
+                             int64_t* ticket_out) {
+  if (!h) return CHI_EINVAL;
+  if (!sums || !ticket_out) return fail(h, CHI_EINVAL, "chi_logp_sums_rows_async: sums_out / ticket_out is NULL");
+  RowMap m;
+  int rc = make_row_map(h, n_rows, slot_of_row, &m);
+  if (rc) return rc;
+  h->rm = m;
+  rc = host_logp_grad(h, B, rows, ce, ca, sl, logp, nullptr, nullptr, nullptr, false, ticket_out, sums);
+  h->rm = identity_rows();
+  return rc;
+}
 int chi_logp_grad_rows_dev(chi_handle* h, int64_t B, int32_t n_rows, const int32_t* slot_of_row, const double* rows,
                            const double* ce, const double* ca, const int32_t* sl, double* logp, double* grad_rows,
                            double* gce, double* gca) {
@@ -1880,24 +2011,7 @@ int chi_shard_sums_dev(chi_handle* h, int64_t B, int32_t width, const double* lo
   cudaStream_t st;
   int rc = comm_stream_of(h, &st);
   if (rc) return rc;
-  if (B == 0) {
-    CK(cudaMemsetAsync(sums_out, 0, (size_t)(width + 2) * sizeof(double), st));
-    return CHI_OK;
-  }
-  // enough blocks to stream at HBM speed, few enough that the last block's pass over the partials is short
-  const int grid = (int)std::min<int64_t>((B + 63) / 64, (int64_t)h->n_sm * 2);
-  const int per = (int)((B + grid - 1) / grid);
-  const int grid2 = (int)((B + per - 1) / per);
-  CK(h->sums_partial.ensure((size_t)grid2 * (width + 2) * sizeof(double)));
-  if (!h->sums_counter.p) {
-    CK(h->sums_counter.ensure(sizeof(unsigned)));
-    CK(cudaMemsetAsync(h->sums_counter.p, 0, sizeof(unsigned), st));
-  }
-  k_shard_sums<<<grid2, CHI_SUMS_THREADS, 0, st>>>(B, width, per, logp, grad, h->sums_partial.d(),
-                                                   (unsigned*)h->sums_counter.p, sums_out);
-  h->launches++;
-  CK(cudaGetLastError());
-  return CHI_OK;
+  return launch_shard_sums(h, st, h->sums_partial, h->sums_counter, B, width, logp, grad, sums_out);
 }
 
 int chi_allgather_dev(chi_handle* h, const double* send, double* recv, int64_t count) {
@@ -1991,6 +2105,35 @@ int chi_microbench_fp64(chi_handle* h, double* tflops_out) {
   cudaEventDestroy(b);
   const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
   *tflops_out = flops / (best * 1e-3) / 1e12;
+  return CHI_OK;
+}
+
+// FP32 FMA peak (TFLOP/s) and SFU peak (tera MUFU.EX2 per second) of the handle's device
+int chi_microbench_fp32(chi_handle* h, double* tflops_out, double* tera_sfu_out) {
+  if (!h || !tflops_out || !tera_sfu_out) return CHI_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(h->w_misc[7].ensure(256));
+  const int iters = 4096, blocks = h->n_sm * 8, threads = 256;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  float best[2] = {1e30f, 1e30f};
+  for (int which = 0; which < 2; ++which)
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaEventRecord(a, h->stream));
+      if (which == 0) k_ffma_peak<<<blocks, threads, 0, h->stream>>>((float*)h->w_misc[7].p, iters, 1.0000001f, 1e-9f);
+      else k_sfu_peak<<<blocks, threads, 0, h->stream>>>((float*)h->w_misc[7].p, iters);
+      h->launches++;
+      CK(cudaEventRecord(b, h->stream));
+      CK(cudaEventSynchronize(b));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, a, b));
+      if (rep > 0) best[which] = std::min(best[which], ms);
+    }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *tflops_out = 2.0 * 16.0 * (double)iters * blocks * threads / (best[0] * 1e-3) / 1e12;
+  *tera_sfu_out = 8.0 * (double)iters * blocks * threads / (best[1] * 1e-3) / 1e12;
   return CHI_OK;
 }
 

@@ -822,4 +822,33 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
   if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
 }
 
+// FP32 FMA peak (16 independent chains per thread) and SFU peak (MUFU.EX2, 8 chains): the denominators of
+// the single-precision spectra kernels' roofline
+__global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 12345.678f) out[0] = s;
+}
+__global__ void __launch_bounds__(256) k_sfu_peak(float* out, int iters) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = -1e-3f * (threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 12345.678f) out[0] = s;
+}
+
 }  // namespace chi

@@ -337,6 +337,56 @@ class Engine:
         self._keep = (rows, coeff_e, coeff_a, sl, out)  # the arrays of the newest call stay referenced
         return int(ticket.value)
 
+    def logp_sums_rows(self, rows, coeff_e=None, coeff_a=None, sightline=None, out=None, want_logp=True):
+        """Totals instead of per-draw gradients (C ABI ``chi_logp_sums_rows``): returns ``(logp [B] | None,
+        sums [2 + n_rows N])`` with ``sums = {sum logp, sum of the gradient rows, non-finite draws}`` over
+        the finite draws; :meth:`unpack_sums` splits it.  The per-draw gradient never leaves the device."""
+        N = self.n_clouds
+        slots = self.row_slots
+        rows = _f64(rows)
+        if rows.ndim != 3 or rows.shape[1:] != (slots.size, N):
+            raise ValueError(f"rows: expected [B, {slots.size}, {N}], got {rows.shape}")
+        B = rows.shape[0]
+        ce = self._coeffs(coeff_e, self.nb_e, B, "coeff_e")
+        ca = self._coeffs(coeff_a, self.nb_a, B, "coeff_a")
+        sl = _sightline(sightline, B)
+        logp = _out_f64(out, "logp", (B,)) if want_logp else None
+        sums = _out_f64(out, "sums", (2 + slots.size * N,))
+        self._check(self._lib.chi_logp_sums_rows(self._h, B, int(slots.size), _lib.as_ip(slots), _lib.as_dp(rows),
+                                                 _lib.as_dp(ce), _lib.as_dp(ca), _lib.as_ip(sl), _lib.as_dp(logp),
+                                                 _lib.as_dp(sums)))
+        return logp, sums
+
+    def logp_sums_rows_async(self, rows, coeff_e, coeff_a, out, sightline=None):
+        """Asynchronous :meth:`logp_sums_rows` (``chi_logp_sums_rows_async``): pinned ``rows`` / coefficients,
+        ``out["sums"]`` (any host array) and optionally pinned ``out["logp"]``; the sums are complete after
+        :meth:`wait` on the returned ticket."""
+        N = self.n_clouds
+        slots = self.row_slots
+        if rows.dtype != np.float64 or not rows.flags.c_contiguous or rows.shape[1:] != (slots.size, N):
+            raise ValueError(f"rows: expected a C-contiguous float64 [B, {slots.size}, {N}] array")
+        B = rows.shape[0]
+        for name, a, shape in (("coeff_e", coeff_e, (B, self.nb_e)), ("coeff_a", coeff_a, (B, self.nb_a))):
+            if shape[-1] and (a is None or a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != shape):
+                raise ValueError(f"{name}: expected a C-contiguous float64 array of shape {shape}")
+        sums = _out_f64(out, "sums", (2 + slots.size * N,))
+        logp = out.get("logp")
+        if logp is not None:
+            logp = _out_f64(out, "logp", (B,))
+        sl = _sightline(sightline, B)
+        ticket = C.c_int64(-1)
+        self._check(self._lib.chi_logp_sums_rows_async(
+            self._h, B, int(slots.size), _lib.as_ip(slots), _lib.as_dp(rows), _lib.as_dp(coeff_e if self.nb_e else None),
+            _lib.as_dp(coeff_a if self.nb_a else None), _lib.as_ip(sl), _lib.as_dp(logp), _lib.as_dp(sums), C.byref(ticket)))
+        self._keep = (rows, coeff_e, coeff_a, sl, out, sums)
+        return int(ticket.value)
+
+    def unpack_sums(self, sums):
+        """``sums [2 + n_rows N]`` -> ``(sum logp, dict of summed gradients keyed by RV name, non-finite draws)``."""
+        n_rows = self.row_slots.size
+        g = np.asarray(sums[1:-1]).reshape(1, n_rows, self.n_clouds)
+        return float(sums[0]), {k: v[0] for k, v in self.unpack_rows(g).items()}, int(round(float(sums[-1])))
+
     def stage_count(self):
         """Number of logp / VJP kernel pipelines (cloud map -> moments -> epilogue) issued so far on
         this handle; :meth:`stage_ms` holds the timings of the latest 64."""
@@ -758,6 +808,12 @@ class Engine:
         opts = {"small_path": _lib.OPT_SMALL_PATH, "small_nl": _lib.OPT_SMALL_NL, "small_chunks": _lib.OPT_SMALL_CHUNKS,
                 "small_stamps": _lib.OPT_SMALL_STAMPS}
         self._check(self._lib.chi_set_option(self._h, opts[name], int(value)))
+
+    def microbench_fp32(self):
+        """``(FP32 FMA TFLOP/s, 1e12 MUFU.EX2 per second)`` of this GPU (``chi_microbench_fp32``)."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self._lib.chi_microbench_fp32(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     def microbench_fp64(self):
         v = C.c_double()

@@ -63,3 +63,43 @@ def test_nccl_two_ranks(cuda_device):
     env = dict(os.environ, NCCL_DEBUG="WARN")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0 and "COMM_WORKER_OK 2" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+@pytest.mark.parametrize("B", [37, 20000])
+def test_host_sums_entry_points(cuda_device, B):
+    """chi_logp_sums_rows[_async]: logp per draw + totals of the gradient over the finite draws; the
+    per-draw gradient stays on the device.  Small batch (one piece) and a pipelined one (pieces on three
+    lanes, sums added in piece order)."""
+    from caribou_hi_b200 import PinnedArray
+
+    spec, data, free, baseline = make_case("emission_absorption_physical", 3, 120, 120, B, seed=31, shared_axis=True)
+    eng = engine_for(spec, data, 0)
+    rows = eng.pack_rows(free)
+    ce, ca = baseline["baseline_emission_norm"], baseline["baseline_absorption_norm"]
+    lp, gr, _, _ = eng.logp_grad_rows(rows, ce, ca)
+    fin = np.isfinite(lp)
+    lp2, sums = eng.logp_sums_rows(rows, ce, ca)
+    assert np.array_equal(lp2, lp, equal_nan=True)
+    tot, g, n_bad = eng.unpack_sums(sums)
+    assert n_bad == (~fin).sum()
+    assert abs(tot - lp[fin].sum()) <= 1e-12 * abs(lp[fin].sum())
+    ref = eng.unpack_rows(gr[fin].sum(axis=0, keepdims=True))
+    for k in ref:
+        assert np.all(np.abs(g[k] - ref[k][0]) <= 1e-11 * np.abs(gr[fin].sum(axis=0)).max()), k
+    # the sums alone; twice the same bits (fixed order)
+    none, sums_b = eng.logp_sums_rows(rows, ce, ca, want_logp=False)
+    assert none is None and np.array_equal(sums_b, sums)
+    # asynchronous, two in flight
+    pin = {k: PinnedArray(v.shape) for k, v in (("rows", rows), ("ce", ce), ("ca", ca))}
+    pin["rows"].array[...] = rows; pin["ce"].array[...] = ce; pin["ca"].array[...] = ca
+    outs = [{"logp": PinnedArray((B,)).array, "sums": np.zeros_like(sums)}, {"sums": np.zeros_like(sums)}]
+    t0 = eng.logp_sums_rows_async(pin["rows"].array, pin["ce"].array, pin["ca"].array, outs[0])
+    t1 = eng.logp_sums_rows_async(pin["rows"].array, pin["ce"].array, pin["ca"].array, outs[1])
+    eng.wait(t1)
+    # the asynchronous call cuts the batch into other pieces than the blocking one (DESIGN 2): the same
+    # bits between asynchronous calls, rounding-level agreement with the blocking call
+    assert np.array_equal(outs[0]["sums"], outs[1]["sums"])
+    assert np.all(np.abs(outs[0]["sums"] - sums) <= 1e-12 * np.abs(sums).max())
+    assert np.array_equal(outs[0]["logp"], lp, equal_nan=True)
+    eng.wait(t0)
+    eng.close()
