@@ -175,12 +175,16 @@ __device__ __forceinline__ double chi_exp2_core(int n, double r, const ExpT& c, 
   m = n >> CHI_EXP_BITS;
   return fma(Tr, q, Tj);
 }
-// y < -1022 (result below 2^-1042): negative doubles order like unsigned ints on the high word.
-// CHI_EXP_U: one unsigned compare -- everything at or beyond the threshold, -inf included, has a high
-// word >= 0xC08FF001, positive numbers and the canonical (positive) NaN of an arithmetic result lie below
-// it; the two-sided form also lets NaNs with the sign bit set through.
+// y < -1022 (result below 2^-1042): negative doubles order like unsigned ints on the high word; the
+// range stops at -inf (0xFFF00000) so that NaNs with the sign bit set still propagate.
+// CHI_EXP_U (A/B variant, REJECTED): one unsigned compare, hi >= 0xC08FF001.  0.6 % faster (fused kernel
+// 1.480 -> 1.471 ms at configs[1], profiles/r2_exp_variants.txt) but WRONG: a NaN optical depth reaches
+// here with its sign bit set (the constants are stored negated: -(log2 e * NaN)), the compare takes it for
+// an underflow and exp(-tau) becomes 0 -- a NaN draw of the reference came out as a finite absorption
+// spectrum (caught by tests/graph_worker.py on the reference's own NaN draws; regression test
+// tests/test_gpu_parity.py::test_nan_inputs_propagate).
 #ifndef CHI_EXP_U
-#define CHI_EXP_U 1  // measured: fused kernel 1.480 -> 1.471 ms at configs[1] (profiles/r2_exp_variants.txt)
+#define CHI_EXP_U 0
 #endif
 __device__ __forceinline__ bool chi_exp2_underflow(int hi) {
 #if CHI_EXP_U

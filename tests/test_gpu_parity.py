@@ -545,3 +545,43 @@ def test_logp_only_calls_match_the_gradient_calls(cuda_device, B):
     assert np.array_equal(m_only, m_g, equal_nan=True)
     assert np.isfinite(m_only).sum() > 0.3 * fin.sum()
     eng.close()
+
+
+@pytest.mark.parametrize("shared", [False, True])
+@pytest.mark.parametrize("lorentzian", [False, True])
+def test_nan_inputs_propagate(cuda_device, shared, lorentzian):
+    """A NaN in any likelihood input of any cloud (the reference's prior produces them: depth 0 -> spin
+    temperature NaN) must make both spectra, logp and the whole gradient NaN -- also for a line much narrower
+    than a channel, whose Gaussian underflows to exactly 0 in every channel (NaN * 0 is NaN), and whatever the
+    sign bit of the NaN."""
+    from caribou_hi_b200 import Engine
+
+    v = np.linspace(-30, 30, 64)
+    va = v if shared else np.linspace(-20, 20, 48)
+    eng = Engine("physics", 3, lorentzian=lorentzian, has_emission=True, has_absorption=True)
+    eng.set_spectra(emission=dict(spectral=v, brightness=np.ones(64), noise=0.1),
+                    absorption=dict(spectral=va, brightness=np.full(va.size, 0.2), noise=0.01))
+    base = {"velocity": [1.0, -2.4, -8.0], "fwhm2": [0.0652, 288.0, 200.0], "fwhm_L": [0.3 * lorentzian] * 3,
+            "tau_total": [1.5, 2.5, 0.57], "tspin": [80.0, 432.0, 1513.0], "filling_factor": [1.0, 0.74, 0.63],
+            "absorption_weight": [0.075, 0.8, 0.07]}
+    neg_nan = np.float64(np.nan) * -1.0
+    neg_nan = np.copysign(np.nan, -1.0)
+    for name in ("tau_total", "velocity", "fwhm2", "absorption_weight"):
+        for n in range(3):
+            for bad in (np.nan, neg_nan):
+                inp = {k: np.array([x], dtype=np.float64) for k, x in base.items()}
+                inp[name][0, n] = bad
+                theta = eng.pack(inp)
+                mu_e, mu_a = eng.spectra(theta)
+                assert np.isnan(mu_a).all(), (name, n, "mu_a")
+                if name != "absorption_weight":
+                    assert np.isnan(mu_e).all(), (name, n, "mu_e")
+                for path in (1, 2):
+                    eng.set_option("small_path", path)
+                    lp, g, _, _ = eng.logp_grad(theta)
+                    assert np.isnan(lp).all(), (name, n, path)
+                eng.set_option("small_path", 0)
+                if lorentzian or name != "fwhm2":
+                    mu_e32, mu_a32 = eng.spectra(theta, dtype=np.float32)
+                    assert np.isnan(mu_a32).all(), (name, n, "mu_a f32")
+    eng.close()
