@@ -17,5 +17,6 @@ from .models import (  # noqa: F401  (same export list as caribou_hi/__init__.py
 )
 from .spec_data import SpecData  # noqa: F401
 from .engine import Engine, PinnedArray  # noqa: F401
+from .optimize import Optimize  # noqa: F401
 
 __version__ = "0.1.0"

@@ -88,3 +88,53 @@ def test_committed_graphs_are_what_the_reference_builds():
                          capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert res.stdout.count("same") == 15
+
+
+def test_linker_registrations_numba_and_jax():
+    """caribou_hi_b200.backends: every Op class gets a numba_funcify / jax_funcify registration; the Numba
+    wrapper (objmode call-back into perform) is compiled with the real Numba and run on a CPU stand-in of an
+    Op; the JAX wrapper is run with a minimal stand-in of jax.pure_callback."""
+    out = run("""
+import sys, types, numpy as np
+jax = types.ModuleType('jax')          # jax is not installed: the two names the registration uses
+class ShapeDtypeStruct:
+    def __init__(self, shape, dtype): self.shape, self.dtype = shape, dtype
+def pure_callback(fn, spec, *args):
+    res = fn(*args)
+    assert all(np.shape(r) == s.shape for r, s in zip(res, spec)), ([np.shape(r) for r in res], [s.shape for s in spec])
+    return res
+jax.ShapeDtypeStruct, jax.pure_callback = ShapeDtypeStruct, pure_callback
+sys.modules['jax'] = jax
+import pytensor.tensor as pt
+from pytensor.link.numba.dispatch import numba_funcify
+from pytensor.link.jax.dispatch import jax_funcify
+from caribou_hi_b200 import backends, ops
+assert sorted(backends.register_all()) == ['jax', 'numba']
+for cls in backends.ALL_OPS:
+    assert numba_funcify.dispatch(cls) is not numba_funcify.dispatch(object), cls
+    assert jax_funcify.dispatch(cls) is not jax_funcify.dispatch(object), cls
+# a CPU stand-in with SpinTempOp's / SpinTempGradOp's signatures exercises the generated wrappers
+class CpuSpin(ops.SpinTempOp):
+    def perform(self, node, inputs, output_storage):
+        tk, de, na = inputs
+        output_storage[0][0] = tk * 2.0 + de + na
+class CpuSpinGrad(ops.SpinTempGradOp):
+    def perform(self, node, inputs, output_storage):
+        tk, de, na, g = inputs
+        output_storage[0][0], output_storage[1][0], output_storage[2][0] = 2.0 * g, g, g
+tk, de, na = pt.dvector('tk'), pt.dvector('de'), pt.dvector('na')
+out = CpuSpin()(tk, de, na)
+a, b, c = np.array([1.0, 2.0]), np.array([0.5, 0.5]), np.array([0.1, 0.2])
+f = numba_funcify(CpuSpin(), node=out.owner)
+assert np.allclose(f(a, b, c), a * 2 + b + c)
+fj = jax_funcify(CpuSpin(), node=out.owner)
+assert np.allclose(fj(a, b, c), a * 2 + b + c)
+gnode = CpuSpinGrad().make_node(tk, de, na, pt.dvector('g'))
+fg = numba_funcify(CpuSpinGrad(), node=gnode)
+r = fg(a, b, c, np.ones(2))
+assert len(r) == 3 and np.allclose(r[0], 2.0)
+rj = jax_funcify(CpuSpinGrad(), node=gnode)(a, b, c, np.ones(2))
+assert len(rj) == 3 and np.allclose(rj[1], 1.0)
+print('OK')
+""")
+    assert "OK" in out
