@@ -13,7 +13,7 @@ properties of the path, plus an oracle spot check of a random subset:
 import numpy as np
 import pytest
 
-from helpers import assert_close, make_case, oracle_logp_grad
+from helpers import assert_close, assert_grad_close, make_case, oracle_logp_grad
 from oracle import models_ref as mr
 
 pytestmark = pytest.mark.gpu
@@ -109,10 +109,8 @@ def test_config2_full_size_properties(cuda_device, shared):
     ref_lp, ref_g = oracle_logp_grad(spec, odata, free, {})
     assert_close(lp[pick], ref_lp, what="oracle logp", axis=None)
     got = eng.unpack_grad(grad[pick])
-    names = sorted(got)
     f2 = np.isfinite(ref_lp)
-    assert_close(np.concatenate([got[n][f2] for n in names], axis=1),
-                 np.concatenate([ref_g[n][f2] for n in names], axis=1), what="oracle gradient")
+    assert_grad_close(got, ref_g, f2, case=(spec, odata, free, {}), what="oracle gradient")
     eng.close()
 
 
@@ -206,3 +204,36 @@ def test_config4_survey_full_size(cuda_device):
         assert np.array_equal(g_s, grad[sel], equal_nan=True)
         part.close()
     eng.close()
+
+
+def test_config3_and_config5_shapes_against_the_oracle(cuda_device):
+    """The many-cloud pseudo-Voigt instantiations at the channel counts the BASELINE configs name, against the
+    ORACLE (not a sibling kernel): k_moments_ea<8,true> and k_eval_small<2,true> at 2048+2048 channels
+    (configs[2]) and k_spectra_ea_t<8,true> plus the fp32 spectra at 4096+4096 channels (configs[4])."""
+    from helpers import engine_for
+
+    for S, B in ((2048, 24), (4096, 16)):
+        spec, data, free, baseline = make_case("emission_absorption_physical", 8, S, S, B, seed=4000 + S, lorentzian=True,
+                                               baseline_degree=0, half_width=100.0, shared_axis=True)
+        eng = engine_for(spec, data, 0)
+        theta = eng.pack(free)
+        ce, ca = baseline["baseline_emission_norm"], baseline["baseline_absorption_norm"]
+        ref_mu = mr.predict(spec, data, free, baseline)
+        mu_e, mu_a = eng.spectra(theta, ce, ca)
+        assert_close(mu_e, ref_mu["emission"], what=f"S={S} mu_e")
+        assert_close(mu_a, ref_mu["absorption"], what=f"S={S} mu_a")
+        m32_e, m32_a = eng.spectra(theta, ce, ca, dtype=np.float32)
+        assert_close(m32_e, ref_mu["emission"], rtol=1e-5, what=f"S={S} mu_e fp32")
+        assert_close(m32_a, ref_mu["absorption"], rtol=1e-5, what=f"S={S} mu_a fp32")
+        if S == 2048:
+            ref_lp, ref_g = oracle_logp_grad(spec, data, free, baseline)
+            fin = np.isfinite(ref_lp)
+            assert fin.sum() >= 8
+            for path in (1, 2):
+                eng.set_option("small_path", path)
+                lp, grad, gce, gca = eng.logp_grad(theta, ce, ca)
+                assert_close(lp, ref_lp, what=f"S={S} logp path {path}", axis=None)
+                got = dict(eng.unpack_grad(grad))
+                got["baseline_emission_norm"], got["baseline_absorption_norm"] = gce, gca
+                assert_grad_close(got, ref_g, fin, case=(spec, data, free, baseline), what=f"S={S} gradient path {path}")
+        eng.close()

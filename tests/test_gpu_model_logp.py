@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import assert_close, engine_for, make_case
+from helpers import assert_close, assert_grad_close, engine_for, make_case
 from oracle import models_ref as mr
 from oracle import priors_ref as pr
 
@@ -56,15 +56,15 @@ def _model_case(kind, lorentzian, N):
     assert_close(lp, ref_lp, what=f"{kind} model logp", axis=None)
     fin = np.isfinite(ref_lp)
     assert fin.sum() >= (16 if N <= 3 else 1)
-    got = eng.unpack_grad(grad)
+    got = dict(eng.unpack_grad(grad))
     names = sorted(got)
-    x = [got[n][fin] for n in names]
-    r = [ref_g[n][fin] for n in names]
     if gce is not None:
-        x.append(gce[fin]); r.append(ref_g["baseline_emission_norm"][fin])
+        got["baseline_emission_norm"] = gce
     if gca is not None:
-        x.append(gca[fin]); r.append(ref_g["baseline_absorption_norm"][fin])
-    assert_close(np.concatenate(x, axis=1), np.concatenate(r, axis=1), what=f"{kind} model grad {names}")
+        got["baseline_absorption_norm"] = gca
+    # per RV vector; the 60-digit arbiter covers the likelihood only, so a component that misses the per-RV
+    # bar here (priors and Jacobians included) must still hold 1e-10 of the draw's largest gradient entry
+    assert_grad_close(got, ref_g, fin, what=f"{kind} model grad {names}", whole_rtol=1e-10)
 
     # transforms round-trip and agree with the constrained draws
     theta = eng.transform(ublock, +1)

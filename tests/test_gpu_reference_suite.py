@@ -137,7 +137,7 @@ def test_model_class_logp_matches_oracle(cuda_device):
     """The class-level API (dict of named RVs in, dict of named gradients out) against
     the oracle, including the SpecData baseline normalisation."""
     from caribou_hi_b200 import EmissionAbsorptionPhysicalModel
-    from helpers import assert_close, oracle_logp_grad
+    from helpers import assert_grad_close, assert_close, oracle_logp_grad
     from oracle import models_ref as mr
 
     emission, absorption = _data()
@@ -159,8 +159,7 @@ def test_model_class_logp_matches_oracle(cuda_device):
     fin = np.isfinite(ref_lp)
     names = sorted(grads)
     assert set(names) == set(ref_g)
-    assert_close(np.concatenate([grads[n][fin] for n in names], axis=1),
-                 np.concatenate([ref_g[n][fin] for n in names], axis=1), what=f"model grads {names}")
+    assert_grad_close(grads, ref_g, fin, case=(spec, data, free, base), what=f"model grads {names}")
     pred = model.predict(point)
     ref_mu = mr.predict(spec, data, free, base)
     for key in pred:
