@@ -787,6 +787,17 @@ def other_configs(local, world, rank, peak64):
         "reference_figure": "optimization.ipynb cell 12: 16000 chain-iterations in 28 s = 571 chain-iterations/s (n_cloud = 2, 8 processes, CPU)",
         "roofline": roof(leaps / (dt * frac_kept) * units_eval / chains, 22.0, peak64,
                          note="latency-bound by construction: one tick = the dependent chain leapfrog -> map -> channels -> contraction of 8 chains")}
+    # the same model with more chains: a tick serves every chain's leapfrog step at once, so chains are
+    # almost free until the machine fills -- the device sampler's operating point is hundreds of chains
+    more = {}
+    for c in (64, 512):
+        t0 = time.perf_counter()
+        _, st = model.sample(draws=100, tune=200, chains=c, seed=3, init_point=truth, jitter=0.05)
+        dt_c = time.perf_counter() - t0
+        more[str(c)] = {"iterations_per_s": 300 / dt_c, "chain_iterations_per_s": c * 300 / dt_c,
+                        "mean_tree_depth": float(st["depth"].mean()), "divergent_fraction": float(st["diverging"].mean())}
+    key0 = [k for k in out if k.startswith("configs[0]")][0]
+    out[key0]["more_chains_200_tune_100_draws"] = more
     return out
 
 

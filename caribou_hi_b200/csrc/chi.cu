@@ -2302,8 +2302,13 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     } else {  // one warp per chain; the tick also maps the new evaluation point
       Lane& L0 = h->lanes[0];
       double* tick_cc = use_eval_small(h, B, false) ? nullptr : L0.cc.d();
-      MODEL_SWITCH(h->cfg.model, (k_nuts_tick_w<M><<<(unsigned)((B + 3) / 4), 128, 0, st>>>(s, A, h->map, h->rm,
-                                                                                        tick_cc, L0.xcon.d())));
+      if (h->opt[CHI_OPT_NUTS_TICK] == 1) {  // A/B and regression reference: every phase through global memory
+        MODEL_SWITCH(h->cfg.model, (k_nuts_tick_w<M, false><<<(unsigned)((B + 3) / 4), 128, 0, st>>>(
+                                       s, A, h->map, h->rm, tick_cc, L0.xcon.d())));
+      } else {  // the common tick staged in shared memory (nuts_warp.cuh: nw_leaf_staged)
+        MODEL_SWITCH(h->cfg.model, (k_nuts_tick_w<M, true><<<(unsigned)((B + 3) / 4), 128, 0, st>>>(
+                                       s, A, h->map, h->rm, tick_cc, L0.xcon.d())));
+      }
       CK(cudaEventRecord(L0.ev_fork, L0.st));  // the cloud constants are ready from here on
       h->call_first_stage = h->stage_calls;
       rc = run_backward(h, L0, B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, nullptr, nullptr, false,

@@ -34,18 +34,18 @@ namespace chi {
 // model kind has (chi_logp_grad_rows: fewer bytes over PCIe).
 // (struct RowMap: launch.cuh)
 
-// the map of one (draw, cloud); also called from the sampler's tick kernel (nuts_warp.cuh)
+// the map of cloud n of one draw: theta_draw / constrained_draw point at the draw's [n_rows][N] /
+// [CHI_NSLOT][N] blocks (global or shared memory), cc_draw at its [N][CHI_CC_STRIDE] constants
 template <int MODEL>
-__device__ __forceinline__ void cloud_map_one(const MapCfg& cfg, const RowMap& rm, int N, const double* __restrict__ theta,
-                                              double* __restrict__ cc, double* __restrict__ constrained, int64_t b,
-                                              int n) {
-  const int64_t t = b * N + n;
+__device__ __forceinline__ void cloud_map_draw(const MapCfg& cfg, const RowMap& rm, int N,
+                                               const double* __restrict__ theta_draw, double* __restrict__ cc_draw,
+                                               double* __restrict__ constrained_draw, int n) {
   double th[CHI_NSLOT];
-  const double* tp = theta + (b * rm.n_rows) * N + n;
+  const double* tp = theta_draw + n;
 #pragma unroll
   for (int s = 0; s < CHI_NSLOT; ++s) th[s] = rm.row[s] >= 0 ? tp[(int64_t)rm.row[s] * N] : 0.0;
-  if (constrained) {
-    double* xp = constrained + (b * CHI_NSLOT) * N + n;
+  if (constrained_draw) {
+    double* xp = constrained_draw + n;
 #pragma unroll
     for (int s = 0; s < CHI_NSLOT; ++s) {
       th[s] = slot_backward(slot_dist<MODEL>(cfg, s), th[s]).x;
@@ -53,7 +53,7 @@ __device__ __forceinline__ void cloud_map_one(const MapCfg& cfg, const RowMap& r
     }
   }
   CloudPhys<double> ph = cloud_phys<MODEL, double>(cfg, th);
-  double* o = cc + t * CHI_CC_STRIDE;
+  double* o = cc_draw + (int64_t)n * CHI_CC_STRIDE;
   o[CC_C] = ph.velocity;
   o[CC_TS] = ph.tspin;
   o[CC_F] = ph.ff;
@@ -66,6 +66,15 @@ __device__ __forceinline__ void cloud_map_one(const MapCfg& cfg, const RowMap& r
                                                 cfg.wch2_a, cfg.lorentzian != 0);
   o[CC_KA] = pa.k; o[CC_AGA] = pa.AG; o[CC_ALA] = pa.AL; o[CC_HA] = pa.h;
   o[11] = 0.0;
+}
+
+// the map of one (draw, cloud) of a batch in global memory; also called from the sampler's tick kernel
+template <int MODEL>
+__device__ __forceinline__ void cloud_map_one(const MapCfg& cfg, const RowMap& rm, int N, const double* __restrict__ theta,
+                                              double* __restrict__ cc, double* __restrict__ constrained, int64_t b,
+                                              int n) {
+  cloud_map_draw<MODEL>(cfg, rm, N, theta + (b * rm.n_rows) * N, cc + (b * N) * CHI_CC_STRIDE,
+                        constrained ? constrained + (b * CHI_NSLOT) * N : nullptr, n);
 }
 
 template <int MODEL>

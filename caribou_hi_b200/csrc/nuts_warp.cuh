@@ -315,13 +315,147 @@ __device__ __forceinline__ void nw_end_iter(const NutsState& s, const NutsAdapt&
   __syncwarp();
 }
 
+// ---- the common tick, staged in shared memory ------------------------------------------------------
+// Most ticks of a chain are "a leaf inside a sub-tree": finish the leapfrog step whose gradient has
+// arrived (nw_leap_b), and since the sub-tree goes on, start the next one (nw_leap_a) and map the new
+// point.  Written with the functions above that is a chain of five store -> load round trips through
+// global memory (qc, pc, gc written by one phase and read back by the next; the evaluation point
+// written and read back by the map), ~1 us each for a kernel whose whole job is latency.  Here the
+// chain's working vectors live in shared memory for the tick: everything the later phases need is
+// read from there, the global copies are still written (later ticks and the rare paths read them) but
+// nothing waits for them.  Same operations in the same order as nw_leap_b + nw_leap_a + the map: the
+// draws are bit-identical (tests/test_gpu_nuts.py::test_tick_variants_agree).
+// Returns true when the tick is complete; false when the sub-tree ended with this leaf (all global
+// state is as nw_leap_b leaves it) and the caller continues with the general path.
+#define CHI_NUTS_MAXD (CHI_NSLOT * CHI_MAX_CLOUDS + 2 * CHI_MAX_BASELINE)
+struct NwStage {
+  double *x, *g, *p, *im, *rs;  // [D]: position, gradient, momentum of the finished leaf; inverse mass; sub-tree momentum sum
+};
+
+template <int MODEL>
+__device__ __forceinline__ bool nw_leaf_staged(const NutsState& s, int64_t b, int lane, const NwStage& w, const MapCfg& cfg,
+                                               const RowMap& rm, double* __restrict__ cc, double* __restrict__ xcon) {
+  const int leaf = s.leaf[b];
+  const int depth = s.depth[b];
+  const int64_t o = b * s.D;
+  const double h = s.dir[b] * s.eps[b];
+  const double lp = s.elogp[b];
+  const double energy0 = s.energy0[b], lw_sub = s.lw_sub[b];
+  double kin = 0.0;
+  CHI_FOR_D(d) {
+    const double x = nuts_ev(s.eu, s.ece, s.eca, s, b, d);
+    const double im = s.inv_mass[o + d];
+    double g = 0.0, p = 0.0;
+    if (s.role[d] == 1) {
+      g = nuts_grad(s, b, d);
+      p = s.ph[o + d] + 0.5 * h * g;
+      kin += 0.5 * im * p * p;
+    }
+    const double rs = s.rsum_s[o + d] + p;
+    w.x[d] = x; w.g[d] = g; w.p[d] = p; w.im[d] = im; w.rs[d] = rs;
+    s.qc[o + d] = x;
+    s.gc[o + d] = g;
+    s.pc[o + d] = p;
+    s.rsum_s[o + d] = rs;
+  }
+  kin = nw_sum(kin);
+  double energy = -lp + kin;
+  if (!(energy == energy) || isinf(energy)) energy = INFINITY;
+  const double delta = energy - energy0;
+  const bool diverging = !(delta <= 1000.0);
+  const double lw_leaf = -delta;
+  const double lw_new = nuts_logaddexp(lw_sub, lw_leaf);
+  int take = 0;
+  if (lane == 0) {
+    unsigned long long st = s.rng[b];
+    take = nuts_uniform(st) < exp(lw_leaf - lw_new);
+    s.rng[b] = st;
+  }
+  take = __shfl_sync(0xffffffffu, take, 0);
+  if (lane == 0) {
+    s.leaf[b] = leaf + 1;
+    s.sum_acc[b] += (delta == delta) ? fmin(1.0, exp(-delta)) : 0.0;
+    s.n_leap[b] += 1;
+    s.lw_sub[b] = lw_new;
+    if (take) s.logp_s[b] = lp;
+    if (diverging) s.diverged[b] = 1;
+  }
+  if (take) {
+    CHI_FOR_D(d) {
+      s.qs[o + d] = w.x[d];
+      s.gs[o + d] = w.g[d];
+    }
+  }
+  // iterative U-turn test through the checkpoints; a lane only touches the entries of its own dimensions
+  bool turning = false;
+  const int idx_max = __popc((unsigned)leaf >> 1);
+  double* ckr = s.ck_r + (b * CHI_NUTS_MAX_DEPTH) * s.D;
+  double* ckrs = s.ck_rs + (b * CHI_NUTS_MAX_DEPTH) * s.D;
+  if ((leaf & 1) == 0) {
+    CHI_FOR_D(d) {
+      ckr[idx_max * s.D + d] = w.p[d];
+      ckrs[idx_max * s.D + d] = w.rs[d];
+    }
+  } else {
+    const int n_sub = __ffs(~(unsigned)leaf) - 1;
+    const int idx_min = idx_max - n_sub + 1;
+    for (int i = idx_max; i >= idx_min && !turning; --i) {
+      const double* ca = ckr + i * s.D;
+      const double* cs = ckrs + i * s.D;
+      // (same arithmetic as nw_turning, with the inverse mass, momentum and momentum sum from shared memory)
+      double da = 0.0, db = 0.0;
+      CHI_FOR_D(d) {
+        if (s.role[d] != 1) continue;
+        const double a = ca[d], bb = w.p[d];
+        const double rsum = (w.rs[d] - cs[d] + a) - 0.5 * (a + bb);
+        da += w.im[d] * a * rsum;
+        db += w.im[d] * bb * rsum;
+      }
+      da = nw_sum(da);
+      db = nw_sum(db);
+      turning = da <= 0.0 || db <= 0.0;
+    }
+  }
+  int stop = 0;
+  if (turning || diverging) stop = turning ? 2 : 3;
+  if (lane == 0 && stop) s.sub_stop[b] = stop;
+  if (stop != 0 || leaf + 1 >= (1 << depth)) {
+    __syncwarp();  // the general path reads what lane 0 and the other lanes wrote
+    return false;
+  }
+  // ---- the sub-tree goes on: first half of the next leapfrog step, straight from shared memory ----
+  const int nu = CHI_NSLOT * s.N;
+  CHI_FOR_D(d) {
+    double x = w.x[d];
+    if (s.role[d] == 1) {
+      const double ph = w.p[d] + 0.5 * h * w.g[d];
+      s.ph[o + d] = ph;
+      x += h * w.im[d] * ph;
+    }
+    w.x[d] = x;
+  }
+  __syncwarp();
+  CHI_FOR_D(d) {
+    const double x = (s.role[d] == 2) ? w.x[d - (d % s.N)] : w.x[d];
+    w.g[d] = x;  // the evaluation point, replicas resolved (w.g is free now)
+    nuts_ev(s.eu, s.ece, s.eca, s, b, d) = x;
+  }
+  __syncwarp();
+  (void)nu;
+  if (cc && lane < s.N)
+    cloud_map_draw<MODEL>(cfg, rm, s.N, w.g, cc + (b * s.N) * CHI_CC_STRIDE,
+                          xcon ? xcon + (b * CHI_NSLOT) * s.N : nullptr, lane);
+  return true;
+}
+
 // one tick of every chain's state machine (see NutsAsync in nuts.cuh); 4 chains per block.  The
 // cloud map of the new evaluation point (k_cloud_map's work: transforms, parameter map, profile
 // constants) is done here by lanes 0..N-1, which takes one kernel out of the dependent chain of a
 // tick.
-template <int MODEL>
+template <int MODEL, bool STAGED>
 __global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A, MapCfg cfg, RowMap rm,
                                                      double* __restrict__ cc, double* __restrict__ xcon) {
+  __shared__ double s_stage[STAGED ? 4 : 1][5][STAGED ? CHI_NUTS_MAXD : 1];
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= s.B) return;
@@ -330,7 +464,16 @@ __global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A, M
   const int started = A.started[b];
   __syncwarp();
   if (started) {
-    if (nw_leap_b(s, b, lane)) {  // the logp / gradient of the leaf in flight has arrived
+    bool finished;
+    if (STAGED) {
+      double(*st)[STAGED ? CHI_NUTS_MAXD : 1] = s_stage[STAGED ? (threadIdx.x >> 5) : 0];
+      const NwStage w = {st[0], st[1], st[2], st[3], st[4]};
+      if (nw_leaf_staged<MODEL>(s, b, lane, w, cfg, rm, cc, xcon)) return;  // the common tick: done
+      finished = true;
+    } else {
+      finished = nw_leap_b(s, b, lane);
+    }
+    if (finished) {  // the logp / gradient of the leaf in flight has arrived
       if (!nw_end_subtree(s, b, lane, A.max_depth)) {
         NutsAdapt a;
         a.target_accept = A.target_accept;

@@ -806,7 +806,7 @@ class Engine:
         (the one-launch evaluation of small batches); ``small_nl`` clouds per thread of that kernel;
         ``small_chunks`` its blocks per draw."""
         opts = {"small_path": _lib.OPT_SMALL_PATH, "small_nl": _lib.OPT_SMALL_NL, "small_chunks": _lib.OPT_SMALL_CHUNKS,
-                "small_stamps": _lib.OPT_SMALL_STAMPS}
+                "small_stamps": _lib.OPT_SMALL_STAMPS, "nuts_tick": _lib.OPT_NUTS_TICK}
         self._check(self._lib.chi_set_option(self._h, opts[name], int(value)))
 
     def microbench_fp32(self):

@@ -462,6 +462,8 @@ int64_t chi_launch_count(const chi_handle* h);
 #define CHI_OPT_SMALL_CHUNKS 2
 #define CHI_OPT_SMALL_STAMPS 3 /* development aid: device pointer to 16 int64 receiving SM-clock offsets
                                   of block 0's phases (0 = off) */
+#define CHI_OPT_NUTS_TICK 4    /* 0 = the sampler's common tick staged in shared memory (default), 1 = every
+                                  phase through global memory (round-1 form; same draws bit for bit) */
 #define CHI_OPT_COUNT 8
 int chi_set_option(chi_handle* h, int option, int64_t value);
 /* Own-microbenchmark peaks of the device the handle is on (the driver's

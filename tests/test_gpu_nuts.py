@@ -117,3 +117,29 @@ def test_lock_step_and_asynchronous_chains_agree(cuda_device):
     d_async, d_lock = runs["async"][1]["depth"].mean(), runs["lock"][1]["depth"].mean()
     assert abs(d_async - d_lock) < 1.0
     assert abs(runs["async"][1]["accept"].mean() - runs["lock"][1]["accept"].mean()) < 0.1
+
+
+@pytest.mark.parametrize("kind_n", [("emission_absorption", 2), ("emission_absorption_physical", 3)])
+def test_tick_variants_agree(cuda_device, kind_n):
+    """The sampler's common tick staged in shared memory (default) does the same operations in the same
+    order as the round-1 form that passes every phase through global memory: identical draws and statistics."""
+    from caribou_hi_b200 import EmissionAbsorptionModel, EmissionAbsorptionPhysicalModel, SpecData
+
+    kind, N = kind_n
+    cls = EmissionAbsorptionModel if kind == "emission_absorption" else EmissionAbsorptionPhysicalModel
+    rng = np.random.default_rng(2)
+    ve, va = np.linspace(-40, 40, 96), np.linspace(-20, 20, 48)
+    out = []
+    for tick in (0, 1):
+        model = cls({"emission": SpecData(ve, rng.normal(5, 1, 96) * 0 + 5.0, 0.5), "absorption": SpecData(va, np.full(48, 0.2), 0.05)},
+                    N, baseline_degree=1)
+        model.add_priors(prior_fwhm_L=1.0) if kind.endswith("physical") else model.add_priors()
+        model.add_likelihood()
+        model.engine.set_option("nuts_tick", tick)
+        post, stats = model.sample(draws=40, tune=60, chains=6, seed=4)
+        out.append((post, stats))
+        model.engine.close()
+    for k in out[0][0]:
+        assert np.array_equal(out[0][0][k], out[1][0][k], equal_nan=True), k
+    for k in out[0][1]:
+        assert np.array_equal(out[0][1][k], out[1][1][k], equal_nan=True), k

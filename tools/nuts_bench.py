@@ -18,6 +18,8 @@ def run(cls, N, S_e, S_a, chains, tune, draws, **priors):
             "absorption": SpecData(va, mu["absorption"][0] + 0.01 * rng.standard_normal(S_a), 0.01)}
     model = cls(data, N, baseline_degree=0)
     model.add_priors(**priors); model.add_likelihood()
+    if os.environ.get("NUTS_TICK"):
+        model.engine.set_option("nuts_tick", int(os.environ["NUTS_TICK"]))
     l0 = model.engine.launch_count()
     t0 = time.perf_counter()
     post, stats = model.sample(draws=draws, tune=tune, chains=chains, seed=2, init_point=truth, jitter=0.05,
