@@ -1,5 +1,5 @@
 """BASELINE configs[2] shape (64 chains x 8 clouds x 2048+2048 channels, pseudo-Voigt): a few
-logp+grad evaluations, for launch lists / latency work.  usage: python tools/small_batch_target.py [reps]"""
+logp+grad evaluations, for launch lists / latency work.  usage: python tools/small_batch_target.py [reps] [small_path]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,8 +7,10 @@ import torch
 from caribou_hi_b200 import Engine, synthetic
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+path = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # chi_set_option small_path: 0 automatic, 1 pipeline, 2 one launch
 kind, N, S, B = "emission_absorption_physical", 8, 2048, 64
 eng = Engine(kind, N, lorentzian=True, prior_fwhm_L=1.0, prior_amplitude=1e21)
+eng.set_option("small_path", path)
 v = np.linspace(-100, 100, S)
 rng = np.random.default_rng(0)
 eng.set_spectra(emission=dict(spectral=v, brightness=rng.normal(10, 5, S), noise=0.1, basis=np.full((1, S), 0.1)),
