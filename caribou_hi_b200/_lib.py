@@ -28,7 +28,7 @@ MODEL_ABSORPTION_PHYSICAL = 4
 MODEL_EMISSION_PHYSICAL = 5
 MODEL_EMISSION_ABSORPTION_PHYSICAL = 6
 
-OPT_SMALL_PATH, OPT_SMALL_NL, OPT_SMALL_CHUNKS, OPT_SMALL_STAMPS, OPT_NUTS_TICK = 0, 1, 2, 3, 4
+OPT_SMALL_PATH, OPT_SMALL_NL, OPT_SMALL_CHUNKS, OPT_SMALL_STAMPS, OPT_NUTS_TICK, OPT_DEV_OVERLAP = 0, 1, 2, 3, 4, 5
 
 ERROR_NAMES = {0: "CHI_OK", -1: "CHI_EINVAL", -2: "CHI_ECUDA", -3: "CHI_ENODEV", -4: "CHI_ESTATE", -5: "CHI_ENOMEM"}
 
@@ -153,6 +153,7 @@ SYMBOLS = {
     "chi_stage_ms": (C.c_int, [_H, C.c_int, C.POINTER(C.c_float)]),
     "chi_launch_count": (C.c_int64, [_H]),
     "chi_set_option": (C.c_int, [_H, C.c_int, C.c_int64]),
+    "chi_dev_join": (C.c_int, [_H]),
     "chi_comm_unique_id": (C.c_int, [C.c_void_p]),
     "chi_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
     "chi_comm_destroy": (C.c_int, [_H]),

@@ -158,6 +158,8 @@ struct chi_handle {
   int64_t call_first_stage = 0;  // stage_calls at the start of the current model-level call
   int64_t launches = 0;
   int64_t opt[CHI_OPT_COUNT] = {};  // chi_set_option
+  int64_t dev_calls = 0;            // CHI_OPT_DEV_OVERLAP: device-resident calls issued (lane rotation)
+  cudaEvent_t ev_dev_in = nullptr;
   // multi-GPU (comm.cuh): communicator, its stream, and the workspace of k_shard_sums
   NcclComm comm = nullptr;
   int comm_rank = 0, comm_size = 1;
@@ -959,6 +961,7 @@ void chi_destroy(chi_handle* h) {
   Buf* bufs[] = {&h->w_gbe, &h->w_gba, &h->w_mue, &h->w_mua};
   for (Buf* b : bufs) b->release();
   for (Buf& b : h->w_misc) b.release();
+  if (h->ev_dev_in) cudaEventDestroy(h->ev_dev_in);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& row : h->ring)
@@ -1353,7 +1356,45 @@ int chi_logp_grad_dev(chi_handle* h, int64_t B, const double* theta, const doubl
   CaptureAware cap_aware(h);
   h->call_first_stage = h->stage_calls;
   h->kernel_ms = 0.f;
+  if (h->opt[CHI_OPT_DEV_OVERLAP] && !h->capturing && !batch_is_small(h, B)) {
+    // Relaxed stream contract (opt-in): consecutive device-resident calls alternate between two lanes,
+    // so the cloud map of call k+1 and the epilogue of call k run next to the other call's channel
+    // kernel instead of in front of / behind it.  Each call starts after everything enqueued on the
+    // handle's stream so far; its outputs are ordered into the handle's stream by chi_dev_join (or
+    // chi_synchronize), not by the call itself.
+    // The small kernels (map, epilogue) go to the lane's HIGH-PRIORITY stream: their blocks are placed
+    // ahead of the other call's channel-kernel blocks as slots free up, so the map of call k+1 is done
+    // when the channel kernel of call k drains and the two channel kernels run back to back.
+    Lane& L = h->lanes[1 + (h->dev_calls++ & 1)];
+    cudaEvent_t& ev = h->ev_dev_in;
+    if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, h->stream));
+    CK(cudaStreamWaitEvent(L.hi, ev, 0));
+    std::swap(L.st, L.hi);  // the map phase launches on what run_backward sees as the lane's stream
+    rc = run_backward(h, L, B, theta, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca, false, PHASE_MAP);
+    std::swap(L.st, L.hi);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(L.st, L.ev_fork, 0));
+    h->epilogue_on_hi = true;
+    rc = run_backward(h, L, B, theta, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca, false, PHASE_REST);
+    h->epilogue_on_hi = false;
+    return rc;
+  }
   return run_backward(h, h->lanes[0], B, theta, ce, ca, sl, nullptr, nullptr, false, logp, grad, gce, gca);
+}
+
+// The handle's stream waits for the device-resident calls issued in CHI_OPT_DEV_OVERLAP mode.
+int chi_dev_join(chi_handle* h) {
+  if (!h) return CHI_EINVAL;
+  CK(cudaSetDevice(h->device));
+  for (int i = 1; i < CHI_LANES; ++i) {
+    Lane& L = h->lanes[i];
+    CK(cudaEventRecord(L.ev_join, L.st));
+    CK(cudaStreamWaitEvent(h->stream, L.ev_join, 0));
+    CK(cudaEventRecord(L.ev_tail, L.hi));
+    CK(cudaStreamWaitEvent(h->stream, L.ev_tail, 0));
+  }
+  return CHI_OK;
 }
 
 int chi_spectra_dev(chi_handle* h, int64_t B, const double* theta, const double* ce, const double* ca,

@@ -801,12 +801,18 @@ class Engine:
     def comm_synchronize(self):
         self._check(self._lib.chi_comm_synchronize(self._h))
 
+    def dev_join(self):
+        """``dev_overlap`` mode: order the outputs of the device-resident calls issued so far into the handle's
+        stream (``chi_dev_join``)."""
+        self._check(self._lib.chi_dev_join(self._h))
+
     def set_option(self, name, value):
         """Tuning / test knobs (``chi_set_option``): ``small_path`` 0 by batch size, 1 never, 2 always
         (the one-launch evaluation of small batches); ``small_nl`` clouds per thread of that kernel;
         ``small_chunks`` its blocks per draw."""
         opts = {"small_path": _lib.OPT_SMALL_PATH, "small_nl": _lib.OPT_SMALL_NL, "small_chunks": _lib.OPT_SMALL_CHUNKS,
-                "small_stamps": _lib.OPT_SMALL_STAMPS, "nuts_tick": _lib.OPT_NUTS_TICK}
+                "small_stamps": _lib.OPT_SMALL_STAMPS, "nuts_tick": _lib.OPT_NUTS_TICK,
+                "dev_overlap": _lib.OPT_DEV_OVERLAP}
         self._check(self._lib.chi_set_option(self._h, opts[name], int(value)))
 
     def microbench_fp32(self):

@@ -464,8 +464,16 @@ int64_t chi_launch_count(const chi_handle* h);
                                   of block 0's phases (0 = off) */
 #define CHI_OPT_NUTS_TICK 4    /* 0 = the sampler's common tick staged in shared memory (default), 1 = every
                                   phase through global memory (round-1 form; same draws bit for bit) */
+#define CHI_OPT_DEV_OVERLAP 5  /* 1 = consecutive chi_logp_grad[_rows]_dev calls of large batches alternate between
+                                  two internal lanes and may overlap (map / epilogue of one call next to the channel
+                                  kernel of the other); each call still starts after everything enqueued on the
+                                  handle's stream before it, but its outputs are ordered into the handle's stream
+                                  by chi_dev_join() or chi_synchronize(), not by the call.  0 (default): every call
+                                  runs on the handle's stream. */
 #define CHI_OPT_COUNT 8
 int chi_set_option(chi_handle* h, int option, int64_t value);
+/* CHI_OPT_DEV_OVERLAP: make the handle's stream wait for the device-resident calls issued so far. */
+int chi_dev_join(chi_handle* h);
 /* Own-microbenchmark peaks of the device the handle is on (the driver's
  * MEASURED_PEAKS.json has no CUDA-core FP64 figure): dependent-free DFMA chains. */
 int chi_microbench_fp64(chi_handle* h, double* tflops_out);
