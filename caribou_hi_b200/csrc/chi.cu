@@ -478,8 +478,19 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     a.basis_a = h->a.basis.d(); a.coeff_a = ca;
     a.vjp = vjp ? 1 : 0; a.gbar_e = vjp ? gbar_e : nullptr; a.gbar_a = vjp ? gbar_a : nullptr;
     a.sl = sl; a.cc = L.cc.d(); a.mom = L.mom_e.d();
-    if (launch_moments_ea(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
-    h->launches++;
+    if (!small && !h->opt[CHI_OPT_EA_ONE_PASS] && moments_ea_two_pass(N, pv, a)) {
+      // the marked draws (a negative or NaN optical depth; normally none) on a few resident blocks next to
+      // the big grid, which then runs without the overflow branch of 2^y (moments_ea.cuh, MODE)
+      CK(cudaStreamWaitEvent(L.aux, L.ev_fork, 0));
+      if (launch_moments_ea_fixup(N, a, h->n_sm, L.aux)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+      CK(cudaEventRecord(L.ev_join, L.aux));
+      if (launch_moments_ea_tame(N, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+      CK(cudaStreamWaitEvent(L.st, L.ev_join, 0));
+      h->launches += 2;
+    } else {
+      if (launch_moments_ea(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+      h->launches++;
+    }
     CK(cudaGetLastError());
     ea.fused = 1; ea.has_e = 1; ea.has_a = 1; ea.nb_e = a.nb_e; ea.nb_a = a.nb_a;
     ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride; ea.mom_e = L.mom_e.d();

@@ -289,6 +289,6 @@ CHI_HD ProfConst<T> profile_consts(const T& fwhm2, const T& fwhm_L, const T& amp
 
 // Packed per-(draw, cloud) constants handed from the map kernel to the channel kernels.
 #define CHI_CC_STRIDE 12
-enum { CC_C = 0, CC_TS, CC_F, CC_KE, CC_AGE, CC_ALE, CC_HE, CC_KA, CC_AGA, CC_ALA, CC_HA };
+enum { CC_C = 0, CC_TS, CC_F, CC_KE, CC_AGE, CC_ALE, CC_HE, CC_KA, CC_AGA, CC_ALA, CC_HA, CC_CAREFUL };
 
 }  // namespace chi

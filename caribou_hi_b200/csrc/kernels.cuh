@@ -65,7 +65,9 @@ __device__ __forceinline__ void cloud_map_draw(const MapCfg& cfg, const RowMap& 
   ProfConst<double> pa = profile_consts<double>(ph.fwhm2, ph.fwhm_L, ph.wt * ph.tau_total,
                                                 cfg.wch2_a, cfg.lorentzian != 0);
   o[CC_KA] = pa.k; o[CC_AGA] = pa.AG; o[CC_ALA] = pa.AL; o[CC_HA] = pa.h;
-  o[11] = 0.0;
+  // 1: an optical depth of this cloud is negative, so 2^y can overflow on it (moments_ea.cuh, MODE); NaNs
+  // need no care, they propagate through the remainder of the exponential whatever the branch
+  o[CC_CAREFUL] = (pe.AG < 0.0 || pe.AL < 0.0 || pa.AG < 0.0 || pa.AL < 0.0) ? 1.0 : 0.0;
 }
 
 // the map of one (draw, cloud) of a batch in global memory; also called from the sampler's tick kernel

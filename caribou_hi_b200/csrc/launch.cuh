@@ -60,6 +60,11 @@ int launch_spectra(int N, bool pv, const SpecArgs& a, cudaStream_t st);
 int launch_spectra_ea(int N, bool pv, const SpecArgs& a, cudaStream_t st);
 struct FusedArgs;
 int launch_moments_ea(int N, bool pv, const FusedArgs& a, cudaStream_t st);
+// two launches for large Gaussian batches (moments_ea.cuh, MODE): the draws without a negative optical depth
+// on `st`, the marked ones on a small persistent grid (launch_ea_tame.cu)
+bool moments_ea_two_pass(int N, bool pv, const FusedArgs& a);
+int launch_moments_ea_tame(int N, const FusedArgs& a, cudaStream_t st);
+int launch_moments_ea_fixup(int N, const FusedArgs& a, int n_sm, cudaStream_t st);
 int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st);
 int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st);
 // ---- argument block of k_eval_small (small.cuh) ----

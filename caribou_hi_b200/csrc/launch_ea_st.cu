@@ -21,4 +21,16 @@ int launch_moments_ea_staged(int N, bool pv, const FusedArgs& a, cudaStream_t st
   }
   return -1;
 }
+
+int launch_moments_ea_tame_staged(int N, const FusedArgs& a, cudaStream_t st) {
+  const int64_t items = a.B * a.n_chunks;
+  const unsigned grid = (unsigned)((items + CHI_WARPS_PER_BLOCK - 1) / CHI_WARPS_PER_BLOCK);
+  switch (N) {
+#define CASE(n) \
+  case n: k_moments_ea<n, false, true, true, true, EA_TAME><<<grid, CHI_BLOCK, 0, st>>>(a); return 0;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+  }
+  return -1;
+}
 }  // namespace chi

@@ -812,7 +812,7 @@ class Engine:
         ``small_chunks`` its blocks per draw."""
         opts = {"small_path": _lib.OPT_SMALL_PATH, "small_nl": _lib.OPT_SMALL_NL, "small_chunks": _lib.OPT_SMALL_CHUNKS,
                 "small_stamps": _lib.OPT_SMALL_STAMPS, "nuts_tick": _lib.OPT_NUTS_TICK,
-                "dev_overlap": _lib.OPT_DEV_OVERLAP}
+                "dev_overlap": _lib.OPT_DEV_OVERLAP, "ea_one_pass": _lib.OPT_EA_ONE_PASS}
         self._check(self._lib.chi_set_option(self._h, opts[name], int(value)))
 
     def microbench_fp32(self):

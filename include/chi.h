@@ -470,6 +470,9 @@ int64_t chi_launch_count(const chi_handle* h);
                                   handle's stream before it, but its outputs are ordered into the handle's stream
                                   by chi_dev_join() or chi_synchronize(), not by the call.  0 (default): every call
                                   runs on the handle's stream. */
+#define CHI_OPT_EA_ONE_PASS 6  /* 1 = large Gaussian batches on a shared axis run the fused channel kernel as ONE
+                                  launch with the overflow branch of 2^y in it (the form small batches always use);
+                                  0 (default) = two launches, see moments_ea.cuh MODE.  Same results bit for bit. */
 #define CHI_OPT_COUNT 8
 int chi_set_option(chi_handle* h, int option, int64_t value);
 /* CHI_OPT_DEV_OVERLAP: make the handle's stream wait for the device-resident calls issued so far. */

@@ -585,3 +585,88 @@ def test_nan_inputs_propagate(cuda_device, shared, lorentzian):
                     mu_e32, mu_a32 = eng.spectra(theta, dtype=np.float32)
                     assert np.isnan(mu_a32).all(), (name, n, "mu_a f32")
     eng.close()
+
+
+@pytest.mark.parametrize("sightlines", [1, 3])
+def test_negative_depths_in_a_large_batch(cuda_device, sightlines):
+    """Large Gaussian batches on a shared axis run the fused channel kernel as two launches (moments_ea.cuh,
+    MODE): every draw without the +inf branch of 2^y, and the draws the cloud map marked -- a negative or NaN
+    optical depth, which the seven physics-level inputs allow -- on a small scanning grid with it.  Marked
+    draws of every flavour (mildly negative, overflowing, NaN, negative absorption weight only) in a batch
+    large enough for that form must give what the one-launch form gives, bit for bit, and what the oracle
+    gives: values where it is finite, the same NaN / -inf elsewhere."""
+    import torch
+    from caribou_hi_b200 import Engine
+
+    rng = np.random.default_rng(41)
+    B, N, S = 8000, 4, 96  # past the small-batch forms (batch_is_small in csrc/chi.cu)
+    v = np.linspace(-40, 40, S)
+    inp = {
+        "velocity": rng.normal(0, 8, (B, N)),
+        "fwhm2": rng.uniform(5, 200, (B, N)),
+        "fwhm_L": np.zeros((B, N)),
+        "tau_total": rng.uniform(0.05, 8, (B, N)),
+        "tspin": rng.uniform(30, 3000, (B, N)),
+        "filling_factor": rng.uniform(0.1, 1.0, (B, N)),
+        "absorption_weight": rng.uniform(0.3, 1.2, (B, N)),
+    }
+    kind = rng.integers(0, 20, B)  # 0..3 are the marked flavours, one draw in five
+    cloud = rng.integers(0, N, B)
+    rows = np.arange(B)
+    for k, (name, value) in enumerate([("tau_total", -0.4), ("tau_total", -2.0e4), ("tau_total", np.nan),
+                                       ("absorption_weight", -0.7)]):
+        sel = kind == k
+        inp[name][rows[sel], cloud[sel]] = value
+    assert (kind < 4).sum() > 1000
+    ye = rng.normal(5, 3, (sightlines, S))
+    ya = rng.normal(0.2, 0.1, (sightlines, S))
+    sl = rng.integers(0, sightlines, B).astype(np.int32)
+
+    eng = Engine("physics", N, lorentzian=False, bg_temp=3.77)
+    if sightlines == 1:
+        eng.set_spectra(emission=dict(spectral=v, brightness=ye[0], noise=0.3, offset=0.0),
+                        absorption=dict(spectral=v, brightness=ya[0], noise=0.02, offset=0.0))
+        sl_arg = None
+    else:
+        eng.set_spectra(emission=dict(spectral=v, brightness=ye, noise=0.3, offset=0.0),
+                        absorption=dict(spectral=v, brightness=ya, noise=0.02, offset=0.0), n_sightlines=sightlines)
+        sl_arg = sl
+    theta = eng.pack(inp)
+    n0 = eng.launch_count()
+    lp2, g2, _, _ = eng.logp_grad(theta, sightline=sl_arg)
+    n_two = eng.launch_count() - n0
+    eng.set_option("ea_one_pass", 1)
+    n0 = eng.launch_count()
+    lp1, g1, _, _ = eng.logp_grad(theta, sightline=sl_arg)
+    n_one = eng.launch_count() - n0
+    eng.set_option("ea_one_pass", 0)
+    assert n_two > n_one, "the two-launch form did not run"
+    assert np.array_equal(lp2, lp1, equal_nan=True)
+    assert np.array_equal(g2, g1, equal_nan=True)
+
+    spec = mr.make_spec("emission_absorption", N, bg_temp=3.77)
+    ref_lp = np.zeros(B)
+    ref_g = {k: np.zeros((B, N)) for k in inp}
+    for s in range(sightlines):
+        m = sl == s if sightlines > 1 else np.ones(B, bool)
+        data = {"emission": mr.OracleData(v, ye[s], 0.3), "absorption": mr.OracleData(v, ya[s], 0.02)}
+        for d in data.values():
+            d._brightness_offset = 0.0
+        it = {k: torch.tensor(x[m], requires_grad=True) for k, x in inp.items()}
+        lp = mr.logp_from_inputs(spec, data, it)  # fwhm_L = 0: the pseudo-Voigt profile is the Gaussian
+        lp.sum().backward()
+        ref_lp[m] = lp.detach().numpy()
+        for k in inp:
+            ref_g[k][m] = it[k].grad.numpy()
+    fin = np.isfinite(ref_lp)
+    assert fin.sum() > 0.8 * B and (~fin).sum() > 300
+    assert np.array_equal(np.isnan(lp2), np.isnan(ref_lp)) and np.array_equal(np.isneginf(lp2), np.isneginf(ref_lp))
+    assert_close(lp2[fin], ref_lp[fin], what="logp of a batch with marked draws", axis=None)
+    got = eng.unpack_grad(g2)
+    mild = fin & (kind < 4)
+    assert mild.sum() > 400  # negative depths that do not overflow: finite, and evaluated by the scanning grid
+    for name in inp:
+        if name == "fwhm_L":
+            continue
+        assert_close(got[name][fin], ref_g[name][fin], what=f"d/d{name} of a batch with marked draws")
+    eng.close()
