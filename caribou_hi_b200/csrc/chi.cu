@@ -27,6 +27,10 @@
 #define CHI_STAGE_RING 64
 
 using namespace chi;
+namespace chi {
+int launch_nuts_chain(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
+                      int max_ticks, size_t dyn_smem, cudaStream_t st);  // launch_chain.cu
+}
 
 namespace {
 
@@ -310,12 +314,13 @@ bool use_eval_small(const chi_handle* h, int64_t B, bool vjp) {
   return !h->graph_path && std::max<int64_t>(B, h->call_draws) <= 128;
 }
 
-int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const double* ce, const double* ca,
-              const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model) {
+// argument block of k_eval_small / k_nuts_chain for a batch; force_chunks > 0 fixes the blocks per draw
+int small_args(chi_handle* h, Lane& L, int64_t B, const double* theta, const double* ce, const double* ca,
+               const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model, int force_chunks,
+               SmallArgs* out, int* NL_out, size_t* dyn_smem_out) {
   const int N = h->cfg.n_clouds;
   const bool pv = h->cfg.lorentzian != 0;
-  cudaEvent_t* evs = h->ring[h->stage_calls % CHI_STAGE_RING];
-  SmallArgs a;
+  SmallArgs& a = *out;
   memset(&a, 0, sizeof(a));
   a.B = B; a.N = N; a.K = h->cfg.model == CHI_MODEL_PHYSICS ? 7 : CHI_NSLOT;
   a.rm = h->rm; a.prior = model ? 1 : 0; a.want_grad = grad ? 1 : 0;
@@ -336,7 +341,7 @@ int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const doub
   a.lgG = lgG;
   const int NP = NL << lgG, cpw = 32 >> lgG;
   // blocks per draw: fill the resident block slots once, at least one warp tile per channel warp
-  const int force_chunks = (int)h->opt[CHI_OPT_SMALL_CHUNKS];
+  if (force_chunks <= 0) force_chunks = (int)h->opt[CHI_OPT_SMALL_CHUNKS];
   int64_t want = std::max<int64_t>(1, ((int64_t)h->n_sm * eval_small_blocks_per_sm(NL)) / B);
   if (force_chunks > 0) want = force_chunks;
   const int max_chunks = std::max(1, S_max / (cpw * 7));
@@ -370,11 +375,46 @@ int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const doub
   for (int i = 0; i < a.nb_e && model; ++i) a.bprior_const += -log(h->bsig_e[i]) - CHI_HALF_LOG_2PI;
   for (int i = 0; i < a.nb_a && model; ++i) a.bprior_const += -log(h->bsig_a[i]) - CHI_HALF_LOG_2PI;
   const int n_gb = (a.nb_e > 1 ? a.nb_e - 1 : 0) + (a.nb_a > 1 ? a.nb_a - 1 : 0);
+  *NL_out = NL;
+  *dyn_smem_out = (size_t)n_gb * CHI_SM_THREADS * sizeof(double);
+  return CHI_OK;
+}
+
+// The sampler's per-chain kernel (nuts_chain.cuh) against the graph of kernels per tick: one block evaluates a
+// whole draw per tick, which wins while a tick is bound by its dependent latency and loses once a draw's channel
+// sums want more than one SM.  Measured on B200 (profiles/r2_nuts_chain.txt), us per tick:
+//   2 clouds x 334+166 channels, 8 chains:                      graph 26   chain kernel 14.5
+//   8 clouds x 2048+2048 channels, pseudo-Voigt, 64 chains:     graph 43   chain kernel 86
+// i.e. chain ~ 10 + 3.1 w, graph ~ 26 + 0.7 w with w = clouds x channels (x 1.5 pseudo-Voigt) in thousands: the
+// crossover is near w = 6.5.
+// CHI_OPT_NUTS_TICK: 0 = by size, 1 = graph with the round-1 tick, 2 = graph with the staged tick, 3 = the chain
+// kernel whenever it can run.
+#define CHI_CHAIN_TICKS 2048
+bool use_nuts_chain(const chi_handle* h, int64_t B) {
+  const int64_t mode = h->opt[CHI_OPT_NUTS_TICK];
+  if (mode == 1 || mode == 2) return false;
+  if (getenv("CHI_NUTS_THREAD")) return false;
+  const int N = h->cfg.n_clouds;
+  if (N * CHI_NSLOT > CHI_SM_THREADS - 96) return false;
+  if (mode == 3) return true;
+  const int64_t S = std::max(h->has_e ? h->e.S : 0, h->has_a ? h->a.S : 0);
+  const int64_t work = (int64_t)N * S * (h->cfg.lorentzian ? 3 : 2) / 2;
+  return work <= 6500 && B <= 8 * (int64_t)h->n_sm;
+}
+
+int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const double* ce, const double* ca,
+              const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model) {
+  cudaEvent_t* evs = h->ring[h->stage_calls % CHI_STAGE_RING];
+  SmallArgs a;
+  int NL = 1;
+  size_t dyn = 0;
+  int rc = small_args(h, L, B, theta, ce, ca, sl, logp, grad, gce, gca, model, 0, &a, &NL, &dyn);
+  if (rc) return rc;
   if (!h->capturing) {
     CK(cudaEventRecord(evs[0], L.st));
     CK(cudaEventRecord(evs[1], L.st));
   }
-  if (launch_eval_small(NL, pv, h->map, a, (size_t)n_gb * CHI_SM_THREADS * sizeof(double), L.st))
+  if (launch_eval_small(NL, h->cfg.lorentzian != 0, h->map, a, dyn, L.st))
     return fail(h, CHI_EINVAL, "unsupported small-batch configuration");
   h->launches++;
   CK(cudaGetLastError());
@@ -2295,7 +2335,24 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   };
   const double eps0 = cfg->init_step > 0.0 ? cfg->init_step : 0.25 / pow((double)std::max(n_free, 1), 0.25);
   k_nuts_init<<<grid, 64, 0, st>>>(s, (unsigned long long)cfg->seed, eps0);
-  rc = evaluate();
+  // the per-chain kernel (nuts_chain.cuh) evaluates a draw with one block; the starting point goes through the
+  // same arithmetic (k_eval_small, one block per draw)
+  const bool chain_kernel = !lock_step && use_nuts_chain(h, B);
+  SmallArgs chain_args;
+  int chain_nl = 1;
+  size_t chain_dyn = 0;
+  if (chain_kernel) {
+    rc = small_args(h, h->lanes[0], B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, s.elogp, s.egu,
+                    nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, 1, &chain_args, &chain_nl, &chain_dyn);
+    if (rc) return rc;
+    if (chain_args.n_chunks != 1) return fail(h, CHI_ECUDA, "chi_nuts_sample: the chain kernel needs one block per draw");
+    if (launch_eval_small(chain_nl, h->cfg.lorentzian != 0, h->map, chain_args, chain_dyn, st))
+      return fail(h, CHI_EINVAL, "unsupported configuration of the chain kernel");
+    h->launches++;
+    CK(cudaGetLastError());
+  } else {
+    rc = evaluate();
+  }
   if (rc) return rc;
   k_nuts_adopt<<<grid, 64, 0, st>>>(s);
   h->launches += 2;
@@ -2339,6 +2396,24 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     A.closes = d_closes;
     A.draws = d_draws; A.stat_accept = d_acc; A.stat_logp = d_lp; A.stat_eps = d_eps;
     A.stat_depth = d_depth; A.stat_diverged = d_div;
+    // every chain needs at most total * (2^max_depth + 1) ticks
+    const int64_t tick_cap = (int64_t)total * ((1LL << max_depth) + 1) + 64;
+    if (chain_kernel) {
+      // one resident block per chain runs whole leapfrog steps tick after tick (nuts_chain.cuh); a launch is
+      // bounded by CHI_CHAIN_TICKS ticks per chain, the host looks at the counter between launches
+      int64_t ticks = 0;
+      h_flags[0] = 0;
+      while (h_flags[0] < B && ticks < tick_cap) {
+        if (launch_nuts_chain(chain_nl, h->cfg.lorentzian != 0, h->map, chain_args, s, A, CHI_CHAIN_TICKS, chain_dyn, st))
+          return fail(h, CHI_EINVAL, "unsupported configuration of the chain kernel");
+        CK(cudaGetLastError());
+        ticks += CHI_CHAIN_TICKS;
+        h->launches++;
+        CK(cudaMemcpyAsync(h_flags, A.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+      }
+      if (h_flags[0] < B) return fail(h, CHI_ECUDA, "chi_nuts_sample: chains did not finish within the tick budget");
+    } else {
     ScopedGraph tgs;
     cudaGraph_t& tg = tgs.g;
     cudaGraphExec_t& tgx = tgs.x;
@@ -2371,8 +2446,6 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     CK(cap_err);
     CK(cudaGraphInstantiate(&tgx, tg, 0));
     CK(cudaGraphGetNodes(tg, nullptr, &tn));
-    // every chain needs at most total * (2^max_depth + 1) ticks
-    const int64_t tick_cap = (int64_t)total * ((1LL << max_depth) + 1) + 64;
     int64_t ticks = 0;
     h_flags[0] = 0;
     while (h_flags[0] < B && ticks < tick_cap) {
@@ -2385,6 +2458,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     if (h_flags[0] < B) {
       return fail(h, CHI_ECUDA, "chi_nuts_sample: chains did not finish within the tick budget");
     }
+    }  // graph of kernels per tick
   }
   ScopedGraph lgs[2];
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};

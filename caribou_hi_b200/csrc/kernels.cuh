@@ -611,12 +611,15 @@ __global__ void k_transform(MapCfg cfg, int64_t total, int N, int direction, con
 // physics-level kernels
 // ---------------------------------------------------------------------------
 // physics.calc_spin_temp, physics.py:58-106
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_spin_temp(int64_t n, const double* __restrict__ tk, const double* __restrict__ dens,
                             const double* __restrict__ na, double* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = spin_temp<double>(tk[i], dens[i], na[i]);
 }
+#endif
 
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_spin_temp_vjp(int64_t n, const double* __restrict__ tk, const double* __restrict__ dens,
                                 const double* __restrict__ na, const double* __restrict__ gbar,
                                 double* __restrict__ g_tk, double* __restrict__ g_dens,
@@ -630,12 +633,14 @@ __global__ void k_spin_temp_vjp(int64_t n, const double* __restrict__ tk, const 
   g_dens[i] = g * r.d[1];
   g_na[i] = g * r.d[2];
 }
+#endif
 
 // elementwise helpers of physics.py that the reference evaluates through PyTensor
 //   CHI_FN_GAUSSIAN                   physics.gaussian   (x, center, fwhm)        physics.py:16-35
 //   CHI_FN_LORENTZIAN                 physics.lorentzian (x, center, fwhm)        physics.py:38-55
 //   CHI_FN_LOG10_COLUMN_DENSITY       (tau_total, spin_temp, -)                   physics.py:191-207
 //   CHI_FN_LOG10_NONTHERMAL_PRESSURE  (log10_density, fwhm2_nonthermal, -)        physics.py:247-262
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_elementwise(int fn, int64_t n, const double* __restrict__ a, const double* __restrict__ b,
                               const double* __restrict__ c, double* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -661,8 +666,10 @@ __global__ void k_elementwise(int fn, int64_t n, const double* __restrict__ a, c
   }
   out[i] = r;
 }
+#endif
 
 // physics.calc_pseudo_voigt, physics.py:265-309 -> profile[S][N]
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_pseudo_voigt(int S, int N, const double* __restrict__ vax,
                                const double* __restrict__ velocity, const double* __restrict__ fwhm2,
                                const double* __restrict__ fwhm_L, double* __restrict__ out) {
@@ -675,8 +682,10 @@ __global__ void k_pseudo_voigt(int S, int N, const double* __restrict__ vax,
   const double d = vax[s] - velocity[n], d2 = d * d;
   out[t] = fma(p.AL, 1.0 / (d2 + p.h), p.AG * chi_exp(-p.k * d2));
 }
+#endif
 
 // physics.radiative_transfer, physics.py:312-365: tau[S][N] -> tb[S]
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_radiative_transfer(int S, int N, const double* __restrict__ tau,
                                      const double* __restrict__ tspin, const double* __restrict__ ff,
                                      double bg, double* __restrict__ out) {
@@ -691,9 +700,11 @@ __global__ void k_radiative_transfer(int S, int N, const double* __restrict__ ta
   }
   out[s] = (bg * P + T) - bg;
 }
+#endif
 
 // VJP of physics.calc_pseudo_voigt: gbar[S][N] -> d/d{velocity, fwhm2, fwhm_L}[N].
 // One block per cloud; the channel sums are the same six moments the hot kernels use.
+#ifndef CHI_DEVICE_ONLY
 __global__ void __launch_bounds__(256) k_pseudo_voigt_vjp(int S, int N, const double* __restrict__ vax,
                                                           const double* __restrict__ velocity,
                                                           const double* __restrict__ fwhm2,
@@ -741,10 +752,12 @@ __global__ void __launch_bounds__(256) k_pseudo_voigt_vjp(int S, int N, const do
   g_fwhm2[n] = g[0];
   g_fwhm_L[n] = g[1];
 }
+#endif
 
 // VJP of physics.radiative_transfer: gbar[S] -> g_tau[S][N] and (atomically summed over
 // channels into zeroed outputs) g_tspin[N], g_ff[N].  N <= CHI_RT_MAX_CLOUDS.
 #define CHI_RT_MAX_CLOUDS 64
+#ifndef CHI_DEVICE_ONLY
 __global__ void __launch_bounds__(128) k_radiative_transfer_vjp(int S, int N, const double* __restrict__ tau,
                                                                 const double* __restrict__ tspin,
                                                                 const double* __restrict__ ff, double bg,
@@ -772,6 +785,7 @@ __global__ void __launch_bounds__(128) k_radiative_transfer_vjp(int S, int N, co
     Q = fma(fma(-f, om[n], 1.0), Q, f * Ts * om[n]);
   }
 }
+#endif
 
 // chi_deterministics: every pm.Deterministic of the model class
 template <int MODEL>
@@ -822,6 +836,7 @@ __global__ void __launch_bounds__(128) k_deterministics(MapCfg cfg, int64_t B, i
 }
 
 // own-microbenchmark: FP64 FMA peak (8 independent chains per thread)
+#ifndef CHI_DEVICE_ONLY
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
          x7 = x0 + 7;
@@ -832,9 +847,11 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
   double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
   if (s == 12345.678) out[0] = s;  // never true; keeps the chains alive
 }
+#endif
 
 // FP32 FMA peak (16 independent chains per thread) and SFU peak (MUFU.EX2, 8 chains): the denominators of
 // the single-precision spectra kernels' roofline
+#ifndef CHI_DEVICE_ONLY
 __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float a, float b) {
   float x[16];
 #pragma unroll
@@ -848,6 +865,8 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float 
   for (int i = 0; i < 16; ++i) s += x[i];
   if (s == 12345.678f) out[0] = s;
 }
+#endif
+#ifndef CHI_DEVICE_ONLY
 __global__ void __launch_bounds__(256) k_sfu_peak(float* out, int iters) {
   float x[8];
 #pragma unroll
@@ -861,5 +880,6 @@ __global__ void __launch_bounds__(256) k_sfu_peak(float* out, int iters) {
   for (int i = 0; i < 8; ++i) s += x[i];
   if (s == 12345.678f) out[0] = s;
 }
+#endif
 
 }  // namespace chi

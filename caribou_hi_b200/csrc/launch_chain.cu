@@ -1,0 +1,42 @@
+// k_nuts_chain<NL, PV> instantiations (nuts_chain.cuh).  Built twice (launch_chain.cu: Gaussian,
+// launch_chain_pv.cu: pseudo-Voigt) so the halves compile in parallel.
+#include "nuts_chain.cuh"
+
+#ifndef CHI_CHAIN_PV
+#define CHI_CHAIN_PV 0
+#endif
+
+namespace chi {
+namespace {
+template <int NL, bool PV>
+int run_chain(const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks, size_t gb_bytes,
+              cudaStream_t st) {
+  k_nuts_chain<NL, PV><<<(unsigned)a.B, CHI_SM_THREADS, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
+  return 0;
+}
+}  // namespace
+
+#if CHI_CHAIN_PV
+int launch_nuts_chain_pv(int NL, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
+                         size_t gb_bytes, cudaStream_t st) {
+#else
+int launch_nuts_chain_pv(int NL, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
+                         size_t gb_bytes, cudaStream_t st);
+static int launch_nuts_chain_g(int NL, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
+                               int max_ticks, size_t gb_bytes, cudaStream_t st) {
+#endif
+  constexpr bool PV = CHI_CHAIN_PV != 0;
+  switch (NL) {
+    case 1: return run_chain<1, PV>(cfg, a, s, A, max_ticks, gb_bytes, st);
+    case 2: return run_chain<2, PV>(cfg, a, s, A, max_ticks, gb_bytes, st);
+  }
+  return -1;
+}
+#if !CHI_CHAIN_PV
+int launch_nuts_chain(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
+                      int max_ticks, size_t gb_bytes, cudaStream_t st) {
+  return pv ? launch_nuts_chain_pv(NL, cfg, a, s, A, max_ticks, gb_bytes, st)
+            : launch_nuts_chain_g(NL, cfg, a, s, A, max_ticks, gb_bytes, st);
+}
+#endif
+}  // namespace chi

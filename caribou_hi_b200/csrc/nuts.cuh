@@ -115,6 +115,7 @@ __device__ __forceinline__ void nuts_set_eval(const NutsState& s, int64_t b, con
 }
 
 // ---- initial evaluation: take logp / gradient of the evaluation point as the current state ----
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_adopt(NutsState s) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
@@ -126,6 +127,7 @@ __global__ void k_nuts_adopt(NutsState s) {
   }
   s.logp[b] = s.elogp[b];
 }
+#endif
 
 // ---- start of a NUTS iteration: fresh momentum, single-node tree --------------------------
 __device__ __forceinline__ void nuts_begin_iter(const NutsState& s, int64_t b) {
@@ -152,12 +154,14 @@ __device__ __forceinline__ void nuts_begin_iter(const NutsState& s, int64_t b) {
   s.diverged[b] = 0;
   s.active[b] = 1;
 }
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_begin_iter(NutsState s) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
   nuts_begin_iter(s, b);
   if (b == 0) *s.n_active = (int)s.B;
 }
+#endif
 
 // ---- start of a doubling: pick the direction, put the cursor on that edge -----------------
 __device__ __forceinline__ void nuts_begin_subtree(const NutsState& s, int64_t b) {
@@ -182,11 +186,13 @@ __device__ __forceinline__ void nuts_begin_subtree(const NutsState& s, int64_t b
   s.lw_sub[b] = -INFINITY;
   s.leaf[b] = 0;
 }
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_begin_subtree(NutsState s) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
   nuts_begin_subtree(s, b);
 }
+#endif
 
 // ---- leapfrog, first half: half kick + drift; the new position becomes the evaluation point ---
 __device__ __forceinline__ void nuts_leap_a(const NutsState& s, int64_t b) {
@@ -275,12 +281,14 @@ __device__ __forceinline__ void nuts_leap_b(const NutsState& s, int64_t b) {
 // One kernel per leapfrog boundary: finish the leaf whose logp/gradient just arrived (do_b) and,
 // unless the chain's sub-tree stopped, start the next one (do_a).  The first launch of a
 // doubling has do_b = 0, the last one do_a = 0.
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_leap(NutsState s, int do_b, int do_a) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B || s.sub_stop[b]) return;
   if (do_b) nuts_leap_b(s, b);
   if (do_a && !s.sub_stop[b]) nuts_leap_a(s, b);
 }
+#endif
 
 // ---- end of a doubling: merge the sub-tree into the tree ------------------------------------
 __device__ __forceinline__ void nuts_end_subtree(const NutsState& s, int64_t b, int max_depth) {
@@ -311,11 +319,13 @@ __device__ __forceinline__ void nuts_end_subtree(const NutsState& s, int64_t b, 
     atomicSub(s.n_active, 1);
   }
 }
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_end_subtree(NutsState s, int max_depth) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B || !s.active[b]) return;
   nuts_end_subtree(s, b, max_depth);
 }
+#endif
 
 // ---- end of the iteration: move to the proposal, adapt, record -------------------------------
 struct NutsAdapt {
@@ -332,6 +342,7 @@ struct NutsAdapt {
 // statistics are merged), which needs B times fewer iterations per window than PyMC's per-chain
 // estimate for the same accuracy.  One block per dimension; then every chain restarts its window
 // and its step-size averaging (k_nuts_restart_window).
+#ifndef CHI_DEVICE_ONLY
 __global__ void __launch_bounds__(128) k_nuts_pool_mass(NutsState s) {
   const int d = blockIdx.x;
   if (s.role[d] != 1) return;
@@ -367,7 +378,9 @@ __global__ void __launch_bounds__(128) k_nuts_pool_mass(NutsState s) {
   const double inv = (cnt / (cnt + 5.0)) * var + 1e-3 * (5.0 / (cnt + 5.0));  // Stan's regularisation
   for (int64_t b = threadIdx.x; b < s.B; b += blockDim.x) s.inv_mass[b * s.D + d] = inv;
 }
+#endif
 
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_restart_window(NutsState s) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
@@ -382,6 +395,7 @@ __global__ void k_nuts_restart_window(NutsState s) {
   s.da_logeps_bar[b] = 0.0;
   s.da_count[b] = 0;
 }
+#endif
 
 __device__ __forceinline__ void nuts_end_iter(const NutsState& s, const NutsAdapt& a, int64_t b, double* draws,
                                               double* stat_accept, int* stat_depth, int* stat_diverged,
@@ -440,12 +454,14 @@ __device__ __forceinline__ void nuts_end_iter(const NutsState& s, const NutsAdap
     stat_eps[draw_index * s.B + b] = s.eps[b];
   }
 }
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_end_iter(NutsState s, NutsAdapt a, double* draws, double* stat_accept, int* stat_depth,
                                 int* stat_diverged, double* stat_logp, double* stat_eps, int64_t draw_index) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
   nuts_end_iter(s, a, b, draws, stat_accept, stat_depth, stat_diverged, stat_logp, stat_eps, draw_index);
 }
+#endif
 
 // ---- asynchronous chains ----------------------------------------------------------------------
 // In lock step every chain waits, in every iteration, for the deepest tree among the chains, so the
@@ -466,6 +482,7 @@ struct NutsAsync {
   int *stat_depth, *stat_diverged;
 };
 
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_tick(NutsState s, NutsAsync A) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
@@ -502,8 +519,10 @@ __global__ void k_nuts_tick(NutsState s, NutsAsync A) {
   }
   nuts_leap_a(s, b);
 }
+#endif
 
 // initial per-chain state of the adaptation
+#ifndef CHI_DEVICE_ONLY
 __global__ void k_nuts_init(NutsState s, unsigned long long seed, double eps0) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
@@ -523,5 +542,6 @@ __global__ void k_nuts_init(NutsState s, unsigned long long seed, double eps0) {
     s.w_m2[o + d] = 0.0;
   }
 }
+#endif
 
 }  // namespace chi

@@ -448,17 +448,15 @@ __device__ __forceinline__ bool nw_leaf_staged(const NutsState& s, int64_t b, in
   return true;
 }
 
-// one tick of every chain's state machine (see NutsAsync in nuts.cuh); 4 chains per block.  The
-// cloud map of the new evaluation point (k_cloud_map's work: transforms, parameter map, profile
-// constants) is done here by lanes 0..N-1, which takes one kernel out of the dependent chain of a
-// tick.
+// one tick of chain b's state machine (see NutsAsync in nuts.cuh), by one warp.  `st`: the warp's
+// [5][CHI_NUTS_MAXD] staging area in shared memory (STAGED).  The cloud map of the new evaluation point
+// (k_cloud_map's work: transforms, parameter map, profile constants) is done here by lanes 0..N-1 when cc is
+// given, which takes one kernel out of the dependent chain of a tick; cc == null: the evaluation maps the
+// point itself (k_eval_small, k_nuts_chain).
 template <int MODEL, bool STAGED>
-__global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A, MapCfg cfg, RowMap rm,
-                                                     double* __restrict__ cc, double* __restrict__ xcon) {
-  __shared__ double s_stage[STAGED ? 4 : 1][5][STAGED ? CHI_NUTS_MAXD : 1];
-  const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (b >= s.B) return;
+__device__ __forceinline__ void nw_tick(const NutsState& s, const NutsAsync& A, const MapCfg& cfg, const RowMap& rm,
+                                        double* __restrict__ cc, double* __restrict__ xcon, const int64_t b, const int lane,
+                                        double (*st)[STAGED ? CHI_NUTS_MAXD : 1]) {
   int it = A.iter[b];
   if (it >= A.n_total) return;  // finished: its evaluation point stays at the last state
   const int started = A.started[b];
@@ -466,7 +464,6 @@ __global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A, M
   if (started) {
     bool finished;
     if (STAGED) {
-      double(*st)[STAGED ? CHI_NUTS_MAXD : 1] = s_stage[STAGED ? (threadIdx.x >> 5) : 0];
       const NwStage w = {st[0], st[1], st[2], st[3], st[4]};
       if (nw_leaf_staged<MODEL>(s, b, lane, w, cfg, rm, cc, xcon)) return;  // the common tick: done
       finished = true;
@@ -501,8 +498,18 @@ __global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A, M
     nw_begin_subtree(s, b, lane);
   }
   nw_leap_a(s, b, lane);
-  // cc == null: the evaluation kernel maps the point itself (k_eval_small)
   if (cc && lane < s.N) cloud_map_one<MODEL>(cfg, rm, s.N, s.eu, cc, xcon, b, lane);
+}
+
+// one tick of every chain; 4 chains per block
+template <int MODEL, bool STAGED>
+__global__ void __launch_bounds__(128) k_nuts_tick_w(NutsState s, NutsAsync A, MapCfg cfg, RowMap rm,
+                                                     double* __restrict__ cc, double* __restrict__ xcon) {
+  __shared__ double s_stage[STAGED ? 4 : 1][5][STAGED ? CHI_NUTS_MAXD : 1];
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= s.B) return;
+  nw_tick<MODEL, STAGED>(s, A, cfg, rm, cc, xcon, b, lane, s_stage[STAGED ? (threadIdx.x >> 5) : 0]);
 }
 
 #undef CHI_FOR_D

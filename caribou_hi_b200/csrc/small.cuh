@@ -27,15 +27,32 @@
 namespace chi {
 
 // ---- the O(N) part, compiled once (not per channel-loop instantiation) -------------------------
+// PyMC's default transform of free RV s (slot_backward with the distribution the model kind gives the slot).
+// One thread per (cloud, slot) evaluates it ONCE per draw into shared memory (sm_eval), where the map and every
+// Jacobian record of the cloud read it: ten exponentials / sigmoids less on the dependent chain of the map, twenty
+// less on that of a Jacobian record.
+static __device__ __noinline__ Transformed sm_transform(const MapCfg* cfg, int s, double u) {
+  int dist = PD_NONE;
+  switch (cfg->model) {
+#define CASE(M) case M: dist = slot_dist<M>(*cfg, s); break;
+    CASE(CHI_MODEL_PHYSICS) CASE(CHI_MODEL_ABSORPTION) CASE(CHI_MODEL_EMISSION) CASE(CHI_MODEL_EMISSION_ABSORPTION)
+    CASE(CHI_MODEL_ABSORPTION_PHYSICAL) CASE(CHI_MODEL_EMISSION_PHYSICAL) CASE(CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL)
+#undef CASE
+  }
+  return slot_backward(dist, u);
+}
+
+// tr: the cloud's CHI_NSLOT transformed free RVs (prior), or null: tp holds constrained values
 template <int MODEL>
-__device__ __forceinline__ void sm_map_impl(const MapCfg& cfg, const RowMap& rm, int N, bool prior,
+__device__ __forceinline__ void sm_map_impl(const MapCfg& cfg, const RowMap& rm, int N, const Transformed* tr,
                                             const double* __restrict__ tp, double* __restrict__ o) {
   double th[CHI_NSLOT];
+  if (tr) {
 #pragma unroll
-  for (int s = 0; s < CHI_NSLOT; ++s) th[s] = rm.row[s] >= 0 ? tp[(int64_t)rm.row[s] * N] : 0.0;
-  if (prior) {
+    for (int s = 0; s < CHI_NSLOT; ++s) th[s] = tr[s].x;
+  } else {
 #pragma unroll
-    for (int s = 0; s < CHI_NSLOT; ++s) th[s] = slot_backward(slot_dist<MODEL>(cfg, s), th[s]).x;
+    for (int s = 0; s < CHI_NSLOT; ++s) th[s] = rm.row[s] >= 0 ? tp[(int64_t)rm.row[s] * N] : 0.0;
   }
   CloudPhys<double> ph = cloud_phys<MODEL, double>(cfg, th);
   o[CC_C] = ph.velocity;
@@ -49,9 +66,10 @@ __device__ __forceinline__ void sm_map_impl(const MapCfg& cfg, const RowMap& rm,
 }
 
 // free RVs of cloud n of one draw (tp = theta of the draw + n) -> the 11 cloud constants (CC_*)
-static __device__ __noinline__ void sm_map(const MapCfg* cfg, const RowMap* rm, int N, int prior, const double* tp, double* o) {
+static __device__ __noinline__ void sm_map(const MapCfg* cfg, const RowMap* rm, int N, const Transformed* tr, const double* tp,
+                                           double* o) {
   switch (cfg->model) {
-#define CASE(M) case M: sm_map_impl<M>(*cfg, *rm, N, prior != 0, tp, o); break;
+#define CASE(M) case M: sm_map_impl<M>(*cfg, *rm, N, tr, tp, o); break;
     CASE(CHI_MODEL_PHYSICS) CASE(CHI_MODEL_ABSORPTION) CASE(CHI_MODEL_EMISSION) CASE(CHI_MODEL_EMISSION_ABSORPTION)
     CASE(CHI_MODEL_ABSORPTION_PHYSICAL) CASE(CHI_MODEL_EMISSION_PHYSICAL) CASE(CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL)
 #undef CASE
@@ -60,16 +78,15 @@ static __device__ __noinline__ void sm_map(const MapCfg* cfg, const RowMap* rm, 
 
 // one record of the Jacobian of the map: tangents along free RV j0 of cloud n (k_jacobian's record)
 template <int MODEL>
-__device__ __forceinline__ void sm_jac_impl(const MapCfg& cfg, const RowMap& rm, int N, bool prior, bool has_e,
+__device__ __forceinline__ void sm_jac_impl(const MapCfg& cfg, const RowMap& rm, int N, const Transformed* tr, bool has_e,
                                             bool has_a, const double* __restrict__ tp, int j0,
                                             double* __restrict__ o, double* __restrict__ prior_out) {
   typedef Dual<1> D;
+  const bool prior = tr != nullptr;
   D th[CHI_NSLOT];
-  double u[CHI_NSLOT];
 #pragma unroll
   for (int s = 0; s < CHI_NSLOT; ++s) {
-    u[s] = rm.row[s] >= 0 ? tp[(int64_t)rm.row[s] * N] : 0.0;
-    th[s] = D(prior ? slot_backward(slot_dist<MODEL>(cfg, s), u[s]).x : u[s]);
+    th[s] = D(prior ? tr[s].x : (rm.row[s] >= 0 ? tp[(int64_t)rm.row[s] * N] : 0.0));
     th[s].d[0] = (s == j0) ? 1.0 : 0.0;
   }
   CloudPhys<D> ph = cloud_phys<MODEL, D>(cfg, th);
@@ -94,20 +111,18 @@ __device__ __forceinline__ void sm_jac_impl(const MapCfg& cfg, const RowMap& rm,
       if (dist == PD_NONE) continue;
       const double w = (s == CHI_FR_FWHM_L_NORM) ? cfg.fwhm_L_weight : 1.0;
       lp = lp + w * slot_density<D>(cfg, dist, th[s], thermal);
-      logj += w * slot_backward(dist, u[s]).logj;
+      logj += w * tr[s].logj;
     }
-    const int dist = slot_dist<MODEL>(cfg, j0);
     const double w = (j0 == CHI_FR_FWHM_L_NORM) ? cfg.fwhm_L_weight : 1.0;
-    const Transformed tr = slot_backward(dist, u[j0]);
-    o[11] = lp.d[0]; o[12] = tr.dxdu; o[13] = w * tr.dlogj;
+    o[11] = lp.d[0]; o[12] = tr[j0].dxdu; o[13] = w * tr[j0].dlogj;
     if (j0 == 0) *prior_out = lp.v + logj;
   }
 }
 
-static __device__ __noinline__ void sm_jac(const MapCfg* cfg, const RowMap* rm, int N, int prior, int has_e, int has_a,
+static __device__ __noinline__ void sm_jac(const MapCfg* cfg, const RowMap* rm, int N, const Transformed* tr, int has_e, int has_a,
                                     const double* tp, int j0, double* o, double* prior_out) {
   switch (cfg->model) {
-#define CASE(M) case M: sm_jac_impl<M>(*cfg, *rm, N, prior != 0, has_e != 0, has_a != 0, tp, j0, o, prior_out); break;
+#define CASE(M) case M: sm_jac_impl<M>(*cfg, *rm, N, tr, has_e != 0, has_a != 0, tp, j0, o, prior_out); break;
     CASE(CHI_MODEL_PHYSICS) CASE(CHI_MODEL_ABSORPTION) CASE(CHI_MODEL_EMISSION) CASE(CHI_MODEL_EMISSION_ABSORPTION)
     CASE(CHI_MODEL_ABSORPTION_PHYSICAL) CASE(CHI_MODEL_EMISSION_PHYSICAL) CASE(CHI_MODEL_EMISSION_ABSORPTION_PHYSICAL)
 #undef CASE
@@ -438,27 +453,48 @@ __device__ __forceinline__ void sm_store_acc(const SmCtx& x, double (&acc)[NL][M
 // then NP x NF fused moments, or NP x NE emission moments followed by NP x NA absorption moments
 // (NP = NL 2^lgG clouds, the model's N first)
 // ---------------------------------------------------------------------------------------------------
-template <int NL, bool PV>
-__global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(MapCfg cfg, SmallArgs a) {
+// shared memory of one block (the sizes do not depend on the instantiation)
+struct SmSmem {
+  double T[CHI_EXP_TABLE];
+  double cc[CHI_MAX_CLOUDS * 2 * CHI_SM_CCS];  // NL 2^lgG <= 32 clouds
+  double beta[2 * CHI_MAX_BASELINE];
+  double red[CHI_SM_WARPS][CHI_SM_MAXREC + 2];
+  double sum[CHI_SM_MAXREC + 2];
+  Transformed tr[CHI_MAX_CLOUDS * CHI_NSLOT];  // [cloud][slot] (prior mode)
+  MapCfg cfg;
+  RowMap rm;
+  int last;
+};
+
+// once per block: exponential table and the map's configuration
+__device__ __forceinline__ void sm_init(SmSmem& S, const MapCfg& cfg, const RowMap& rm) {
+  const int tid = threadIdx.x;
+  if (tid == 0) { S.cfg = cfg; S.rm = rm; }
+  for (int i = tid; i < CHI_EXP_TABLE; i += CHI_SM_THREADS) S.T[i] = g_exp2_table[CHI_EXP_REPL ? (i >> 4) << 3 : i];
+}
+
+// One (draw, chunk) of the evaluation by the whole block; the first statement after sm_init (or after the
+// previous call) must be reached by every thread.  tb / ce_b / ca_b: the draw's theta block [n_rows][N] and
+// baseline coefficients (global or shared memory; null = no coefficients).
+// CHAIN (nuts_chain.cuh: one block evaluates the same chain tick after tick, n_chunks == 1): the block's
+// record is the draw's record, so it stays in shared memory -- no record in global memory, no counter.
+template <int NL, bool PV, bool CHAIN>
+__device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const SmallArgs& a, const int64_t b, const int chunk,
+                                        const double* tb, const double* ce_b, const double* ca_b) {
   constexpr int NF = PV ? 10 : 6, NE = PV ? 8 : 5, NA = PV ? 6 : 3;
-  __shared__ double s_T[CHI_EXP_TABLE];
-  __shared__ double s_cc[CHI_MAX_CLOUDS * 2 * CHI_SM_CCS];  // NL 2^lgG <= 32 clouds
-  __shared__ double s_beta[2 * CHI_MAX_BASELINE];
-  __shared__ double s_red[CHI_SM_WARPS][CHI_SM_MAXREC + 2];
-  __shared__ double s_sum[CHI_SM_MAXREC + 2];
-  __shared__ MapCfg s_cfg;
-  __shared__ RowMap s_rm;
-  __shared__ int s_last;
-  extern __shared__ double s_gb_dyn[];  // (nb_e - 1 + nb_a - 1) x CHI_SM_THREADS when baselines have > 1 term
+  double* const s_T = S.T;
+  double* const s_cc = S.cc;
+  double* const s_beta = S.beta;
+  double(*const s_red)[CHI_SM_MAXREC + 2] = S.red;
+  double* const s_sum = S.sum;
+  MapCfg& s_cfg = S.cfg;
+  RowMap& s_rm = S.rm;
+  int& s_last = S.last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t b = blockIdx.x / a.n_chunks;
-  const int chunk = (int)(blockIdx.x - b * a.n_chunks);
   const int N = a.N, G = 1 << a.lgG, NP = NL * G;
   const int nbe = a.nb_e, nba = a.nb_a;
 
-  if (tid == 0) { s_cfg = cfg; s_rm = a.rm; }
-  for (int i = tid; i < CHI_EXP_TABLE; i += CHI_SM_THREADS) s_T[i] = g_exp2_table[CHI_EXP_REPL ? (i >> 4) << 3 : i];
   // null clouds pad the lane groups: tau = 0, f = 0
   for (int i = tid; i < NP * CHI_SM_CCS; i += CHI_SM_THREADS) {
     const int k = i % CHI_SM_CCS;
@@ -467,23 +503,32 @@ __global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(
   if (tid < 2 * CHI_MAX_BASELINE) {
     const bool e = tid < CHI_MAX_BASELINE;
     const int i = e ? tid : tid - CHI_MAX_BASELINE;
-    const double* c = e ? a.coeff_e : a.coeff_a;
+    const double* c = e ? ce_b : ca_b;
     const int nb = e ? nbe : nba;
-    s_beta[tid] = (c && i < nb) ? c[b * nb + i] : 0.0;
+    s_beta[tid] = (c && i < nb) ? c[i] : 0.0;
   }
   const int n_gb = (nbe > 1 ? nbe - 1 : 0) + (nba > 1 ? nba - 1 : 0);
   for (int i = 0; i < n_gb; ++i) s_gb_dyn[i * CHI_SM_THREADS + tid] = 0.0;
   __syncthreads();
+  if (a.prior) {
+    // the transforms of the draw's free RVs, one thread each (the channel warps have nothing else to do yet)
+    if (tid < N * CHI_NSLOT) {
+      const int n = tid / CHI_NSLOT, sl_ = tid - n * CHI_NSLOT;
+      const double u = s_rm.row[sl_] >= 0 ? tb[(int64_t)s_rm.row[sl_] * N + n] : 0.0;
+      S.tr[tid] = sm_transform(&s_cfg, sl_, u);
+    }
+    __syncthreads();
+  }
 
   // ---- map (warp 0) next to the Jacobian records of this block (last warps) ----
   const int ncw = CHI_SM_WARPS - a.jac_warps;  // channel warps
-  const double* tb = a.theta + (b * a.rm.n_rows) * N;
   // the draw's likelihood constant, fetched early by the thread that writes logp at the very end
   double lconst_b = 0.0;
   if (tid == CHI_SM_THREADS - 32 && a.lconst) lconst_b = __ldg(a.lconst + (a.sl ? a.sl[b] : 0));
   long long t_0 = 0, t_map = 0, t_jac = 0, t_chan = 0;
   if (a.stamps) t_0 = clock64();
-  if (warp == 0 && lane < N) sm_map(&s_cfg, &s_rm, N, a.prior, tb + lane, s_cc + lane * CHI_SM_CCS);
+  if (warp == 0 && lane < N)
+    sm_map(&s_cfg, &s_rm, N, a.prior ? S.tr + lane * CHI_NSLOT : nullptr, tb + lane, s_cc + lane * CHI_SM_CCS);
   if (a.stamps) t_map = clock64();
   if (warp >= ncw) {
     // records r = n K + j of this draw with r % n_chunks == chunk
@@ -492,7 +537,7 @@ __global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(
     if (r < N * a.K) {
       const int n = r / a.K, j0 = r - n * a.K;
       if (a.want_grad || (a.prior && j0 == 0))
-        sm_jac(&s_cfg, &s_rm, N, a.prior, a.fused || a.has_e, a.fused || a.has_a, tb + n, j0,
+        sm_jac(&s_cfg, &s_rm, N, a.prior ? S.tr + n * CHI_NSLOT : nullptr, a.fused || a.has_e, a.fused || a.has_a, tb + n, j0,
                a.jac + ((b * N + n) * a.K + j0) * CHI_JAC_W, a.prior_buf + b * N + n);
     }
     if (a.stamps) t_jac = clock64();
@@ -564,42 +609,51 @@ __global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(
   }
   if (a.stamps) t_chan = clock64();
   __syncthreads();
-  if (a.stamps && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == CHI_SM_WARPS - 1)) {
+  if (a.stamps && b == 0 && chunk == 0 && lane == 0 && (warp == 0 || warp == CHI_SM_WARPS - 1)) {
     long long* o = a.stamps + (warp == 0 ? 0 : 8);
     o[0] = t_map - t_0; o[1] = t_jac - t_0; o[2] = t_chan - t_0; o[3] = clock64() - t_0;
   }
-  // channel-warp partials in fixed order -> the (draw, chunk) record
-  double* rec = a.mom + ((int64_t)blockIdx.x) * stride;
-  for (int t = tid; t < stride; t += CHI_SM_THREADS) {
-    double v = 0.0;
-    for (int w = 0; w < ncw; ++w) v += s_red[w][t];
-    rec[t] = v;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned done = atomicAdd(a.counter + b, 1u);
-    s_last = (done == (unsigned)a.n_chunks - 1u);
-    if (s_last) a.counter[b] = 0;  // ready for the next launch
-  }
-  __syncthreads();
-  if (a.stamps && blockIdx.x == 0 && tid == 0) a.stamps[4] = clock64() - t_0;
-  if (!s_last) return;
-  __threadfence();
-
-  // ---- this block completed the draw: chunk sums in fixed order, then the contraction ----
-  const double* rec0 = a.mom + (b * a.n_chunks) * stride;
-  for (int t = tid; t < stride; t += CHI_SM_THREADS) {
-    double v = 0.0;
-    int c = 0;
-    for (; c + 4 <= a.n_chunks; c += 4) {  // four loads in flight, summed in chunk order
-      const double* p = rec0 + (int64_t)c * stride + t;
-      const double v0 = __ldcg(p), v1 = __ldcg(p + stride), v2 = __ldcg(p + 2 * (int64_t)stride),
-                   v3 = __ldcg(p + 3 * (int64_t)stride);
-      v = (((v + v0) + v1) + v2) + v3;
+  if (CHAIN) {
+    // the block's record is the draw's record (0 + v, as the general form sums a single chunk)
+    for (int t = tid; t < stride; t += CHI_SM_THREADS) {
+      double v = 0.0;
+      for (int w = 0; w < ncw; ++w) v += s_red[w][t];
+      s_sum[t] = 0.0 + v;
     }
-    for (; c < a.n_chunks; ++c) v += __ldcg(rec0 + (int64_t)c * stride + t);
-    s_sum[t] = v;
+  } else {
+    // channel-warp partials in fixed order -> the (draw, chunk) record
+    double* rec = a.mom + (b * a.n_chunks + chunk) * stride;
+    for (int t = tid; t < stride; t += CHI_SM_THREADS) {
+      double v = 0.0;
+      for (int w = 0; w < ncw; ++w) v += s_red[w][t];
+      rec[t] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned done = atomicAdd(a.counter + b, 1u);
+      s_last = (done == (unsigned)a.n_chunks - 1u);
+      if (s_last) a.counter[b] = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (a.stamps && b == 0 && chunk == 0 && tid == 0) a.stamps[4] = clock64() - t_0;
+    if (!s_last) return;
+    __threadfence();
+
+    // ---- this block completed the draw: chunk sums in fixed order, then the contraction ----
+    const double* rec0 = a.mom + (b * a.n_chunks) * stride;
+    for (int t = tid; t < stride; t += CHI_SM_THREADS) {
+      double v = 0.0;
+      int c = 0;
+      for (; c + 4 <= a.n_chunks; c += 4) {  // four loads in flight, summed in chunk order
+        const double* p = rec0 + (int64_t)c * stride + t;
+        const double v0 = __ldcg(p), v1 = __ldcg(p + stride), v2 = __ldcg(p + 2 * (int64_t)stride),
+                     v3 = __ldcg(p + 3 * (int64_t)stride);
+        v = (((v + v0) + v1) + v2) + v3;
+      }
+      for (; c < a.n_chunks; ++c) v += __ldcg(rec0 + (int64_t)c * stride + t);
+      s_sum[t] = v;
+    }
   }
   // the per-cloud prior terms of the draw (written by the Jacobian warps of its blocks)
   if (a.prior && tid < N) s_red[0][tid] = __ldcg(a.prior_buf + b * N + tid);
@@ -697,6 +751,17 @@ __global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(
     for (int s = a.K; s < CHI_NSLOT; ++s)
       if (a.rm.row[s] >= 0) go[(int64_t)a.rm.row[s] * N] = 0.0;
   if (a.stamps && tid == 0) a.stamps[6] = clock64() - t_0;
+}
+
+template <int NL, bool PV>
+__global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(MapCfg cfg, SmallArgs a) {
+  __shared__ SmSmem S;
+  extern __shared__ double s_gb_dyn[];  // (nb_e - 1 + nb_a - 1) x CHI_SM_THREADS when baselines have > 1 term
+  const int64_t b = blockIdx.x / a.n_chunks;
+  const int chunk = (int)(blockIdx.x - b * a.n_chunks);
+  sm_init(S, cfg, a.rm);
+  sm_eval<NL, PV, false>(S, s_gb_dyn, a, b, chunk, a.theta + (b * a.rm.n_rows) * a.N,
+                         a.coeff_e ? a.coeff_e + b * a.nb_e : nullptr, a.coeff_a ? a.coeff_a + b * a.nb_a : nullptr);
 }
 
 }  // namespace chi

@@ -462,8 +462,13 @@ int64_t chi_launch_count(const chi_handle* h);
 #define CHI_OPT_SMALL_CHUNKS 2
 #define CHI_OPT_SMALL_STAMPS 3 /* development aid: device pointer to 16 int64 receiving SM-clock offsets
                                   of block 0's phases (0 = off) */
-#define CHI_OPT_NUTS_TICK 4    /* 0 = the sampler's common tick staged in shared memory (default), 1 = every
-                                  phase through global memory (round-1 form; same draws bit for bit) */
+#define CHI_OPT_NUTS_TICK 4    /* how chi_nuts_sample runs a tick of its free-running chains:
+                                  0 = by model size (default): 3 for small models, 2 otherwise;
+                                  1 = a CUDA graph of kernels per tick, the tick passing every phase through global
+                                      memory (round-1 form; same draws as 2 bit for bit);
+                                  2 = that graph with the common tick staged in shared memory;
+                                  3 = one resident block per chain runs whole leapfrog steps tick after tick inside
+                                      one kernel (csrc/nuts_chain.cuh), whenever the model fits (<= 16 clouds) */
 #define CHI_OPT_DEV_OVERLAP 5  /* 1 = consecutive chi_logp_grad[_rows]_dev calls of large batches alternate between
                                   two internal lanes and may overlap (map / epilogue of one call next to the channel
                                   kernel of the other); each call still starts after everything enqueued on the

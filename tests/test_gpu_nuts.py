@@ -119,27 +119,53 @@ def test_lock_step_and_asynchronous_chains_agree(cuda_device):
     assert abs(runs["async"][1]["accept"].mean() - runs["lock"][1]["accept"].mean()) < 0.1
 
 
-@pytest.mark.parametrize("kind_n", [("emission_absorption", 2), ("emission_absorption_physical", 3)])
-def test_tick_variants_agree(cuda_device, kind_n):
-    """The sampler's common tick staged in shared memory (default) does the same operations in the same
-    order as the round-1 form that passes every phase through global memory: identical draws and statistics."""
+def _sample_with(kind, N, options, chains=6, draws=40, tune=60, shared=False):
     from caribou_hi_b200 import EmissionAbsorptionModel, EmissionAbsorptionPhysicalModel, SpecData
 
-    kind, N = kind_n
     cls = EmissionAbsorptionModel if kind == "emission_absorption" else EmissionAbsorptionPhysicalModel
-    rng = np.random.default_rng(2)
-    ve, va = np.linspace(-40, 40, 96), np.linspace(-20, 20, 48)
-    out = []
-    for tick in (0, 1):
-        model = cls({"emission": SpecData(ve, rng.normal(5, 1, 96) * 0 + 5.0, 0.5), "absorption": SpecData(va, np.full(48, 0.2), 0.05)},
-                    N, baseline_degree=1)
-        model.add_priors(prior_fwhm_L=1.0) if kind.endswith("physical") else model.add_priors()
-        model.add_likelihood()
-        model.engine.set_option("nuts_tick", tick)
-        post, stats = model.sample(draws=40, tune=60, chains=6, seed=4)
-        out.append((post, stats))
-        model.engine.close()
-    for k in out[0][0]:
-        assert np.array_equal(out[0][0][k], out[1][0][k], equal_nan=True), k
-    for k in out[0][1]:
-        assert np.array_equal(out[0][1][k], out[1][1][k], equal_nan=True), k
+    ve = np.linspace(-40, 40, 96)
+    va = ve if shared else np.linspace(-20, 20, 48)
+    model = cls({"emission": SpecData(ve, np.full(96, 5.0), 0.5), "absorption": SpecData(va, np.full(va.size, 0.2), 0.05)},
+                N, baseline_degree=1)
+    model.add_priors(prior_fwhm_L=1.0) if kind.endswith("physical") else model.add_priors()
+    model.add_likelihood()
+    for name, value in options.items():
+        model.engine.set_option(name, value)
+    n0 = model.engine.launch_count()
+    post, stats = model.sample(draws=draws, tune=tune, chains=chains, seed=4)
+    launches = model.engine.launch_count() - n0
+    model.engine.close()
+    return post, stats, launches
+
+
+def _same_run(a, b):
+    for k in a[0]:
+        assert np.array_equal(a[0][k], b[0][k], equal_nan=True), k
+    for k in a[1]:
+        assert np.array_equal(a[1][k], b[1][k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("kind_n", [("emission_absorption", 2), ("emission_absorption_physical", 3)])
+def test_tick_variants_agree(cuda_device, kind_n):
+    """The sampler's common tick staged in shared memory (nuts_tick 2) does the same operations in the same
+    order as the round-1 form that passes every phase through global memory (1): identical draws and
+    statistics."""
+    kind, N = kind_n
+    _same_run(_sample_with(kind, N, {"nuts_tick": 2}), _sample_with(kind, N, {"nuts_tick": 1}))
+
+
+@pytest.mark.parametrize("kind_n_shared", [("emission_absorption", 2, False), ("emission_absorption", 2, True),
+                                           ("emission_absorption_physical", 3, True), ("emission_absorption_physical", 6, False)])
+def test_chain_kernel_matches_the_graph_of_kernels(cuda_device, kind_n_shared):
+    """The per-chain kernel (nuts_chain.cuh: one resident block runs whole leapfrog steps tick after tick; the
+    default for small models) against the graph of two kernels per tick it fuses -- the staged tick and the
+    one-launch evaluation with one block per draw: the same operations in the same order, so identical draws
+    and statistics, from a handful of launches instead of thousands."""
+    kind, N, shared = kind_n_shared
+    chain = _sample_with(kind, N, {"nuts_tick": 3}, shared=shared)
+    graph = _sample_with(kind, N, {"nuts_tick": 2, "small_path": 2, "small_chunks": 1}, shared=shared)
+    _same_run(chain, graph)
+    assert chain[2] < 60 and graph[2] > 20 * chain[2], (chain[2], graph[2])
+    auto = _sample_with(kind, N, {}, shared=shared)  # this size takes the chain kernel by itself
+    _same_run(chain, auto)
+    assert auto[2] == chain[2]
