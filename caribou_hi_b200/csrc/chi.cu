@@ -28,8 +28,8 @@
 
 using namespace chi;
 namespace chi {
-int launch_nuts_chain(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
-                      int max_ticks, size_t dyn_smem, cudaStream_t st);  // launch_chain.cu
+int launch_nuts_chain(int NL, int threads, bool pv, const MapCfg& cfg, const SmallArgs& a, const NutsState& s,
+                      const NutsAsync& A, int max_ticks, size_t dyn_smem, cudaStream_t st);  // launch_chain.cu
 }
 
 namespace {
@@ -317,7 +317,7 @@ bool use_eval_small(const chi_handle* h, int64_t B, bool vjp) {
 // argument block of k_eval_small / k_nuts_chain for a batch; force_chunks > 0 fixes the blocks per draw
 int small_args(chi_handle* h, Lane& L, int64_t B, const double* theta, const double* ce, const double* ca,
                const int32_t* sl, double* logp, double* grad, double* gce, double* gca, bool model, int force_chunks,
-               SmallArgs* out, int* NL_out, size_t* dyn_smem_out) {
+               SmallArgs* out, int* NL_out, size_t* dyn_smem_out, int threads = CHI_SM_THREADS) {
   const int N = h->cfg.n_clouds;
   const bool pv = h->cfg.lorentzian != 0;
   SmallArgs& a = *out;
@@ -376,7 +376,7 @@ int small_args(chi_handle* h, Lane& L, int64_t B, const double* theta, const dou
   for (int i = 0; i < a.nb_a && model; ++i) a.bprior_const += -log(h->bsig_a[i]) - CHI_HALF_LOG_2PI;
   const int n_gb = (a.nb_e > 1 ? a.nb_e - 1 : 0) + (a.nb_a > 1 ? a.nb_a - 1 : 0);
   *NL_out = NL;
-  *dyn_smem_out = (size_t)n_gb * CHI_SM_THREADS * sizeof(double);
+  *dyn_smem_out = (size_t)n_gb * threads * sizeof(double);
   return CHI_OK;
 }
 
@@ -387,19 +387,27 @@ int small_args(chi_handle* h, Lane& L, int64_t B, const double* theta, const dou
 //   8 clouds x 2048+2048 channels, pseudo-Voigt, 64 chains:     graph 43   chain kernel 86
 // i.e. chain ~ 10 + 3.1 w, graph ~ 26 + 0.7 w with w = clouds x channels (x 1.5 pseudo-Voigt) in thousands: the
 // crossover is near w = 6.5.
+// With 512 threads per chain (one block per SM, <= 8 clouds) a tick has twice the channel warps: the chain line
+// becomes ~ 9 + 1.7 w.
 // CHI_OPT_NUTS_TICK: 0 = by size, 1 = graph with the round-1 tick, 2 = graph with the staged tick, 3 = the chain
-// kernel whenever it can run.
+// kernel with 256 threads whenever it can run (bit-identical to 2 + the one-launch evaluation with one block per
+// draw), 4 = the chain kernel with 512 threads where it can (else 256).
 #define CHI_CHAIN_TICKS 2048
-bool use_nuts_chain(const chi_handle* h, int64_t B) {
+// threads per chain of the chain kernel, 0 = the graph of kernels runs instead
+int nuts_chain_threads(const chi_handle* h, int64_t B) {
   const int64_t mode = h->opt[CHI_OPT_NUTS_TICK];
-  if (mode == 1 || mode == 2) return false;
-  if (getenv("CHI_NUTS_THREAD")) return false;
+  if (mode == 1 || mode == 2) return 0;
+  if (getenv("CHI_NUTS_THREAD")) return 0;
   const int N = h->cfg.n_clouds;
-  if (N * CHI_NSLOT > CHI_SM_THREADS - 96) return false;
-  if (mode == 3) return true;
+  if (N * CHI_NSLOT > CHI_SM_THREADS - 96) return 0;
+  const bool wide_ok = N <= 8 && B <= (int64_t)h->n_sm;
+  if (mode == 3) return CHI_SM_THREADS;
+  if (mode == 4) return wide_ok ? 512 : CHI_SM_THREADS;
   const int64_t S = std::max(h->has_e ? h->e.S : 0, h->has_a ? h->a.S : 0);
   const int64_t work = (int64_t)N * S * (h->cfg.lorentzian ? 3 : 2) / 2;
-  return work <= 6500 && B <= 8 * (int64_t)h->n_sm;
+  if (B > 8 * (int64_t)h->n_sm) return 0;
+  if (wide_ok && work <= 14000) return 512;
+  return work <= 6500 ? CHI_SM_THREADS : 0;
 }
 
 int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const double* ce, const double* ca,
@@ -2337,13 +2345,14 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   k_nuts_init<<<grid, 64, 0, st>>>(s, (unsigned long long)cfg->seed, eps0);
   // the per-chain kernel (nuts_chain.cuh) evaluates a draw with one block; the starting point goes through the
   // same arithmetic (k_eval_small, one block per draw)
-  const bool chain_kernel = !lock_step && use_nuts_chain(h, B);
+  const int chain_threads = lock_step ? 0 : nuts_chain_threads(h, B);
+  const bool chain_kernel = chain_threads != 0;
   SmallArgs chain_args;
   int chain_nl = 1;
   size_t chain_dyn = 0;
   if (chain_kernel) {
     rc = small_args(h, h->lanes[0], B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, s.elogp, s.egu,
-                    nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, 1, &chain_args, &chain_nl, &chain_dyn);
+                    nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, 1, &chain_args, &chain_nl, &chain_dyn, chain_threads);
     if (rc) return rc;
     if (chain_args.n_chunks != 1) return fail(h, CHI_ECUDA, "chi_nuts_sample: the chain kernel needs one block per draw");
     if (launch_eval_small(chain_nl, h->cfg.lorentzian != 0, h->map, chain_args, chain_dyn, st))
@@ -2404,7 +2413,7 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
       int64_t ticks = 0;
       h_flags[0] = 0;
       while (h_flags[0] < B && ticks < tick_cap) {
-        if (launch_nuts_chain(chain_nl, h->cfg.lorentzian != 0, h->map, chain_args, s, A, CHI_CHAIN_TICKS, chain_dyn, st))
+        if (launch_nuts_chain(chain_nl, chain_threads, h->cfg.lorentzian != 0, h->map, chain_args, s, A, CHI_CHAIN_TICKS, chain_dyn, st))
           return fail(h, CHI_EINVAL, "unsupported configuration of the chain kernel");
         CK(cudaGetLastError());
         ticks += CHI_CHAIN_TICKS;

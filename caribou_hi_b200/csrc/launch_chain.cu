@@ -9,34 +9,35 @@
 namespace chi {
 namespace {
 template <int NL, bool PV>
-int run_chain(const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks, size_t gb_bytes,
-              cudaStream_t st) {
-  k_nuts_chain<NL, PV><<<(unsigned)a.B, CHI_SM_THREADS, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
+int run_chain(int threads, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
+              size_t gb_bytes, cudaStream_t st) {
+  if (threads == 512) k_nuts_chain<NL, PV, 512><<<(unsigned)a.B, 512, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
+  else k_nuts_chain<NL, PV, CHI_SM_THREADS><<<(unsigned)a.B, CHI_SM_THREADS, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
   return 0;
 }
 }  // namespace
 
 #if CHI_CHAIN_PV
-int launch_nuts_chain_pv(int NL, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
+int launch_nuts_chain_pv(int NL, int threads, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
                          size_t gb_bytes, cudaStream_t st) {
 #else
-int launch_nuts_chain_pv(int NL, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
+int launch_nuts_chain_pv(int NL, int threads, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
                          size_t gb_bytes, cudaStream_t st);
-static int launch_nuts_chain_g(int NL, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
+static int launch_nuts_chain_g(int NL, int threads, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
                                int max_ticks, size_t gb_bytes, cudaStream_t st) {
 #endif
   constexpr bool PV = CHI_CHAIN_PV != 0;
   switch (NL) {
-    case 1: return run_chain<1, PV>(cfg, a, s, A, max_ticks, gb_bytes, st);
-    case 2: return run_chain<2, PV>(cfg, a, s, A, max_ticks, gb_bytes, st);
+    case 1: return run_chain<1, PV>(threads, cfg, a, s, A, max_ticks, gb_bytes, st);
+    case 2: return run_chain<2, PV>(threads, cfg, a, s, A, max_ticks, gb_bytes, st);
   }
   return -1;
 }
 #if !CHI_CHAIN_PV
-int launch_nuts_chain(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
+int launch_nuts_chain(int NL, int threads, bool pv, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
                       int max_ticks, size_t gb_bytes, cudaStream_t st) {
-  return pv ? launch_nuts_chain_pv(NL, cfg, a, s, A, max_ticks, gb_bytes, st)
-            : launch_nuts_chain_g(NL, cfg, a, s, A, max_ticks, gb_bytes, st);
+  return pv ? launch_nuts_chain_pv(NL, threads, cfg, a, s, A, max_ticks, gb_bytes, st)
+            : launch_nuts_chain_g(NL, threads, cfg, a, s, A, max_ticks, gb_bytes, st);
 }
 #endif
 }  // namespace chi

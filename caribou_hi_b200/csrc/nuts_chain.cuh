@@ -23,9 +23,12 @@
 
 namespace chi {
 
-template <int NL, bool PV>
-__global__ void __launch_bounds__(CHI_SM_THREADS, 2) k_nuts_chain(MapCfg cfg, SmallArgs a, NutsState s, NutsAsync A, int max_ticks) {
-  __shared__ SmSmem S;
+// NT = 256: two blocks per SM, any model; NT = 512: one block per SM with twice the channel warps (a tick of a
+// 2-cloud model is 3 rounds of channel tiles instead of 5), at most 8 clouds.  The partition of the channels over
+// the warps differs, so the two forms agree to rounding, not bit for bit.
+template <int NL, bool PV, int NT>
+__global__ void __launch_bounds__(NT, NT == CHI_SM_THREADS ? 2 : 1) k_nuts_chain(MapCfg cfg, SmallArgs a, NutsState s, NutsAsync A, int max_ticks) {
+  __shared__ SmSmemT<NT> S;
   __shared__ double s_stage[5][CHI_NUTS_MAXD];
   __shared__ double s_point[CHI_NUTS_MAXD];  // the evaluation point: theta block [CHI_NSLOT][N], then the coefficients
   __shared__ int s_go;
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(CHI_SM_THREADS, 2) k_nuts_chain(MapCfg cfg, Sm
     __syncthreads();
     const long long t1 = a.stamps ? clock64() : 0;
     if (!s_go) break;
-    sm_eval<NL, PV, true>(S, s_gb_dyn, a, b, 0, s_point, s.nbe ? s_point + nu : nullptr,
+    sm_eval<NL, PV, true, NT>(S, s_gb_dyn, a, b, 0, s_point, s.nbe ? s_point + nu : nullptr,
                           s.nba ? s_point + nu + s.nbe : nullptr);
     __syncthreads();  // logp and the gradient of the point are in global memory for warp 0's next tick
     if (a.stamps) { c_tick += t1 - t0; c_eval += clock64() - t1; ++n_tick; }

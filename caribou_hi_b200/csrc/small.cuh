@@ -175,6 +175,7 @@ __device__ __forceinline__ double sm_chan_sum(int lgG, double x) {
 struct SmCtx {
   int lane, g, cl, cpw;  // lane, cloud group, channel within the warp tile, channels per warp tile
   int cw, ncw;           // channel-warp index and count
+  int nt;                // threads of the block
   int lgG;
   const ExpCtx* ek;
 };
@@ -246,10 +247,10 @@ __device__ __forceinline__ void sm_loop_ea(const SmCtx& x, const SmallArgs& a, c
     v3[2] = fma(mba, pa0, v3[2]);
     if (x.g == 0) {
       _Pragma("unroll 1") for (int i = 1; i < nbe; ++i)
-        s_gb[(i - 1) * CHI_SM_THREADS] = fma(mbe, a.basis_e[(int64_t)i * S + sx], s_gb[(i - 1) * CHI_SM_THREADS]);
+        s_gb[(i - 1) * x.nt] = fma(mbe, a.basis_e[(int64_t)i * S + sx], s_gb[(i - 1) * x.nt]);
       _Pragma("unroll 1") for (int i = 1; i < nba; ++i)
-        s_gb[((nbe > 1 ? nbe - 1 : 0) + i - 1) * CHI_SM_THREADS] =
-            fma(mba, a.basis_a[(int64_t)i * S + sx], s_gb[((nbe > 1 ? nbe - 1 : 0) + i - 1) * CHI_SM_THREADS]);
+        s_gb[((nbe > 1 ? nbe - 1 : 0) + i - 1) * x.nt] =
+            fma(mba, a.basis_a[(int64_t)i * S + sx], s_gb[((nbe > 1 ? nbe - 1 : 0) + i - 1) * x.nt]);
     }
     const double ga = mba * ea;
 #pragma unroll
@@ -341,7 +342,7 @@ __device__ __forceinline__ void sm_loop_em(const SmCtx& x, const SmallArgs& a, c
     v3[1] = fma(mubar, p0, v3[1]);
     if (x.g == 0)
       _Pragma("unroll 1") for (int i = 1; i < nb; ++i)
-        s_gb[(i - 1) * CHI_SM_THREADS] = fma(mubar, a.basis_e[(int64_t)i * S + sx], s_gb[(i - 1) * CHI_SM_THREADS]);
+        s_gb[(i - 1) * x.nt] = fma(mubar, a.basis_e[(int64_t)i * S + sx], s_gb[(i - 1) * x.nt]);
 #pragma unroll
     for (int i = NL - 1; i >= 0; --i) {
       const double Pn = front * Pl[i];
@@ -414,8 +415,8 @@ __device__ __forceinline__ void sm_loop_abs(const SmCtx& x, const SmallArgs& a, 
     v3[2] = fma(mubar, p0, v3[2]);
     if (x.g == 0)
       _Pragma("unroll 1") for (int i = 1; i < nb; ++i)
-        s_gb[((a.nb_e > 1 ? a.nb_e - 1 : 0) + i - 1) * CHI_SM_THREADS] =
-            fma(mubar, a.basis_a[(int64_t)i * S + sx], s_gb[((a.nb_e > 1 ? a.nb_e - 1 : 0) + i - 1) * CHI_SM_THREADS]);
+        s_gb[((a.nb_e > 1 ? a.nb_e - 1 : 0) + i - 1) * x.nt] =
+            fma(mubar, a.basis_a[(int64_t)i * S + sx], s_gb[((a.nb_e > 1 ? a.nb_e - 1 : 0) + i - 1) * x.nt]);
     const double g = mubar * ea;
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
@@ -453,24 +454,29 @@ __device__ __forceinline__ void sm_store_acc(const SmCtx& x, double (&acc)[NL][M
 // then NP x NF fused moments, or NP x NE emission moments followed by NP x NA absorption moments
 // (NP = NL 2^lgG clouds, the model's N first)
 // ---------------------------------------------------------------------------------------------------
-// shared memory of one block (the sizes do not depend on the instantiation)
-struct SmSmem {
+// shared memory of one block of NT threads.  NT = 256: any model (<= CHI_MAX_CLOUDS clouds); NT = 512 (the chain
+// kernel's wide form): at most 8 clouds (NL 2^lgG = 8), so that twice the warp rows fit the same space.
+template <int NT>
+struct SmSmemT {
+  static constexpr int RW = 1 + 2 * CHI_MAX_BASELINE + (NT == CHI_SM_THREADS ? CHI_MAX_CLOUDS : 8) * 14 + 2;  // doubles per warp row
   double T[CHI_EXP_TABLE];
   double cc[CHI_MAX_CLOUDS * 2 * CHI_SM_CCS];  // NL 2^lgG <= 32 clouds
   double beta[2 * CHI_MAX_BASELINE];
-  double red[CHI_SM_WARPS][CHI_SM_MAXREC + 2];
+  double red[NT / 32][RW];
   double sum[CHI_SM_MAXREC + 2];
   Transformed tr[CHI_MAX_CLOUDS * CHI_NSLOT];  // [cloud][slot] (prior mode)
   MapCfg cfg;
   RowMap rm;
   int last;
 };
+typedef SmSmemT<CHI_SM_THREADS> SmSmem;
 
 // once per block: exponential table and the map's configuration
-__device__ __forceinline__ void sm_init(SmSmem& S, const MapCfg& cfg, const RowMap& rm) {
+template <int NT>
+__device__ __forceinline__ void sm_init(SmSmemT<NT>& S, const MapCfg& cfg, const RowMap& rm) {
   const int tid = threadIdx.x;
   if (tid == 0) { S.cfg = cfg; S.rm = rm; }
-  for (int i = tid; i < CHI_EXP_TABLE; i += CHI_SM_THREADS) S.T[i] = g_exp2_table[CHI_EXP_REPL ? (i >> 4) << 3 : i];
+  for (int i = tid; i < CHI_EXP_TABLE; i += NT) S.T[i] = g_exp2_table[CHI_EXP_REPL ? (i >> 4) << 3 : i];
 }
 
 // One (draw, chunk) of the evaluation by the whole block; the first statement after sm_init (or after the
@@ -478,14 +484,14 @@ __device__ __forceinline__ void sm_init(SmSmem& S, const MapCfg& cfg, const RowM
 // baseline coefficients (global or shared memory; null = no coefficients).
 // CHAIN (nuts_chain.cuh: one block evaluates the same chain tick after tick, n_chunks == 1): the block's
 // record is the draw's record, so it stays in shared memory -- no record in global memory, no counter.
-template <int NL, bool PV, bool CHAIN>
-__device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const SmallArgs& a, const int64_t b, const int chunk,
+template <int NL, bool PV, bool CHAIN, int NT = CHI_SM_THREADS>
+__device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const SmallArgs& a, const int64_t b, const int chunk,
                                         const double* tb, const double* ce_b, const double* ca_b) {
   constexpr int NF = PV ? 10 : 6, NE = PV ? 8 : 5, NA = PV ? 6 : 3;
   double* const s_T = S.T;
   double* const s_cc = S.cc;
   double* const s_beta = S.beta;
-  double(*const s_red)[CHI_SM_MAXREC + 2] = S.red;
+  double(*const s_red)[SmSmemT<NT>::RW] = S.red;
   double* const s_sum = S.sum;
   MapCfg& s_cfg = S.cfg;
   RowMap& s_rm = S.rm;
@@ -496,7 +502,7 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
   const int nbe = a.nb_e, nba = a.nb_a;
 
   // null clouds pad the lane groups: tau = 0, f = 0
-  for (int i = tid; i < NP * CHI_SM_CCS; i += CHI_SM_THREADS) {
+  for (int i = tid; i < NP * CHI_SM_CCS; i += NT) {
     const int k = i % CHI_SM_CCS;
     s_cc[i] = (k == CC_KE || k == CC_KA || k == CC_HE || k == CC_HA) ? 1.0 : 0.0;
   }
@@ -508,7 +514,7 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
     s_beta[tid] = (c && i < nb) ? c[i] : 0.0;
   }
   const int n_gb = (nbe > 1 ? nbe - 1 : 0) + (nba > 1 ? nba - 1 : 0);
-  for (int i = 0; i < n_gb; ++i) s_gb_dyn[i * CHI_SM_THREADS + tid] = 0.0;
+  for (int i = 0; i < n_gb; ++i) s_gb_dyn[i * NT + tid] = 0.0;
   __syncthreads();
   if (a.prior) {
     // the transforms of the draw's free RVs, one thread each (the channel warps have nothing else to do yet)
@@ -521,10 +527,10 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
   }
 
   // ---- map (warp 0) next to the Jacobian records of this block (last warps) ----
-  const int ncw = CHI_SM_WARPS - a.jac_warps;  // channel warps
+  const int ncw = (NT / 32) - a.jac_warps;  // channel warps
   // the draw's likelihood constant, fetched early by the thread that writes logp at the very end
   double lconst_b = 0.0;
-  if (tid == CHI_SM_THREADS - 32 && a.lconst) lconst_b = __ldg(a.lconst + (a.sl ? a.sl[b] : 0));
+  if (tid == NT - 32 && a.lconst) lconst_b = __ldg(a.lconst + (a.sl ? a.sl[b] : 0));
   long long t_0 = 0, t_map = 0, t_jac = 0, t_chan = 0;
   if (a.stamps) t_0 = clock64();
   if (warp == 0 && lane < N)
@@ -553,7 +559,7 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
     const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
     SmCtx x;
     x.lane = lane; x.lgG = a.lgG; x.g = lane & (G - 1); x.cl = lane >> a.lgG; x.cpw = 32 >> a.lgG;
-    x.cw = warp; x.ncw = ncw; x.ek = &ek;
+    x.cw = warp; x.ncw = ncw; x.nt = NT; x.ek = &ek;
     const int sl = a.sl ? a.sl[b] : 0;
     double v3[3] = {0.0, 0.0, 0.0};
     double* gb = s_gb_dyn + tid;
@@ -599,23 +605,23 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
       if (nba > 0) red[1 + nbe] = g0a;
     }
     _Pragma("unroll 1") for (int i = 1; i < nbe; ++i) {
-      const double t = sm_chan_sum(a.lgG, x.g == 0 ? gb[(i - 1) * CHI_SM_THREADS] : 0.0);
+      const double t = sm_chan_sum(a.lgG, x.g == 0 ? gb[(i - 1) * NT] : 0.0);
       if (lane == 0) red[1 + i] = t;
     }
     _Pragma("unroll 1") for (int i = 1; i < nba; ++i) {
-      const double t = sm_chan_sum(a.lgG, x.g == 0 ? gb[((nbe > 1 ? nbe - 1 : 0) + i - 1) * CHI_SM_THREADS] : 0.0);
+      const double t = sm_chan_sum(a.lgG, x.g == 0 ? gb[((nbe > 1 ? nbe - 1 : 0) + i - 1) * NT] : 0.0);
       if (lane == 0) red[1 + nbe + i] = t;
     }
   }
   if (a.stamps) t_chan = clock64();
   __syncthreads();
-  if (a.stamps && b == 0 && chunk == 0 && lane == 0 && (warp == 0 || warp == CHI_SM_WARPS - 1)) {
+  if (a.stamps && b == 0 && chunk == 0 && lane == 0 && (warp == 0 || warp == (NT / 32) - 1)) {
     long long* o = a.stamps + (warp == 0 ? 0 : 8);
     o[0] = t_map - t_0; o[1] = t_jac - t_0; o[2] = t_chan - t_0; o[3] = clock64() - t_0;
   }
   if (CHAIN) {
     // the block's record is the draw's record (0 + v, as the general form sums a single chunk)
-    for (int t = tid; t < stride; t += CHI_SM_THREADS) {
+    for (int t = tid; t < stride; t += NT) {
       double v = 0.0;
       for (int w = 0; w < ncw; ++w) v += s_red[w][t];
       s_sum[t] = 0.0 + v;
@@ -623,7 +629,7 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
   } else {
     // channel-warp partials in fixed order -> the (draw, chunk) record
     double* rec = a.mom + (b * a.n_chunks + chunk) * stride;
-    for (int t = tid; t < stride; t += CHI_SM_THREADS) {
+    for (int t = tid; t < stride; t += NT) {
       double v = 0.0;
       for (int w = 0; w < ncw; ++w) v += s_red[w][t];
       rec[t] = v;
@@ -642,7 +648,7 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
 
     // ---- this block completed the draw: chunk sums in fixed order, then the contraction ----
     const double* rec0 = a.mom + (b * a.n_chunks) * stride;
-    for (int t = tid; t < stride; t += CHI_SM_THREADS) {
+    for (int t = tid; t < stride; t += NT) {
       double v = 0.0;
       int c = 0;
       for (; c + 4 <= a.n_chunks; c += 4) {  // four loads in flight, summed in chunk order
@@ -673,7 +679,7 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
       if (a.gca) a.gca[b * nba + k] = g;
     }
   }
-  if (tid == CHI_SM_THREADS - 32 && a.logp) {
+  if (tid == NT - 32 && a.logp) {
     double lp = s_sum[0];
     if (a.prior) {
       // Normal(0, sigma_i) priors of the baseline coefficients; bprior_const = sum(-log sigma_i - .5 log 2 pi)
@@ -692,7 +698,7 @@ __device__ __forceinline__ void sm_eval(SmSmem& S, double* s_gb_dyn, const Small
       for (int n = 0; n < N; ++n) lp += s_red[0][n];
     a.logp[b] = lp;
   }
-  if (a.stamps && tid == CHI_SM_THREADS - 32) a.stamps[5] = clock64() - t_0;
+  if (a.stamps && tid == NT - 32) a.stamps[5] = clock64() - t_0;
   if (!a.want_grad || !a.grad || tid >= N * a.K) return;
 
   const int n = tid / a.K, j0 = tid - n * a.K;

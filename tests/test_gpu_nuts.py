@@ -166,6 +166,13 @@ def test_chain_kernel_matches_the_graph_of_kernels(cuda_device, kind_n_shared):
     graph = _sample_with(kind, N, {"nuts_tick": 2, "small_path": 2, "small_chunks": 1}, shared=shared)
     _same_run(chain, graph)
     assert chain[2] < 60 and graph[2] > 20 * chain[2], (chain[2], graph[2])
-    auto = _sample_with(kind, N, {}, shared=shared)  # this size takes the chain kernel by itself
-    _same_run(chain, auto)
-    assert auto[2] == chain[2]
+    # a model this small takes the chain kernel by itself, in its wide form (512 threads per chain: the channels
+    # are spread over twice the warps, so the sums agree with the 256-thread form to rounding and the chains part
+    # ways after a while; the first draws of the warm-up still agree closely)
+    auto = _sample_with(kind, N, {}, shared=shared)
+    wide = _sample_with(kind, N, {"nuts_tick": 4}, shared=shared)
+    _same_run(auto, wide)
+    assert auto[2] < 60
+    for k in ("accept", "depth"):
+        assert np.all(np.isfinite(auto[1][k]))
+    assert abs(auto[1]["accept"].mean() - chain[1]["accept"].mean()) < 0.25, (auto[1]["accept"].mean(), chain[1]["accept"].mean())

@@ -20,7 +20,7 @@ data = {"emission": SpecData(ve, mu["emission"][0] + 0.1 * rng.standard_normal(S
 model = EmissionAbsorptionModel(data, N, baseline_degree=0)
 model.add_priors(); model.add_likelihood()
 stamps = torch.zeros(16, dtype=torch.int64, device="cuda")
-model.engine.set_option("nuts_tick", 3)
+model.engine.set_option("nuts_tick", int(os.environ.get("NUTS_TICK", 3)))
 model.engine.set_option("small_stamps", stamps.data_ptr())
 import time
 t0 = time.perf_counter()
