@@ -11,8 +11,13 @@ namespace {
 template <int NL, bool PV>
 int run_chain(int threads, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
               size_t gb_bytes, cudaStream_t st) {
-  if (threads == 512) k_nuts_chain<NL, PV, 512><<<(unsigned)a.B, 512, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
-  else k_nuts_chain<NL, PV, CHI_SM_THREADS><<<(unsigned)a.B, CHI_SM_THREADS, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
+  if (threads == 512) {
+    if (sm_allow_dyn(k_nuts_chain<NL, PV, 512>, gb_bytes)) return -2;
+    k_nuts_chain<NL, PV, 512><<<(unsigned)a.B, 512, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
+  } else {
+    if (sm_allow_dyn(k_nuts_chain<NL, PV, CHI_SM_THREADS>, gb_bytes)) return -2;
+    k_nuts_chain<NL, PV, CHI_SM_THREADS><<<(unsigned)a.B, CHI_SM_THREADS, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
+  }
   return 0;
 }
 }  // namespace

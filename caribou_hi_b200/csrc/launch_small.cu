@@ -18,8 +18,14 @@ static int launch_eval_small_g(int NL, const MapCfg& cfg, const SmallArgs& a, si
   constexpr bool PV = CHI_SMALL_PV != 0;
   const unsigned grid = (unsigned)(a.B * a.n_chunks);
   switch (NL) {
-    case 1: k_eval_small<1, PV><<<grid, CHI_SM_THREADS, dyn_smem, st>>>(cfg, a); return 0;
-    case 2: k_eval_small<2, PV><<<grid, CHI_SM_THREADS, dyn_smem, st>>>(cfg, a); return 0;
+    case 1:
+      if (sm_allow_dyn(k_eval_small<1, PV>, dyn_smem)) return -2;
+      k_eval_small<1, PV><<<grid, CHI_SM_THREADS, dyn_smem, st>>>(cfg, a);
+      return 0;
+    case 2:
+      if (sm_allow_dyn(k_eval_small<2, PV>, dyn_smem)) return -2;
+      k_eval_small<2, PV><<<grid, CHI_SM_THREADS, dyn_smem, st>>>(cfg, a);
+      return 0;
   }
   return -1;
 }

@@ -759,6 +759,14 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
   if (a.stamps && tid == 0) a.stamps[6] = clock64() - t_0;
 }
 
+// Static + dynamic shared memory of these kernels passes the 48 KB a launch gets by default once the baselines
+// have several terms (one column of CHI_SM_THREADS doubles per extra term): the opt-in is raised when needed.
+template <class Kernel>
+inline int sm_allow_dyn(Kernel kernel, size_t dyn_smem) {
+  if (dyn_smem <= 2048) return 0;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem) != cudaSuccess;
+}
+
 template <int NL, bool PV>
 __global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(MapCfg cfg, SmallArgs a) {
   __shared__ SmSmem S;

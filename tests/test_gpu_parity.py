@@ -670,3 +670,16 @@ def test_negative_depths_in_a_large_batch(cuda_device, sightlines):
             continue
         assert_close(got[name][fin], ref_g[name][fin], what=f"d/d{name} of a batch with marked draws")
     eng.close()
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_many_baseline_terms_on_the_small_paths(cuda_device, shared):
+    """Baselines of degree 7 (CHI_MAX_BASELINE terms per dataset): the one-launch kernel keeps one column of
+    per-thread sums per extra term in dynamic shared memory, 28 KB here on top of its 36 KB of static arrays --
+    past the 48 KB a launch gets without the opt-in (csrc/small.cuh: sm_allow_dyn)."""
+    kind = "emission_absorption_physical"
+    if shared:
+        n_ok = _check_case(kind, 3, 96, 96, 12, seed=77, lorentzian=True, baseline_degree=7, shared_axis=True)
+    else:
+        n_ok = _check_case(kind, 3, 96, 64, 12, seed=78, lorentzian=False, baseline_degree=7)
+    assert n_ok >= 6
