@@ -21,6 +21,7 @@
 #include "launch.cuh"
 
 namespace chi {
+#define CHI_LOG2E_MAP 1.4426950408889634074
 
 // ---------------------------------------------------------------------------
 // k_cloud_map
@@ -67,7 +68,10 @@ __device__ __forceinline__ void cloud_map_draw(const MapCfg& cfg, const RowMap& 
   o[CC_KA] = pa.k; o[CC_AGA] = pa.AG; o[CC_ALA] = pa.AL; o[CC_HA] = pa.h;
   // 1: an optical depth of this cloud is negative, so 2^y can overflow on it (moments_ea.cuh, MODE); NaNs
   // need no care, they propagate through the remainder of the exponential whatever the branch
-  o[CC_CAREFUL] = (pe.AG < 0.0 || pe.AL < 0.0 || pa.AG < 0.0 || pa.AL < 0.0) ? 1.0 : 0.0;
+  // ... or its Gaussian depth is so large that 2^y of it can underflow (summed over the N clouds for the
+  // absorption spectrum): the plain form of the kernel leaves out that select as well
+  const double big = (1000.0 / CHI_LOG2E_MAP) / N;
+  o[CC_CAREFUL] = (pe.AG < 0.0 || pe.AL < 0.0 || pa.AG < 0.0 || pa.AL < 0.0 || pe.AG > big || pa.AG > big) ? 1.0 : 0.0;
 }
 
 // the map of one (draw, cloud) of a batch in global memory; also called from the sampler's tick kernel

@@ -195,7 +195,8 @@ __device__ __forceinline__ bool chi_exp2_underflow(int hi) {
 }
 
 // 2^y
-template <bool OVERFLOW = true>
+// UNDERFLOW = false: the caller knows y > -1022 (or NaN), the zero select is left out
+template <bool OVERFLOW = true, bool UNDERFLOW = true>
 __device__ __forceinline__ double chi_exp2(double y, const ExpT& c) {
   const int hi = __double2hiint(y);
   const double t = y + c.k[0];
@@ -206,7 +207,7 @@ __device__ __forceinline__ double chi_exp2(double y, const ExpT& c) {
   int ph;
   asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(ph) : "r"(m), "r"(__double2hiint(p)));
   // the range stops at -inf (0xFFF00000) so that NaNs still propagate through r and p
-  ph = chi_exp2_underflow(hi) ? 0 : ph;
+  if (UNDERFLOW) ph = chi_exp2_underflow(hi) ? 0 : ph;
   double out = __hiloint2double(ph, __double2loint(p));
   if (OVERFLOW) {
     // y >= 1024 (0x4090000000000000) up to and including +inf gives +inf
@@ -219,7 +220,7 @@ __device__ __forceinline__ double chi_exp2(double y, const ExpT& c) {
 // 2^(a b): the product never materialises -- t = fma(a, b, magic) rounds a b to a multiple of 2^-10
 // in one step and r = fma(a, b, -nf) is the exact remainder, one FP64 instruction fewer than
 // chi_exp2(a * b); the range tests read the rounded argument nf instead of y.
-template <bool OVERFLOW = true>
+template <bool OVERFLOW = true, bool UNDERFLOW = true>
 __device__ __forceinline__ double chi_exp2_prod(double a, double b, const ExpT& c) {
   const double t = fma(a, b, c.k[0]);
   const double nf = t - c.k[0];
@@ -229,7 +230,7 @@ __device__ __forceinline__ double chi_exp2_prod(double a, double b, const ExpT& 
   const double p = chi_exp2_core(__double2loint(t), r, c, m);
   int ph;
   asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(ph) : "r"(m), "r"(__double2hiint(p)));
-  ph = chi_exp2_underflow(hi) ? 0 : ph;
+  if (UNDERFLOW) ph = chi_exp2_underflow(hi) ? 0 : ph;
   double out = __hiloint2double(ph, __double2loint(p));
   if (OVERFLOW) {
     const bool overflow = (unsigned)(hi - 0x40900000) <= (0x7FF00000u - 0x40900000u);

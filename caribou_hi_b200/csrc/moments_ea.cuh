@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
           xs = fma(nALa, q[n], xs);
           om[n] = 1.0 - chi_exp2<OVF>(x, ek);
         } else {
-          om[n] = 1.0 - chi_exp2_prod<OVF>(nAGe, E[n], ek);
+          om[n] = 1.0 - chi_exp2_prod<OVF, OVF>(nAGe, E[n], ek);
         }
         Pn[n] = P;
         const double u = om[n] * P;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
         P = fma(-f, u, P);
       }
       const double mu_e = (bg * P + T) - bg + base_e;   // physics.py:362-365
-      const double ea = chi_exp2<OVF>(xs, ek);
+      const double ea = chi_exp2<OVF, OVF>(xs, ek);
       const double mu_a = (1.0 - ea) + base_a;          // absorption_model.py:91
       double mbe, mba;
       if (VJP && a.vjp) {
