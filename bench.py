@@ -46,7 +46,7 @@ def workload_name(draws):
 # --------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # --------------------------------------------------------------------------------------
-NCU_DRAM_BYTES_PER_DRAW = 8083968.0 / 20000.0  # k_moments_ea<4,0,1,0,1,EA_TAME>, profiles/r2b_ncu_full_summary.txt
+NCU_DRAM_BYTES_PER_DRAW = 8083712.0 / 20000.0  # k_moments_ea<4,0,1,0,1,EA_TAME>, profiles/r2c_ncu_full_summary.txt
 
 
 class ClockSampler:
@@ -541,7 +541,7 @@ def run_b200(args):
                          # profiles/ (20000 draws per launch: 8.09 MB read, writes absorbed by L2),
                          # scaled to this launch's draws
                          "traffic": (NCU_DRAM_BYTES_PER_DRAW * draws_launch) if fused else None,
-                         "traffic_source": "profiles/r2b_ncu_full_summary.txt" if fused else None,
+                         "traffic_source": "profiles/r2c_ncu_full_summary.txt" if fused else None,
                          "hbm": {"achieved": bytes_em / t_em / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_em / t_em / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
@@ -554,7 +554,7 @@ def run_b200(args):
             vt, st_step, dn, ct = time_oracle(256, 2, 1, min_seconds=4.0)
             result["cpu_baseline_torch"] = {"value": vt, "unit": UNIT, "cores": ct, "kind": "port",
                                             "sample": f"256 draws x {dn} steps, torch-CPU fp64 autograd oracle"}
-        result["roofline"]["traffic_source"] = "profiles/r2b_ncu_full_summary.txt (ncu --set full, scaled to this launch's draws)" if fused else None
+        result["roofline"]["traffic_source"] = "profiles/r2c_ncu_full_summary.txt (ncu --set full, scaled to this launch's draws)" if fused else None
     else:
         result = None
     eng.close()
