@@ -439,13 +439,21 @@ __device__ __forceinline__ void sm_loop_abs(const SmCtx& x, const SmallArgs& a, 
 // warp totals of a thread's NL x M accumulators -> shared s_red[warp][(g NL + i) M + j] (lanes < G write)
 template <int NL, int M>
 __device__ __forceinline__ void sm_store_acc(const SmCtx& x, double (&acc)[NL][M], double* s_red_warp, int off) {
+  // every accumulator goes through the same butterfly over the channel lanes (sm_chan_sum); one loop over the
+  // steps with the NL x M independent shuffles of a step in flight together, not NL x M loops one after another
+#pragma unroll 1
+  for (int m = 16; m >= (1 << x.lgG); m >>= 1) {
 #pragma unroll
-  for (int i = 0; i < NL; ++i)
+    for (int i = 0; i < NL; ++i)
 #pragma unroll
-    for (int j = 0; j < M; ++j) {
-      const double t = sm_chan_sum(x.lgG, acc[i][j]);
-      if (x.cl == 0) s_red_warp[off + (x.g * NL + i) * M + j] = t;
-    }
+      for (int j = 0; j < M; ++j) acc[i][j] += __shfl_xor_sync(CHI_FULL, acc[i][j], m);
+  }
+  if (x.cl == 0) {
+#pragma unroll
+    for (int i = 0; i < NL; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) s_red_warp[off + (x.g * NL + i) * M + j] = acc[i][j];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -583,7 +591,9 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
         const int c0 = chunk * a.chunk_e, c1 = min(a.S_e, c0 + a.chunk_e);
         const double* ch = a.chan_e + (int64_t)sl * ((a.S_e + 31) >> 5) * 128;
         if (c0 < c1) sm_loop_em<NL, PV>(x, a, s_cc, ch, c0, c1, s_beta[0], s_beta, gb, acc, v3);
+        if (a.stamps && b == 0 && chunk == 0 && tid == 0) a.stamps[7] = clock64() - t_0;
         sm_store_acc<NL, NE>(x, acc, red, 1 + nbe + nba);
+        if (a.stamps && b == 0 && chunk == 0 && tid == 0) a.stamps[15] = clock64() - t_0;
       }
       if (a.has_a) {
         double acc[NL][NA];
@@ -598,7 +608,12 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
       }
     }
     // logp and the baseline terms live on the lanes of cloud group 0 (every group computed the same values)
-    const double lp = sm_chan_sum(a.lgG, v3[0]), g0e = sm_chan_sum(a.lgG, v3[1]), g0a = sm_chan_sum(a.lgG, v3[2]);
+#pragma unroll 1
+    for (int m = 16; m >= (1 << a.lgG); m >>= 1) {  // the three sums through one butterfly (sm_chan_sum's steps)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v3[j] += __shfl_xor_sync(CHI_FULL, v3[j], m);
+    }
+    const double lp = v3[0], g0e = v3[1], g0a = v3[2];
     if (lane == 0) {
       red[0] = -0.5 * lp;
       if (nbe > 0) red[1] = g0e;

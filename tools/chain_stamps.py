@@ -31,5 +31,5 @@ n = max(int(st[14]), 1)
 mhz = 1965.0
 print(f"{chains} chains: 200 iterations in {dt:.2f} s; block 0: {n} ticks, state machine {st[12]/n/mhz:.2f} us/tick, "
       f"evaluation {st[13]/n/mhz:.2f} us/tick")
-print("evaluation phases of the last tick (us from its start): map %.2f jac %.2f chan %.2f joined %.2f | logp %.2f grad %.2f"
-      % (st[0]/mhz, st[9]/mhz, st[2]/mhz, st[3]/mhz, st[5]/mhz, st[6]/mhz))
+print("evaluation phases of the last tick (us from its start): map %.2f jac %.2f [emission loop %.2f, its sums %.2f] chan %.2f joined %.2f | logp %.2f grad %.2f"
+      % (st[0]/mhz, st[9]/mhz, st[7]/mhz, st[15]/mhz, st[2]/mhz, st[3]/mhz, st[5]/mhz, st[6]/mhz))
