@@ -141,7 +141,10 @@ class _HIBase(ABC):
                init_point=None, jitter=None, pool_mass=False, lock_step=False):
         """Batched NUTS over ``chains`` on the device -- the role of ``BaseModel.sample`` /
         ``pm.sample`` in the reference (optimization.ipynb cell 12), but with all chains in one
-        process and one batched logp+grad kernel pipeline per leapfrog step.
+        process: small models run one resident thread block per chain that does whole leapfrog steps
+        inside one kernel (``csrc/nuts_chain.cuh``), larger ones a CUDA graph of the chains' state
+        machine + one batched logp+grad kernel pipeline per leapfrog step
+        (``Engine.set_option("nuts_tick", ...)`` forces either).
 
         Starting points follow PyMC's "jitter" initialisation: the model's initial point (the
         origin of the unconstrained space, i.e. the moment of each prior -- or ``init_point``, a
