@@ -28,7 +28,7 @@ MODEL_ABSORPTION_PHYSICAL = 4
 MODEL_EMISSION_PHYSICAL = 5
 MODEL_EMISSION_ABSORPTION_PHYSICAL = 6
 
-OPT_SMALL_PATH, OPT_SMALL_NL, OPT_SMALL_CHUNKS, OPT_SMALL_STAMPS, OPT_NUTS_TICK, OPT_DEV_OVERLAP, OPT_EA_ONE_PASS = 0, 1, 2, 3, 4, 5, 6
+OPT_SMALL_PATH, OPT_SMALL_NL, OPT_SMALL_CHUNKS, OPT_SMALL_STAMPS, OPT_NUTS_TICK, OPT_DEV_OVERLAP, OPT_EA_ONE_PASS, OPT_SMALL_CLUSTER = 0, 1, 2, 3, 4, 5, 6, 7
 
 ERROR_NAMES = {0: "CHI_OK", -1: "CHI_EINVAL", -2: "CHI_ECUDA", -3: "CHI_ENODEV", -4: "CHI_ESTATE", -5: "CHI_ENOMEM"}
 

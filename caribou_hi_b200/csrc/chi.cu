@@ -298,11 +298,12 @@ bool batch_is_small(const chi_handle* h, int64_t B) {
 //   * more than 8 clouds: the pipeline runs on the 12- / 16-cloud instantiations (255 registers,
 //     kilobytes of spills); one launch is 2.4x faster (57.6 -> 23.9 us at 32 chains x 16 clouds);
 //   * launched from the host one call at a time (the Op / Engine path): a call costs what its
-//     launches cost the host, one launch instead of four is 46.6 against 54.3 us at 64 chains x
-//     8 clouds x 2048+2048 channels, 28.6 against 40.8 us at 8 chains x 2 clouds;
+//     launches cost the host, one launch instead of four is 44.0 against 53.6 us at 64 chains x
+//     8 clouds x 2048+2048 channels, 25.9 against 38.8 us at 8 chains x 2 clouds;
 //   * replayed from a CUDA graph (the sampler's ticks): launches are free and the pipeline's channel
-//     kernel executes fewer instructions per channel (every cloud in one thread): 29.2 against
-//     31.6 us -> the sampler keeps the pipeline (graph_path).
+//     kernel executes fewer instructions per channel (every cloud in one thread); with records and a
+//     counter in global memory the one launch lost there (31.6 against 29.2 us); as a cluster it is level,
+//     but not inside the sampler (see the end of this function).
 // CHI_OPT_SMALL_PATH overrides (tests run both paths).
 bool use_eval_small(const chi_handle* h, int64_t B, bool vjp) {
   if (vjp || h->epilogue_on_hi || h->cfg.n_clouds * CHI_NSLOT > CHI_SM_THREADS - 96) return false;
@@ -311,6 +312,12 @@ bool use_eval_small(const chi_handle* h, int64_t B, bool vjp) {
   if (mode == 2) return true;
   if (!batch_is_small(h, B)) return false;
   if (h->cfg.n_clouds > 8) return true;
+  // (graph_path = the sampler's graph of kernels per tick.  With the blocks of a draw meeting as a cluster the
+  // one launch is level with the pipeline for a LIKELIHOOD evaluation replayed from a graph -- 28.8 against 28.9 us
+  // at configs[2]'s shape, 11.2 against 13.9 at 8 chains x 2 clouds -- but the sampler evaluates the MODEL logp,
+  // whose prior terms lengthen the Jacobian warps, and its tick kernel maps the point for the pipeline: measured
+  // inside the sampler the pipeline stays ahead, 29 against 25 it/s at configs[2]'s size, 124 against 116 at 8
+  // chains x 2 clouds.)
   return !h->graph_path && std::max<int64_t>(B, h->call_draws) <= 128;
 }
 
@@ -346,6 +353,9 @@ int small_args(chi_handle* h, Lane& L, int64_t B, const double* theta, const dou
   if (force_chunks > 0) want = force_chunks;
   const int max_chunks = std::max(1, S_max / (cpw * 7));
   int nc = (int)std::min<int64_t>(want, max_chunks);
+  // up to 8 blocks per draw meet as a thread-block cluster (small.cuh, SM_CLUSTER): a little over is not worth
+  // the trip through global memory
+  if (nc > 8 && nc <= 10 && force_chunks <= 0 && h->opt[CHI_OPT_SMALL_CLUSTER] != 1) nc = 8;
   auto chunk_len = [&](int S) { int len = (S + nc - 1) / nc; return std::max(cpw, (len + cpw - 1) / cpw * cpw); };
   a.chunk_e = a.S_e ? chunk_len(a.S_e) : 0;
   a.chunk_a = a.S_a ? chunk_len(a.S_a) : 0;
@@ -422,7 +432,11 @@ int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const doub
     CK(cudaEventRecord(evs[0], L.st));
     CK(cudaEventRecord(evs[1], L.st));
   }
-  if (launch_eval_small(NL, h->cfg.lorentzian != 0, h->map, a, dyn, L.st))
+  // several blocks per draw: as one thread-block cluster that exchanges through distributed shared memory
+  // (small.cuh, SM_CLUSTER) unless CHI_OPT_SMALL_CLUSTER says otherwise
+  const bool cluster = a.n_chunks >= 2 && a.n_chunks <= 8 && h->opt[CHI_OPT_SMALL_CLUSTER] != 1;
+  if (cluster ? launch_eval_small_cl(NL, h->cfg.lorentzian != 0, h->map, a, dyn, L.st)
+              : launch_eval_small(NL, h->cfg.lorentzian != 0, h->map, a, dyn, L.st))
     return fail(h, CHI_EINVAL, "unsupported small-batch configuration");
   h->launches++;
   CK(cudaGetLastError());

@@ -113,6 +113,8 @@ struct SmallArgs {
 
 // one-launch evaluation of a small batch (small.cuh); NL = clouds per thread (1 or 2)
 int launch_eval_small(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, size_t dyn_smem, cudaStream_t st);
+// the same evaluation with the blocks of a draw as one thread-block cluster (2 <= n_chunks <= 8)
+int launch_eval_small_cl(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, size_t gb_bytes, cudaStream_t st);
 int eval_small_blocks_per_sm(int NL);
 
 // cloud count of the instantiation that serves a model with N clouds

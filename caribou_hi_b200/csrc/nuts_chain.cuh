@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(NT, NT == CHI_SM_THREADS ? 2 : 1) k_nuts_chain
     __syncthreads();
     const long long t1 = a.stamps ? clock64() : 0;
     if (!s_go) break;
-    sm_eval<NL, PV, true, NT>(S, s_gb_dyn, a, b, 0, s_point, s.nbe ? s_point + nu : nullptr,
+    sm_eval<NL, PV, SM_CHAIN, NT>(S, s_gb_dyn, a, b, 0, s_point, s.nbe ? s_point + nu : nullptr,
                           s.nba ? s_point + nu + s.nbe : nullptr);
     __syncthreads();  // logp and the gradient of the point are in global memory for warp 0's next tick
     if (a.stamps) { c_tick += t1 - t0; c_eval += clock64() - t1; ++n_tick; }

@@ -21,6 +21,8 @@
 // Reference arithmetic: physics.py:265-365, the add_likelihood() bodies, pm.Normal logp and its
 // reverse-mode gradient, as in moments.cuh / moments_ea.cuh (same moments, same record layout).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "launch.cuh"
 #include "moments_ea.cuh"
 
@@ -492,9 +494,19 @@ __device__ __forceinline__ void sm_init(SmSmemT<NT>& S, const MapCfg& cfg, const
 // baseline coefficients (global or shared memory; null = no coefficients).
 // CHAIN (nuts_chain.cuh: one block evaluates the same chain tick after tick, n_chunks == 1): the block's
 // record is the draw's record, so it stays in shared memory -- no record in global memory, no counter.
-template <int NL, bool PV, bool CHAIN, int NT = CHI_SM_THREADS>
+// SM_CLUSTER: the n_chunks blocks of a draw are one thread-block CLUSTER (launched with that cluster dimension,
+// n_chunks <= 8).  Every block pushes its record, and its Jacobian warps their records, straight into the shared
+// memory of the cluster's first block (distributed shared memory: `xbuf` = this block's exchange area
+// [n_chunks][stride] records, [N K][CHI_JAC_W] Jacobian records, [N] prior terms); one cluster barrier later the
+// first block has everything on its own SM.  This replaces the trip through global memory of SM_GLOBAL -- write
+// the record, fence, count the draw's blocks with an atomic, and whichever block comes last reads everything
+// back through L2 -- which is ~5 us of a 27 us evaluation at configs[2]'s shape.  Same sums in the same order.
+enum { SM_GLOBAL = 0, SM_CHAIN = 1, SM_CLUSTER = 2 };
+
+template <int NL, bool PV, int MODE, int NT = CHI_SM_THREADS>
 __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const SmallArgs& a, const int64_t b, const int chunk,
-                                        const double* tb, const double* ce_b, const double* ca_b) {
+                                        const double* tb, const double* ce_b, const double* ca_b, double* xbuf = nullptr) {
+  constexpr bool CHAIN = MODE == SM_CHAIN, CLUSTER = MODE == SM_CLUSTER;
   constexpr int NF = PV ? 10 : 6, NE = PV ? 8 : 5, NA = PV ? 6 : 3;
   double* const s_T = S.T;
   double* const s_cc = S.cc;
@@ -509,6 +521,9 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
   const int N = a.N, G = 1 << a.lgG, NP = NL * G;
   const int nbe = a.nb_e, nba = a.nb_a;
 
+  // (every block of the cluster must be running before anything is stored into the first block's shared memory:
+  // arrive here, wait just before the first such store -- the wait hides behind the set-up below)
+  if (CLUSTER) cooperative_groups::this_cluster().barrier_arrive();
   // null clouds pad the lane groups: tau = 0, f = 0
   for (int i = tid; i < NP * CHI_SM_CCS; i += NT) {
     const int k = i % CHI_SM_CCS;
@@ -534,6 +549,14 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
     __syncthreads();
   }
 
+  // where the draw's records meet: the first block of the cluster, or the workspace in global memory
+  double* lead = nullptr;
+  if (CLUSTER) {
+    cooperative_groups::this_cluster().barrier_wait();
+    lead = cooperative_groups::this_cluster().map_shared_rank(xbuf, 0);
+  }
+  double* const jac_b = CLUSTER ? lead + a.n_chunks * a.stride : a.jac + b * N * a.K * CHI_JAC_W;
+  double* const prior_b = CLUSTER ? jac_b + N * a.K * CHI_JAC_W : a.prior_buf + b * N;
   // ---- map (warp 0) next to the Jacobian records of this block (last warps) ----
   const int ncw = (NT / 32) - a.jac_warps;  // channel warps
   // the draw's likelihood constant, fetched early by the thread that writes logp at the very end
@@ -552,7 +575,7 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
       const int n = r / a.K, j0 = r - n * a.K;
       if (a.want_grad || (a.prior && j0 == 0))
         sm_jac(&s_cfg, &s_rm, N, a.prior ? S.tr + n * CHI_NSLOT : nullptr, a.fused || a.has_e, a.fused || a.has_a, tb + n, j0,
-               a.jac + ((b * N + n) * a.K + j0) * CHI_JAC_W, a.prior_buf + b * N + n);
+               jac_b + (n * a.K + j0) * CHI_JAC_W, prior_b + n);
     }
     if (a.stamps) t_jac = clock64();
   } else {
@@ -641,6 +664,20 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
       for (int w = 0; w < ncw; ++w) v += s_red[w][t];
       s_sum[t] = 0.0 + v;
     }
+  } else if (CLUSTER) {
+    for (int t = tid; t < stride; t += NT) {
+      double v = 0.0;
+      for (int w = 0; w < ncw; ++w) v += s_red[w][t];
+      lead[chunk * stride + t] = v;
+    }
+    cooperative_groups::this_cluster().sync();  // every record and Jacobian record of the draw is in the first block
+    if (a.stamps && b == 0 && chunk == 0 && tid == 0) a.stamps[4] = clock64() - t_0;
+    if (chunk != 0) return;
+    for (int t = tid; t < stride; t += NT) {
+      double v = 0.0;
+      for (int c = 0; c < a.n_chunks; ++c) v += xbuf[c * stride + t];  // chunk order, as SM_GLOBAL
+      s_sum[t] = v;
+    }
   } else {
     // channel-warp partials in fixed order -> the (draw, chunk) record
     double* rec = a.mom + (b * a.n_chunks + chunk) * stride;
@@ -677,7 +714,7 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
     }
   }
   // the per-cloud prior terms of the draw (written by the Jacobian warps of its blocks)
-  if (a.prior && tid < N) s_red[0][tid] = __ldcg(a.prior_buf + b * N + tid);
+  if (a.prior && tid < N) s_red[0][tid] = CLUSTER ? prior_b[tid] : __ldcg(prior_b + tid);
   __syncthreads();
   const bool use_e = a.fused || a.has_e, use_a = a.fused || a.has_a;
   const int nbe_u = use_e ? nbe : 0, nba_u = use_a ? nba : 0;
@@ -718,10 +755,10 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
 
   const int n = tid / a.K, j0 = tid - n * a.K;
   const double* cc = s_cc + n * CHI_SM_CCS;
-  const double* Jg = a.jac + ((b * N + n) * a.K + j0) * CHI_JAC_W;
+  const double* Jg = jac_b + (n * a.K + j0) * CHI_JAC_W;
   double J[CHI_JAC_W];
 #pragma unroll
-  for (int i = 0; i < CHI_JAC_W; ++i) J[i] = __ldcg(Jg + i);
+  for (int i = 0; i < CHI_JAC_W; ++i) J[i] = CLUSTER ? Jg[i] : __ldcg(Jg + i);
   const double f = cc[CC_F];
   double g = 0.0, cbar = 0.0;
   const double* m0 = s_sum + 1 + nbe + nba;
@@ -789,8 +826,22 @@ __global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small(
   const int64_t b = blockIdx.x / a.n_chunks;
   const int chunk = (int)(blockIdx.x - b * a.n_chunks);
   sm_init(S, cfg, a.rm);
-  sm_eval<NL, PV, false>(S, s_gb_dyn, a, b, chunk, a.theta + (b * a.rm.n_rows) * a.N,
-                         a.coeff_e ? a.coeff_e + b * a.nb_e : nullptr, a.coeff_a ? a.coeff_a + b * a.nb_a : nullptr);
+  sm_eval<NL, PV, SM_GLOBAL>(S, s_gb_dyn, a, b, chunk, a.theta + (b * a.rm.n_rows) * a.N,
+                             a.coeff_e ? a.coeff_e + b * a.nb_e : nullptr, a.coeff_a ? a.coeff_a + b * a.nb_a : nullptr);
+}
+
+// the cluster form (SM_CLUSTER): launched with cluster dimension n_chunks; x_off = byte offset of the exchange
+// area in the dynamic shared memory
+template <int NL, bool PV>
+__global__ void __launch_bounds__(CHI_SM_THREADS, NL <= 2 ? 2 : 1) k_eval_small_cl(MapCfg cfg, SmallArgs a, unsigned x_off) {
+  __shared__ SmSmem S;
+  extern __shared__ double s_gb_dyn[];
+  const int64_t b = blockIdx.x / a.n_chunks;
+  const int chunk = (int)(blockIdx.x - b * a.n_chunks);  // == the block's rank in its cluster
+  sm_init(S, cfg, a.rm);
+  sm_eval<NL, PV, SM_CLUSTER>(S, s_gb_dyn, a, b, chunk, a.theta + (b * a.rm.n_rows) * a.N,
+                              a.coeff_e ? a.coeff_e + b * a.nb_e : nullptr, a.coeff_a ? a.coeff_a + b * a.nb_a : nullptr,
+                              reinterpret_cast<double*>(reinterpret_cast<char*>(s_gb_dyn) + x_off));
 }
 
 }  // namespace chi

@@ -480,6 +480,10 @@ int64_t chi_launch_count(const chi_handle* h);
 #define CHI_OPT_EA_ONE_PASS 6  /* 1 = large Gaussian batches on a shared axis run the fused channel kernel as ONE
                                   launch with the overflow branch of 2^y in it (the form small batches always use);
                                   0 (default) = two launches, see moments_ea.cuh MODE.  Same results bit for bit. */
+#define CHI_OPT_SMALL_CLUSTER 7 /* 0 (default) = when the one-launch evaluation of a small batch runs 2..8 blocks per
+                                  draw they form a thread-block cluster and meet in distributed shared memory;
+                                  1 = they meet in global memory (records + a counter per draw).  Same results
+                                  bit for bit. */
 #define CHI_OPT_COUNT 8
 int chi_set_option(chi_handle* h, int option, int64_t value);
 /* CHI_OPT_DEV_OVERLAP: make the handle's stream wait for the device-resident calls issued so far. */

@@ -685,3 +685,45 @@ def test_many_baseline_terms_on_the_small_paths(cuda_device, shared):
     else:
         n_ok = _check_case(kind, 3, 96, 64, 12, seed=78, lorentzian=False, baseline_degree=7)
     assert n_ok >= 6
+
+
+@pytest.mark.parametrize("kind_n", [("emission_absorption_physical", 8, True, True), ("emission_absorption", 2, False, False),
+                                    ("absorption_physical", 3, True, False), ("emission_physical", 5, False, False)])
+def test_cluster_form_of_the_one_launch_kernel(cuda_device, kind_n):
+    """Several blocks per draw of the one-launch evaluation: as one thread-block cluster that meets in the first
+    block's (distributed) shared memory (default), or through records and a counter in global memory
+    (small_cluster 1).  Same sums in the same order: the results agree bit for bit, for likelihood and model
+    logp, whatever the number of blocks per draw."""
+    kind, N, lorentzian, shared = kind_n
+    spec, data, free, baseline = make_case(kind, N, 700, 420, 10, seed=31 + N, lorentzian=lorentzian, baseline_degree=1,
+                                           shared_axis=shared)
+    eng = engine_for(spec, data, 1)
+    theta = eng.pack(free)
+    ce, ca = baseline.get("baseline_emission_norm"), baseline.get("baseline_absorption_norm")
+    eng.set_option("small_path", 2)
+    ref_lp, _ = oracle_logp_grad(spec, data, free, baseline)
+    for chunks in (0, 2, 3, 5, 8):
+        eng.set_option("small_chunks", chunks)
+        out = []
+        for off in (0, 1):
+            eng.set_option("small_cluster", off)
+            out.append(eng.logp_grad(theta, ce, ca))
+        for x, y in zip(*out):
+            if x is not None:
+                assert np.array_equal(x, y, equal_nan=True), (chunks,)
+        assert_close(out[0][0], ref_lp, what=f"{kind} logp, cluster of {chunks}", axis=None)
+    eng.set_option("small_chunks", 0)
+    eng.set_option("small_cluster", 0)
+    # the model logp (priors and transforms on the device) through the same two forms
+    eng.set_priors()
+    u = np.random.default_rng(5).normal(0, 0.3, theta.shape)
+    out = []
+    for off in (0, 1):
+        eng.set_option("small_cluster", off)
+        out.append(eng.model_logp_grad(u, ce, ca))
+    eng.set_option("small_cluster", 0)
+    assert np.isfinite(out[0][0]).sum() >= 5
+    for x, y in zip(*out):
+        if x is not None:
+            assert np.array_equal(x, y, equal_nan=True)
+    eng.close()
