@@ -807,6 +807,39 @@ def other_configs(local, world, rank, peak64):
                         "mean_tree_depth": float(st["depth"].mean()), "divergent_fraction": float(st["diverging"].mean())}
     key0 = [k for k in out if k.startswith("configs[0]")][0]
     out[key0]["more_chains_200_tune_100_draws"] = more
+    out[key0]["how"] = ("chi_nuts_sample through Model.sample(): one resident thread block per chain runs whole leapfrog "
+                        "steps inside one kernel (csrc/nuts_chain.cuh)")
+    model.engine.close()
+
+    # ---- the sampler at configs[2]'s size: 64 chains x 8 clouds x 2048+2048 channels, pseudo-Voigt ----
+    from caribou_hi_b200 import EmissionAbsorptionPhysicalModel
+
+    S2, N2, chains2, tune2, draws2 = 2048, 8, 64, 200, 100
+    v2 = np.linspace(-60, 60, S2)
+    zero = {"emission": SpecData(v2, np.zeros(S2), 0.1), "absorption": SpecData(v2, np.zeros(S2), 0.01)}
+    sim = EmissionAbsorptionPhysicalModel(zero, N2, baseline_degree=0)
+    sim.add_priors(prior_fwhm_L=1.0); sim.add_likelihood()
+    truth = sim.sample_prior(1, np.random.default_rng(7))
+    for _ in range(20):
+        mu = sim.predict(truth)
+        if all(np.all(np.isfinite(m)) for m in mu.values()):
+            break
+        truth = sim.sample_prior(1, rng)
+    sim.engine.close()
+    data = {"emission": SpecData(v2, mu["emission"][0] + 0.1 * rng.standard_normal(S2), 0.1),
+            "absorption": SpecData(v2, mu["absorption"][0] + 0.01 * rng.standard_normal(S2), 0.01)}
+    model = EmissionAbsorptionPhysicalModel(data, N2, baseline_degree=0)
+    model.add_priors(prior_fwhm_L=1.0); model.add_likelihood()
+    t0 = time.perf_counter()
+    _, st = model.sample(draws=draws2, tune=tune2, chains=chains2, seed=2, init_point=truth, jitter=0.05)
+    dt2 = time.perf_counter() - t0
+    key2 = [k for k in out if k.startswith("configs[2]")][0]
+    out[key2]["nuts_64_chains_200_tune_100_draws"] = {
+        "iterations_per_s": (tune2 + draws2) / dt2, "chain_iterations_per_s": chains2 * (tune2 + draws2) / dt2,
+        "mean_tree_depth": float(st["depth"].mean()), "divergent_fraction": float(st["diverging"].mean()), "seconds": dt2,
+        "how": "the four blocks of a chain as one thread-block cluster, whole leapfrog steps inside one kernel "
+               "(csrc/nuts_chain.cuh, k_nuts_chain_cl)"}
+    model.engine.close()
     return out
 
 

@@ -30,6 +30,8 @@ using namespace chi;
 namespace chi {
 int launch_nuts_chain(int NL, int threads, bool pv, const MapCfg& cfg, const SmallArgs& a, const NutsState& s,
                       const NutsAsync& A, int max_ticks, size_t dyn_smem, cudaStream_t st);  // launch_chain.cu
+int launch_nuts_chain_cl(int NL, bool pv, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A,
+                         int max_ticks, size_t gb_bytes, cudaStream_t st);
 }
 
 namespace {
@@ -403,10 +405,27 @@ int small_args(chi_handle* h, Lane& L, int64_t B, const double* theta, const dou
 // kernel with 256 threads whenever it can run (bit-identical to 2 + the one-launch evaluation with one block per
 // draw), 4 = the chain kernel with 512 threads where it can (else 256).
 #define CHI_CHAIN_TICKS 2048
+// blocks per chain of the chain kernel's CLUSTER form (k_nuts_chain_cl), 0 = not that form: every block of every
+// chain has to be resident (two blocks per SM), and a cluster has at most 8 blocks
+int nuts_chain_cluster(const chi_handle* h, int64_t B) {
+  const int64_t mode = h->opt[CHI_OPT_NUTS_TICK];
+  const int N = h->cfg.n_clouds;
+  if (N * CHI_NSLOT > CHI_SM_THREADS - 96 || getenv("CHI_NUTS_THREAD")) return 0;
+  const int nc = (int)std::min<int64_t>(8, (2 * (int64_t)h->n_sm) / std::max<int64_t>(B, 1));
+  if (nc < 2) return 0;
+  if (mode == 5) return nc;
+  if (mode != 0) return 0;
+  // by size: past the single-block forms (nuts_chain_threads) and while a block's share of the channels stays
+  // small enough for the per-tick latency to matter (measured: profiles/r2_nuts_chain.txt)
+  const int64_t S = std::max(h->has_e ? h->e.S : 0, h->has_a ? h->a.S : 0);
+  const int64_t work = (int64_t)N * S * (h->cfg.lorentzian ? 3 : 2) / 2;
+  const bool single = (N <= 8 && B <= (int64_t)h->n_sm && work <= 14000) || work <= 6500;
+  return (!single && work / nc <= 12000) ? nc : 0;
+}
 // threads per chain of the chain kernel, 0 = the graph of kernels runs instead
 int nuts_chain_threads(const chi_handle* h, int64_t B) {
   const int64_t mode = h->opt[CHI_OPT_NUTS_TICK];
-  if (mode == 1 || mode == 2) return 0;
+  if (mode == 1 || mode == 2 || mode == 5) return 0;
   if (getenv("CHI_NUTS_THREAD")) return 0;
   const int N = h->cfg.n_clouds;
   if (N * CHI_NSLOT > CHI_SM_THREADS - 96) return 0;
@@ -2359,12 +2378,28 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
   k_nuts_init<<<grid, 64, 0, st>>>(s, (unsigned long long)cfg->seed, eps0);
   // the per-chain kernel (nuts_chain.cuh) evaluates a draw with one block; the starting point goes through the
   // same arithmetic (k_eval_small, one block per draw)
-  const int chain_threads = lock_step ? 0 : nuts_chain_threads(h, B);
-  const bool chain_kernel = chain_threads != 0;
+  int chain_cluster = lock_step ? 0 : nuts_chain_cluster(h, B);
+  int chain_threads = (lock_step || chain_cluster) ? 0 : nuts_chain_threads(h, B);
   SmallArgs chain_args;
   int chain_nl = 1;
   size_t chain_dyn = 0;
-  if (chain_kernel) {
+  if (chain_cluster) {
+    rc = small_args(h, h->lanes[0], B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, s.elogp, s.egu,
+                    nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, chain_cluster, &chain_args, &chain_nl, &chain_dyn);
+    if (rc) return rc;
+    chain_cluster = chain_args.n_chunks;  // (what the channel count allows)
+    if (chain_cluster < 2 || chain_cluster > 8) {  // a model this short per block: the single-block form
+      chain_cluster = 0;
+      chain_threads = CHI_SM_THREADS;
+    }
+  }
+  const bool chain_kernel = chain_threads != 0 || chain_cluster != 0;
+  if (chain_cluster) {
+    if (launch_eval_small_cl(chain_nl, h->cfg.lorentzian != 0, h->map, chain_args, chain_dyn, st))
+      return fail(h, CHI_EINVAL, "unsupported configuration of the chain kernel");
+    h->launches++;
+    CK(cudaGetLastError());
+  } else if (chain_kernel) {
     rc = small_args(h, h->lanes[0], B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, s.elogp, s.egu,
                     nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, 1, &chain_args, &chain_nl, &chain_dyn, chain_threads);
     if (rc) return rc;
@@ -2427,7 +2462,9 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
       int64_t ticks = 0;
       h_flags[0] = 0;
       while (h_flags[0] < B && ticks < tick_cap) {
-        if (launch_nuts_chain(chain_nl, chain_threads, h->cfg.lorentzian != 0, h->map, chain_args, s, A, CHI_CHAIN_TICKS, chain_dyn, st))
+        if (chain_cluster ? launch_nuts_chain_cl(chain_nl, h->cfg.lorentzian != 0, h->map, chain_args, s, A, CHI_CHAIN_TICKS, chain_dyn, st)
+                          : launch_nuts_chain(chain_nl, chain_threads, h->cfg.lorentzian != 0, h->map, chain_args, s, A,
+                                              CHI_CHAIN_TICKS, chain_dyn, st))
           return fail(h, CHI_EINVAL, "unsupported configuration of the chain kernel");
         CK(cudaGetLastError());
         ticks += CHI_CHAIN_TICKS;

@@ -66,4 +66,51 @@ __global__ void __launch_bounds__(NT, NT == CHI_SM_THREADS ? 2 : 1) k_nuts_chain
   }
 }
 
+// The same with the n_chunks blocks of a chain as one thread-block CLUSTER (small.cuh, SM_CLUSTER), for models
+// whose channel sums want more than one SM per chain (configs[2]: 8 clouds x 2048+2048 channels): the cluster's
+// first block runs the chain's state machine and publishes the evaluation point in its shared memory; after a
+// cluster barrier every block copies the point through distributed shared memory and evaluates its chunk of the
+// channels; records and Jacobian records meet in the first block (sm_eval), which contracts them and goes on
+// to the next tick.  Three cluster barriers per tick, no launch, no trip through global memory.  Bit-identical
+// to the graph of {staged tick, k_eval_small_cl with the same blocks per draw}.
+template <int NL, bool PV>
+__global__ void __launch_bounds__(CHI_SM_THREADS, 2) k_nuts_chain_cl(MapCfg cfg, SmallArgs a, NutsState s, NutsAsync A, int max_ticks,
+                                                                     unsigned x_off) {
+  namespace cg = cooperative_groups;
+  __shared__ SmSmem S;
+  __shared__ double s_stage[5][CHI_NUTS_MAXD];
+  __shared__ double s_point[CHI_NUTS_MAXD + 1];  // the evaluation point, then 1.0 / 0.0: evaluate it / the chain is done
+  extern __shared__ double s_gb_dyn[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t b = blockIdx.x / a.n_chunks;
+  const int rank = (int)(blockIdx.x - b * a.n_chunks);  // == cluster.block_rank()
+  if (A.iter[b] >= A.n_total) return;  // finished in an earlier launch (the same answer in every block of the cluster)
+  const int nu = CHI_NSLOT * s.N, D = s.D;
+  double* const xbuf = reinterpret_cast<double*>(reinterpret_cast<char*>(s_gb_dyn) + x_off);
+  const double* const lead_point = cluster.map_shared_rank(s_point, 0);
+  sm_init(S, cfg, a.rm);
+  __syncthreads();
+  for (int t = 0; t < max_ticks; ++t) {
+    if (rank == 0 && tid < 32) {
+      nw_tick<CHI_MODEL_PHYSICS, true>(s, A, S.cfg, S.rm, nullptr, nullptr, b, lane, s_stage);
+      __syncwarp();
+      const bool go = A.iter[b] < A.n_total;
+      for (int d = lane; d < D; d += 32) s_point[d] = nuts_ev(s.eu, s.ece, s.eca, s, b, d);
+      if (lane == 0) s_point[D] = go ? 1.0 : 0.0;
+    }
+    cluster.sync();  // the point is published; also: every block is done with the previous tick
+    if (rank != 0)
+      for (int d = tid; d <= D; d += CHI_SM_THREADS) s_point[d] = lead_point[d];
+    __syncthreads();
+    if (s_point[D] == 0.0) {
+      cluster.sync();  // nobody leaves while its shared memory may still be read
+      break;
+    }
+    sm_eval<NL, PV, SM_CLUSTER>(S, s_gb_dyn, a, b, rank, s_point, s.nbe ? s_point + nu : nullptr,
+                                s.nba ? s_point + nu + s.nbe : nullptr, xbuf);
+    __syncthreads();
+  }
+}
+
 }  // namespace chi

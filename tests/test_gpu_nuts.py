@@ -166,6 +166,12 @@ def test_chain_kernel_matches_the_graph_of_kernels(cuda_device, kind_n_shared):
     graph = _sample_with(kind, N, {"nuts_tick": 2, "small_path": 2, "small_chunks": 1}, shared=shared)
     _same_run(chain, graph)
     assert chain[2] < 60 and graph[2] > 20 * chain[2], (chain[2], graph[2])
+    # the cluster form: the blocks of a chain (8 asked for; what the channel count allows) as one thread-block
+    # cluster, against the same graph with that many blocks per draw
+    cluster = _sample_with(kind, N, {"nuts_tick": 5}, shared=shared)
+    graph_cl = _sample_with(kind, N, {"nuts_tick": 2, "small_path": 2, "small_chunks": 8}, shared=shared)
+    _same_run(cluster, graph_cl)
+    assert cluster[2] < 60
     # a model this small takes the chain kernel by itself, in its wide form (512 threads per chain: the channels
     # are spread over twice the warps, so the sums agree with the 256-thread form to rounding and the chains part
     # ways after a while; the first draws of the warm-up still agree closely)
