@@ -68,10 +68,12 @@ __device__ __forceinline__ void cloud_map_draw(const MapCfg& cfg, const RowMap& 
   o[CC_KA] = pa.k; o[CC_AGA] = pa.AG; o[CC_ALA] = pa.AL; o[CC_HA] = pa.h;
   // 1: an optical depth of this cloud is negative, so 2^y can overflow on it (moments_ea.cuh, MODE); NaNs
   // need no care, they propagate through the remainder of the exponential whatever the branch
-  // ... or its Gaussian depth is so large that 2^y of it can underflow (summed over the N clouds for the
-  // absorption spectrum): the plain form of the kernel leaves out that select as well
+  // ... or its peak depth (Gaussian part + Lorentzian part, AL / h at the line centre) is so large that 2^y of it
+  // can underflow (summed over the N clouds for the absorption spectrum): the plain forms of the kernels leave
+  // out that select as well
   const double big = (1000.0 / CHI_LOG2E_MAP) / N;
-  o[CC_CAREFUL] = (pe.AG < 0.0 || pe.AL < 0.0 || pa.AG < 0.0 || pa.AL < 0.0 || pe.AG > big || pa.AG > big) ? 1.0 : 0.0;
+  o[CC_CAREFUL] = (pe.AG < 0.0 || pe.AL < 0.0 || pa.AG < 0.0 || pa.AL < 0.0 || pe.AG + pe.AL / pe.h > big ||
+                   pa.AG + pa.AL / pa.h > big) ? 1.0 : 0.0;
 }
 
 // the map of one (draw, cloud) of a batch in global memory; also called from the sampler's tick kernel

@@ -4,6 +4,8 @@
 // exp and the Newton reciprocal; one block per draw, threads walk channels, 8-byte coalesced
 // stores of mu.  emission: physics.py:294-309 + physics.py:345-365; absorption:
 // absorption_model.py:88-91.
+#include <type_traits>
+
 #include "launch.cuh"
 
 namespace chi {
@@ -18,9 +20,11 @@ __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
     double* d = s_c[threadIdx.x];
     d[0] = 0.0; d[1] = -1.0; d[2] = 0.0; d[3] = 0.0; d[4] = 1.0; d[5] = d[6] = d[7] = 0.0;
   }
+  bool marked = false;
   if (threadIdx.x < a.N) {
     const double* p = a.cc + (b * a.N + threadIdx.x) * CHI_CC_STRIDE;
     double* d = s_c[threadIdx.x];
+    marked = p[CC_CAREFUL] != 0.0;
     d[0] = p[CC_C];
     if (EMISSION) {
       d[1] = -CHI_LOG2E * p[CC_KE]; d[2] = -CHI_LOG2E * p[CC_AGE]; d[3] = -CHI_LOG2E * p[CC_ALE]; d[4] = p[CC_HE];
@@ -35,6 +39,12 @@ __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
   const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
   const int S = a.S;
   double* __restrict__ out = a.mu + b * S;
+  // The range selects of exp(-tau) (overflow: a negative depth; underflow: a huge one) are only compiled into the
+  // copy of the loop that draws marked by the cloud map take (cc[..][CC_CAREFUL], kernels.cuh); the choice is
+  // uniform over the block.  14 of ~70 instructions per (channel, cloud) less for everybody else.
+  const bool careful = __syncthreads_or(marked) != 0;
+  auto channels = [&](auto tag) {
+  constexpr bool SEL = decltype(tag)::value;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     const double v = a.vax[s];
     double base = a.offset ? a.offset[s] : 0.0;
@@ -55,7 +65,7 @@ __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
       double P = 1.0, T = 0.0;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
-        const double u = (1.0 - chi_exp2<true>(x[n], ek)) * P;
+        const double u = (1.0 - chi_exp2<SEL, SEL>(x[n], ek)) * P;
         T = fma(s_c[n][7], u, T);
         P = fma(-s_c[n][5], u, P);
       }
@@ -64,10 +74,13 @@ __global__ void __launch_bounds__(256) k_spectra_t(SpecArgs a) {
       double xs = 0.0;
 #pragma unroll
       for (int n = 0; n < N; ++n) xs += x[n];
-      r = (1.0 - chi_exp2<true>(xs, ek)) + base;
+      r = (1.0 - chi_exp2<SEL, SEL>(xs, ek)) + base;
     }
     out[s] = r;
   }
+  };
+  if (careful) channels(std::true_type{});
+  else channels(std::false_type{});
 }
 
 // Both spectra of a shared axis in one pass: exp(-k d^2) of a cloud is evaluated once and feeds
@@ -84,9 +97,11 @@ __global__ void __launch_bounds__(256) k_spectra_ea_t(SpecArgs a) {
     for (int i = 0; i < 10; ++i) d[i] = 0.0;
     d[1] = -1.0; d[8] = 1.0;
   }
+  bool marked = false;
   if (threadIdx.x < a.N) {
     const double* p = a.cc + (b * a.N + threadIdx.x) * CHI_CC_STRIDE;
     double* d = s_c[threadIdx.x];
+    marked = p[CC_CAREFUL] != 0.0;
     d[0] = p[CC_C]; d[1] = -CHI_LOG2E * p[CC_KE]; d[2] = -CHI_LOG2E * p[CC_AGE]; d[3] = p[CC_F] * p[CC_TS];
     d[4] = p[CC_F]; d[5] = -CHI_LOG2E * p[CC_AGA]; d[6] = -CHI_LOG2E * p[CC_ALE]; d[7] = -CHI_LOG2E * p[CC_ALA];
     d[8] = p[CC_HE]; d[9] = 0.0;
@@ -98,6 +113,9 @@ __global__ void __launch_bounds__(256) k_spectra_ea_t(SpecArgs a) {
   const int S = a.S;
   double* __restrict__ out_e = a.mu + b * S;
   double* __restrict__ out_a = a.mu_a + b * S;
+  const bool careful = __syncthreads_or(marked) != 0;  // as in k_spectra_t
+  auto channels = [&](auto tag) {
+  constexpr bool SEL = decltype(tag)::value;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     const double v = a.vax[s];
     double base_e = a.offset ? a.offset[s] : 0.0, base_a = a.offset_a ? a.offset_a[s] : 0.0;
@@ -121,13 +139,16 @@ __global__ void __launch_bounds__(256) k_spectra_ea_t(SpecArgs a) {
         x = fma(nALe, q, x);
         xs = fma(nALa, q, xs);
       }
-      const double u = (1.0 - chi_exp2<true>(x, ek)) * P;
+      const double u = (1.0 - chi_exp2<SEL, SEL>(x, ek)) * P;
       T = fma(fTs, u, T);
       P = fma(-f, u, P);
     }
     out_e[s] = (a.bg * P + T) - a.bg + base_e;
-    out_a[s] = (1.0 - chi_exp2<true>(xs, ek)) + base_a;
+    out_a[s] = (1.0 - chi_exp2<SEL, SEL>(xs, ek)) + base_a;
   }
+  };
+  if (careful) channels(std::true_type{});
+  else channels(std::false_type{});
 }
 
 template <int N, bool PV>

@@ -671,6 +671,21 @@ def test_negative_depths_in_a_large_batch(cuda_device, sightlines):
         if name == "fwhm_L":
             continue
         assert_close(got[name][fin], ref_g[name][fin], what=f"d/d{name} of a batch with marked draws")
+    if sightlines == 1:
+        # the spectra kernels choose between their two loops per block (= per draw) from the same marks
+        data = {"emission": mr.OracleData(v, ye[0], 0.3), "absorption": mr.OracleData(v, ya[0], 0.02)}
+        for d in data.values():
+            d._brightness_offset = 0.0
+        with np.errstate(all="ignore"):
+            ref_mu = mr.predict_from_inputs(spec, data, {k: torch.tensor(x[:600]) for k, x in inp.items()})
+        mu_e, mu_a = eng.spectra(theta[:600])
+        for got_mu, key in ((mu_e, "emission"), (mu_a, "absorption")):
+            ref = ref_mu[key].numpy()
+            ok = np.isfinite(ref).all(axis=1)
+            assert ok.sum() > 450 and (~ok).sum() > 20
+            assert_close(got_mu[ok], ref[ok], what=f"mu_{key} of a batch with marked draws")
+            assert np.array_equal(np.isnan(got_mu[~ok]), np.isnan(ref[~ok])), key
+            assert np.array_equal(np.isinf(got_mu[~ok]), np.isinf(ref[~ok])), key
     eng.close()
 
 
