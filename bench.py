@@ -381,6 +381,31 @@ def run_b200(args):
     units_step = draws * N * (S_E + S_A)
     value = world * units_step * args.steps / (ms * 1e-3)
 
+    # ---- the same device-resident steps with the library's opt-in overlap of consecutive calls ----
+    # (CHI_OPT_DEV_OVERLAP: calls alternate between two internal lanes, so the cloud map of step i+1 and the
+    # epilogue of step i run next to the other step's channel kernel; outputs are ordered into the handle's stream
+    # by chi_dev_join.  Reported beside `value`, which stays the default one-stream form.)
+    overlapped = None
+    if world == 1 and not args.no_extras:
+        eng.set_option("dev_overlap", 1)
+        for i in range(args.warmup):
+            step(i, exchange=False)
+        eng.dev_join()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record(stream)
+        for i in range(args.steps):
+            step(i, exchange=False)
+        eng.dev_join()
+        o1.record(stream)
+        barrier()
+        eng.set_option("dev_overlap", 0)
+        oms = o0.elapsed_time(o1)
+        overlapped = {"value": units_step * args.steps / (oms * 1e-3), "unit": "units/s", "ms_per_step": oms / args.steps,
+                      "how": "chi_set_option(CHI_OPT_DEV_OVERLAP, 1): consecutive chi_logp_grad_dev calls on two alternating "
+                             "lanes, chi_dev_join before the closing event; same results bit for bit "
+                             "(tests/test_gpu_comm.py::test_overlapped_device_calls_give_the_same_bits)"}
+
     # ---- end to end through the public host API: pinned host -> device -> pinned host ----
     # packed blocks: exactly the free RVs of the model class in, exactly their gradients out
     e2e_steps = max(2, min(args.steps, 30))
@@ -526,6 +551,7 @@ def run_b200(args):
                 "note": "every rank at once; on the 8-GPU bench host the ranks share ~150 GB/s (8-11 GB/s each way per "
                         "rank against 55 GB/s for one rank alone, profiles/r2_e2e_diag_n8.txt)"},
             "gpu_launches": launches,
+            "value_overlapped_calls": overlapped,
             "stage_ms": {"cloud_map": float(stage[0]), "moments_emission": float(stage[1]),
                          "moments_absorption": float(stage[2]), "epilogue": float(stage[3]),
                          "launches_per_step_of_each_kernel": pieces,
