@@ -120,13 +120,19 @@ def test_lock_step_and_asynchronous_chains_agree(cuda_device):
 
 
 def _sample_with(kind, N, options, chains=6, draws=40, tune=60, shared=False):
-    from caribou_hi_b200 import EmissionAbsorptionModel, EmissionAbsorptionPhysicalModel, SpecData
+    import caribou_hi_b200 as chb
+    from caribou_hi_b200 import SpecData
 
-    cls = EmissionAbsorptionModel if kind == "emission_absorption" else EmissionAbsorptionPhysicalModel
+    cls = {"emission_absorption": chb.EmissionAbsorptionModel, "emission_absorption_physical": chb.EmissionAbsorptionPhysicalModel,
+           "absorption_physical": chb.AbsorptionPhysicalModel, "emission": chb.EmissionModel}[kind]
     ve = np.linspace(-40, 40, 96)
     va = ve if shared else np.linspace(-20, 20, 48)
-    model = cls({"emission": SpecData(ve, np.full(96, 5.0), 0.5), "absorption": SpecData(va, np.full(va.size, 0.2), 0.05)},
-                N, baseline_degree=1)
+    data = {}
+    if "emission" in kind:
+        data["emission"] = SpecData(ve, np.full(96, 5.0), 0.5)
+    if "absorption" in kind:
+        data["absorption"] = SpecData(va, np.full(va.size, 0.2), 0.05)
+    model = cls(data, N, baseline_degree=1)
     model.add_priors(prior_fwhm_L=1.0) if kind.endswith("physical") else model.add_priors()
     model.add_likelihood()
     for name, value in options.items():
@@ -155,7 +161,8 @@ def test_tick_variants_agree(cuda_device, kind_n):
 
 
 @pytest.mark.parametrize("kind_n_shared", [("emission_absorption", 2, False), ("emission_absorption", 2, True),
-                                           ("emission_absorption_physical", 3, True), ("emission_absorption_physical", 6, False)])
+                                           ("emission_absorption_physical", 3, True), ("emission_absorption_physical", 6, False),
+                                           ("absorption_physical", 3, False), ("emission", 2, False)])
 def test_chain_kernel_matches_the_graph_of_kernels(cuda_device, kind_n_shared):
     """The per-chain kernel (nuts_chain.cuh: one resident block runs whole leapfrog steps tick after tick; the
     default for small models) against the graph of two kernels per tick it fuses -- the staged tick and the
