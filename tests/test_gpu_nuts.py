@@ -189,3 +189,53 @@ def test_chain_kernel_matches_the_graph_of_kernels(cuda_device, kind_n_shared):
     for k in ("accept", "depth"):
         assert np.all(np.isfinite(auto[1][k]))
     assert abs(auto[1]["accept"].mean() - chain[1]["accept"].mean()) < 0.25, (auto[1]["accept"].mean(), chain[1]["accept"].mean())
+
+
+def test_chain_kernels_with_one_sightline_per_chain(cuda_device):
+    """The survey use of the sampler: every chain samples the posterior of its OWN sightline's spectra
+    (chi_nuts_sample's sightline argument).  The per-chain kernel in its three forms against the graph of
+    kernels they fuse: bit-identical draws for the 256-thread and the cluster form, and every chain's
+    posterior mean velocity follows its own sightline's line."""
+    from caribou_hi_b200 import Engine
+    from caribou_hi_b200 import layout
+
+    N, S, n_sl = 1, 128, 5
+    v = np.linspace(-30, 30, S)
+    centres = np.linspace(-12, 12, n_sl)
+    rng = np.random.default_rng(9)
+    ye = np.stack([8.0 * np.exp(-0.5 * ((v - c) / 3.0) ** 2) for c in centres]) + 0.2 * rng.standard_normal((n_sl, S))
+    ya = np.stack([0.3 * np.exp(-0.5 * ((v - c) / 3.0) ** 2) for c in centres]) + 0.01 * rng.standard_normal((n_sl, S))
+
+    def run(options):
+        eng = Engine("emission_absorption", N, prior_velocity=(0.0, 15.0))
+        eng.set_spectra(emission=dict(spectral=v, brightness=ye, noise=0.2, basis=np.ones((1, S)), offset=0.0),
+                        absorption=dict(spectral=v, brightness=ya, noise=0.01, basis=np.ones((1, S)), offset=0.0),
+                        n_sightlines=n_sl)
+        eng.set_priors()
+        for k, val in options.items():
+            eng.set_option(k, val)
+        chains = 10
+        sl = (np.arange(chains) % n_sl).astype(np.int32)
+        u0 = np.zeros((chains, layout.NSLOT, N))
+        u0 += 0.05 * np.random.default_rng(3).standard_normal(u0.shape)
+        n0 = eng.launch_count()
+        out = eng.nuts_sample(u0, n_tune=150, n_draws=60, seed=11, sightline=sl)
+        out["launches"] = eng.launch_count() - n0
+        eng.close()
+        return out, sl
+
+    chain, sl = run({"nuts_tick": 3})
+    graph, _ = run({"nuts_tick": 2, "small_path": 2, "small_chunks": 1})
+    for k in ("u", "accept", "depth", "logp", "step_size", "coeff_e", "coeff_a"):
+        assert np.array_equal(chain[k], graph[k], equal_nan=True), k
+    assert chain["launches"] < 300 and graph["launches"] > 20 * chain["launches"], (chain["launches"], graph["launches"])
+    cluster, _ = run({"nuts_tick": 5})
+    graph_cl, _ = run({"nuts_tick": 2, "small_path": 2, "small_chunks": 8})
+    for k in ("u", "accept", "depth", "logp"):
+        assert np.array_equal(cluster[k], graph_cl[k], equal_nan=True), k
+    wide, _ = run({"nuts_tick": 4})
+    # each chain found its own sightline's line: velocity = prior mean + 15 * velocity_norm
+    idx = layout.slot_names("emission_absorption", False)["velocity_norm"]  # Normal: unconstrained = constrained
+    for res in (chain, cluster, wide):
+        x = res["u"][:, :, idx, 0].mean(axis=0) * 15.0
+        assert np.all(np.abs(x - centres[sl]) < 1.5), (x, centres[sl])
