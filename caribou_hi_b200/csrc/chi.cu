@@ -454,9 +454,13 @@ int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const doub
   // several blocks per draw: as one thread-block cluster that exchanges through distributed shared memory
   // (small.cuh, SM_CLUSTER) unless CHI_OPT_SMALL_CLUSTER says otherwise
   const bool cluster = a.n_chunks >= 2 && a.n_chunks <= 8 && h->opt[CHI_OPT_SMALL_CLUSTER] != 1;
-  if (cluster ? launch_eval_small_cl(NL, h->cfg.lorentzian != 0, h->map, a, dyn, L.st)
-              : launch_eval_small(NL, h->cfg.lorentzian != 0, h->map, a, dyn, L.st))
-    return fail(h, CHI_EINVAL, "unsupported small-batch configuration");
+  int lrc = -1;
+  if (cluster) {
+    lrc = launch_eval_small_cl(NL, h->cfg.lorentzian != 0, h->map, a, dyn, L.st);
+    if (lrc) cudaGetLastError();  // (a cluster that cannot be placed: the global-memory form computes the same)
+  }
+  if (lrc) lrc = launch_eval_small(NL, h->cfg.lorentzian != 0, h->map, a, dyn, L.st);
+  if (lrc) return fail(h, CHI_EINVAL, "unsupported small-batch configuration");
   h->launches++;
   CK(cudaGetLastError());
   if (!h->capturing) {
