@@ -595,8 +595,18 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.chan = h->e.chan.d(); a.basis = h->e.basis.d();
     a.coeff = ce; a.sl = sl; a.gbar = vjp ? gbar_e : nullptr; a.cc = L.cc.d(); a.mom = L.mom_e.d();
-    if (launch_moments_em(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
-    h->launches++;
+    if (!small && !h->opt[CHI_OPT_EA_ONE_PASS] && moments_em_two_pass(N, a)) {
+      // as for the fused kernel: the marked draws on a wave of resident blocks next to the big grid
+      CK(cudaStreamWaitEvent(L.aux, L.ev_fork, 0));
+      if (launch_moments_em_fixup(N, pv, a, h->n_sm, L.aux)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+      CK(cudaEventRecord(L.ev_join, L.aux));
+      if (launch_moments_em_tame(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+      CK(cudaStreamWaitEvent(L.st, L.ev_join, 0));
+      h->launches += 2;
+    } else {
+      if (launch_moments_em(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+      h->launches++;
+    }
     CK(cudaGetLastError());
     ea.has_e = 1; ea.nb_e = a.n_base; ea.chunks_e = a.n_chunks; ea.stride_e = a.mom_stride;
     ea.mom_e = L.mom_e.d();

@@ -66,6 +66,10 @@ bool moments_ea_two_pass(int N, bool pv, const FusedArgs& a);
 int launch_moments_ea_tame(int N, const FusedArgs& a, cudaStream_t st);
 int launch_moments_ea_fixup(int N, const FusedArgs& a, int n_sm, cudaStream_t st);
 int launch_moments_em(int N, bool pv, const ChanArgs& a, cudaStream_t st);
+// two launches for large batches (moments.cuh, MODE; launch_em_tame.cu)
+bool moments_em_two_pass(int N, const ChanArgs& a);
+int launch_moments_em_tame(int N, bool pv, const ChanArgs& a, cudaStream_t st);
+int launch_moments_em_fixup(int N, bool pv, const ChanArgs& a, int n_sm, cudaStream_t st);
 int launch_moments_abs(int N, bool pv, const ChanArgs& a, cudaStream_t st);
 // ---- argument block of k_eval_small (small.cuh) ----
 #define CHI_SM_THREADS 256

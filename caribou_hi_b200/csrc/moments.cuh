@@ -401,9 +401,17 @@ constexpr int ab_min_blocks(int N, bool pv) {
 // ---------------------------------------------------------------------------
 // SB ("simple baseline") instantiations serve n_base <= 1 -- the reference's default
 // baseline_degree = 0 -- and carry no baseline loops.
-template <int N, bool PV, bool SB, bool STAGED = false>
+// MODE: see moments_ea.cuh -- EA_ALL one launch with the range selects of exp(-tau) in it; EA_TAME every draw the
+// cloud map did not mark, without them; EA_FIXUP a wave of resident blocks that scans the marks and evaluates the
+// marked draws.  (Emission kernel, two axes: 1.197 -> 1.115 ms Gaussian, 1.517 -> 1.457 ms pseudo-Voigt at 1e5
+// draws x 4 clouds x 1000 channels.  The absorption kernel, one exponential per channel, gains 2 % and keeps one form.)
+enum { EA_ALL = 0, EA_TAME = 1, EA_FIXUP = 2 };
+
+template <int N, bool PV, bool SB, bool STAGED = false, int MODE = EA_ALL>
 __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(ChanArgs a) {
   constexpr int NE = EmLayout<PV>::NE;
+  constexpr bool SEL = MODE != EA_TAME;
+  static_assert(!(STAGED && MODE == EA_FIXUP), "the scan form reads the channel data through L1");
   __shared__ __align__(16) double s_c[CHI_WARPS_PER_BLOCK][N][8];
   __shared__ double s_gb[SB ? 1 : CHI_MAX_BASELINE - CHI_BASE_REG][SB ? 1 : CHI_BLOCK];
   __shared__ double s_beta[CHI_WARPS_PER_BLOCK][CHI_MAX_BASELINE];
@@ -418,169 +426,192 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
   }
   fill_exp_table(s_T);  // contains the block barrier
 
-  const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
-  if (item >= a.B * a.n_chunks) return;
-  const int64_t b = item / a.n_chunks;
-  const int chunk = (int)(item - b * a.n_chunks);
-  const int nb = a.n_base, S = a.S;
+  int it = 0;  // STAGED: groups fetched so far (buffer and mbarrier phase)
+  auto one_item = [&](const int64_t item) {
+    const int64_t b = item / a.n_chunks;
+    const int chunk = (int)(item - b * a.n_chunks);
+    const int nb = a.n_base, S = a.S;
 
-  if (lane < a.n_real) {
-    const double* p = a.cc + (b * a.n_real + lane) * CHI_CC_STRIDE;
-    const double f = p[CC_F], ts = p[CC_TS];
-    double* d = s_c[warp][lane];
-    d[0] = p[CC_C]; d[1] = -CHI_LOG2E * p[CC_KE]; d[2] = -CHI_LOG2E * p[CC_AGE]; d[3] = f * ts;
-    d[4] = f; d[5] = ts; d[6] = -CHI_LOG2E * p[CC_ALE]; d[7] = p[CC_HE];
-  } else if (lane < N) {  // null cloud
-    double* d = s_c[warp][lane];
-    d[0] = 0.0; d[1] = -1.0; d[2] = 0.0; d[3] = 0.0; d[4] = 0.0; d[5] = 0.0; d[6] = 0.0; d[7] = 1.0;
-  }
-  if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
-  if (!SB)
-    for (int i = CHI_BASE_REG; i < nb; ++i) s_gb[i - CHI_BASE_REG][threadIdx.x] = 0.0;
-  __syncwarp();
-  const double beta0 = nb > 0 ? s_beta[warp][0] : 0.0, beta1 = (!SB && nb > 1) ? s_beta[warp][1] : 0.0;
-  const double* __restrict__ bas1 = a.basis + S;
-
-  const int sl = a.sl ? a.sl[b] : 0;
-  const double* __restrict__ ch = a.chan + (int64_t)sl * ((S + 31) >> 5) * 128 + lane;
-  const double* __restrict__ G = a.gbar ? a.gbar + b * S : nullptr;
-
-  double acc[N][NE];
-#pragma unroll
-  for (int n = 0; n < N; ++n)
-#pragma unroll
-    for (int j = 0; j < NE; ++j) acc[n][j] = 0.0;
-  double lp = 0.0, gb0 = 0.0, gb1 = 0.0;
-  const double bg = a.bg;
-  const double(*sc)[8] = s_c[warp];
-  const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
-
-  const int s_end = min(S, (chunk + 1) * a.chunk_len);
-  const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&s_stage[STAGED ? warp : 0][0][0]);
-  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&s_bar[STAGED ? warp : 0][0]);
-  int it = 0;
-  if (STAGED && lane == 0 && chunk * a.chunk_len < s_end)
-    tma_fetch<1024>(ch - lane + (int64_t)((chunk * a.chunk_len) >> 5) * 128, stage_addr, bar_addr);
-  // STAGED: the whole warp runs every group (lanes past a ragged end carry zero weight)
-  for (int s = chunk * a.chunk_len + lane; (STAGED ? s - lane : s) < s_end; s += 32) {
-    const double* __restrict__ cs = ch + (int64_t)(s >> 5) * 128;  // lane offset is in ch
-    const int sx = STAGED ? min(s, s_end - 1) : s;
-    const double* __restrict__ sg = cs;
-    double v, p0;
-    if (STAGED) {
-      const int buf = it & 1;
-      __syncwarp();  // every lane is done reading the other buffer
-      if (lane == 0 && s - lane + 32 < s_end)
-        tma_fetch<1024>(cs - lane + 128, stage_addr + (buf ^ 1) * 1024, bar_addr + (buf ^ 1) * 8);
-      mbar_wait(bar_addr + buf * 8, (it >> 1) & 1);
-      sg = &s_stage[warp][buf][lane];
-      ++it;
-      v = sg[0]; p0 = sg[32];
-    } else {
-      v = __ldg(cs); p0 = __ldg(cs + 32);
+    bool marked = false;
+    if (lane < a.n_real) {
+      const double* p = a.cc + (b * a.n_real + lane) * CHI_CC_STRIDE;
+      const double f = p[CC_F], ts = p[CC_TS];
+      double* d = s_c[warp][lane];
+      d[0] = p[CC_C]; d[1] = -CHI_LOG2E * p[CC_KE]; d[2] = -CHI_LOG2E * p[CC_AGE]; d[3] = f * ts;
+      d[4] = f; d[5] = ts; d[6] = -CHI_LOG2E * p[CC_ALE]; d[7] = p[CC_HE];
+      marked = p[CC_CAREFUL] != 0.0;
+    } else if (lane < N) {  // null cloud
+      double* d = s_c[warp][lane];
+      d[0] = 0.0; d[1] = -1.0; d[2] = 0.0; d[3] = 0.0; d[4] = 0.0; d[5] = 0.0; d[6] = 0.0; d[7] = 1.0;
     }
-    double p1 = 0.0, base = beta0 * p0;  // p_0 is 0 without a baseline
-    if (!SB) {
-      if (nb > 1) { p1 = bas1[s]; base = fma(beta1, p1, base); }
-      for (int i = CHI_BASE_REG; i < nb; ++i) base = fma(s_beta[warp][i], a.basis[(int64_t)i * S + s], base);
-    }
+    if (MODE == EA_TAME && __any_sync(0xffffffffu, marked)) return;  // EA_FIXUP's draw
+    if (lane < nb) s_beta[warp][lane] = a.coeff ? a.coeff[b * nb + lane] : 0.0;
+    if (!SB)
+      for (int i = CHI_BASE_REG; i < nb; ++i) s_gb[i - CHI_BASE_REG][threadIdx.x] = 0.0;
+    __syncwarp();
+    const double beta0 = nb > 0 ? s_beta[warp][0] : 0.0, beta1 = (!SB && nb > 1) ? s_beta[warp][1] : 0.0;
+    const double* __restrict__ bas1 = a.basis + S;
 
-    // ---- forward, nearest cloud first ----
-    double om[N], Pn[N], E[N], q[N];
-    double P = 1.0, T = 0.0;
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      double c0, nk, nAG, f, fTs, Ts;
-      lds2(&sc[n][0], c0, nk);
-      lds2(&sc[n][2], nAG, fTs);
-      lds2(&sc[n][4], f, Ts);
-      const double d = v - c0, d2 = d * d;
-      E[n] = chi_exp2_prod<false>(nk, d2, ek);
-      if (PV) {
-        double x = nAG * E[n];                  // -tau log2(e)
-        double nAL, h;
-        lds2(&sc[n][6], nAL, h);
-        q[n] = chi_rcp(d2 + h);
-        x = fma(nAL, q[n], x);
-        om[n] = 1.0 - chi_exp2(x, ek);          // 1 - e^-tau
+    const int sl = a.sl ? a.sl[b] : 0;
+    const double* __restrict__ ch = a.chan + (int64_t)sl * ((S + 31) >> 5) * 128 + lane;
+    const double* __restrict__ G = a.gbar ? a.gbar + b * S : nullptr;
+
+    double acc[N][NE];
+  #pragma unroll
+    for (int n = 0; n < N; ++n)
+  #pragma unroll
+      for (int j = 0; j < NE; ++j) acc[n][j] = 0.0;
+    double lp = 0.0, gb0 = 0.0, gb1 = 0.0;
+    const double bg = a.bg;
+    const double(*sc)[8] = s_c[warp];
+    const ExpCtx ek = CHI_LOAD_EXPCTX(s_T);
+
+    const int s_end = min(S, (chunk + 1) * a.chunk_len);
+    const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&s_stage[STAGED ? warp : 0][0][0]);
+    const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&s_bar[STAGED ? warp : 0][0]);
+    if (STAGED && lane == 0 && chunk * a.chunk_len < s_end)
+      tma_fetch<1024>(ch - lane + (int64_t)((chunk * a.chunk_len) >> 5) * 128, stage_addr, bar_addr);
+    // STAGED: the whole warp runs every group (lanes past a ragged end carry zero weight)
+    for (int s = chunk * a.chunk_len + lane; (STAGED ? s - lane : s) < s_end; s += 32) {
+      const double* __restrict__ cs = ch + (int64_t)(s >> 5) * 128;  // lane offset is in ch
+      const int sx = STAGED ? min(s, s_end - 1) : s;
+      const double* __restrict__ sg = cs;
+      double v, p0;
+      if (STAGED) {
+        const int buf = it & 1;
+        __syncwarp();  // every lane is done reading the other buffer
+        if (lane == 0 && s - lane + 32 < s_end)
+          tma_fetch<1024>(cs - lane + 128, stage_addr + (buf ^ 1) * 1024, bar_addr + (buf ^ 1) * 8);
+        mbar_wait(bar_addr + buf * 8, (it >> 1) & 1);
+        sg = &s_stage[warp][buf][lane];
+        ++it;
+        v = sg[0]; p0 = sg[32];
       } else {
-        om[n] = 1.0 - chi_exp2_prod(nAG, E[n], ek);
+        v = __ldg(cs); p0 = __ldg(cs + 32);
       }
-      Pn[n] = P;
-      const double u = om[n] * P;
-      T = fma(fTs, u, T);                       // f Ts (1-e) x attenuation in front
-      P = fma(-f, u, P);                        // P (1 - f + f e)
-    }
-    const double mu = (bg * P + T) - bg + base;  // ON - OFF, physics.py:362-365
-    double mubar;
-    if (G) {
-      mubar = G[sx];
-    } else {
-      const double r = (STAGED ? sg[64] : __ldg(cs + 64)) - mu;
-      mubar = (STAGED ? sg[96] : __ldg(cs + 96)) * r;  // d logp / d mu
-      if (STAGED && s >= s_end) mubar = 0.0;    // padded lanes of a ragged end
-      lp = fma(mubar, r, lp);                   // -0.5 applied once at the end
-    }
-    if (STAGED && s >= s_end) mubar = 0.0;
-    gb0 = fma(mubar, p0, gb0);
-    if (!SB) {
-      if (nb > 1) gb1 = fma(mubar, p1, gb1);
-      for (int i = CHI_BASE_REG; i < nb; ++i)
-        s_gb[i - CHI_BASE_REG][threadIdx.x] =
-            fma(mubar, a.basis[(int64_t)i * S + s], s_gb[i - CHI_BASE_REG][threadIdx.x]);
+      double p1 = 0.0, base = beta0 * p0;  // p_0 is 0 without a baseline
+      if (!SB) {
+        if (nb > 1) { p1 = bas1[s]; base = fma(beta1, p1, base); }
+        for (int i = CHI_BASE_REG; i < nb; ++i) base = fma(s_beta[warp][i], a.basis[(int64_t)i * S + s], base);
+      }
+
+      // ---- forward, nearest cloud first ----
+      double om[N], Pn[N], E[N], q[N];
+      double P = 1.0, T = 0.0;
+  #pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double c0, nk, nAG, f, fTs, Ts;
+        lds2(&sc[n][0], c0, nk);
+        lds2(&sc[n][2], nAG, fTs);
+        lds2(&sc[n][4], f, Ts);
+        const double d = v - c0, d2 = d * d;
+        E[n] = chi_exp2_prod<false>(nk, d2, ek);
+        if (PV) {
+          double x = nAG * E[n];                  // -tau log2(e)
+          double nAL, h;
+          lds2(&sc[n][6], nAL, h);
+          q[n] = chi_rcp(d2 + h);
+          x = fma(nAL, q[n], x);
+          om[n] = 1.0 - chi_exp2<SEL, SEL>(x, ek);  // 1 - e^-tau
+        } else {
+          om[n] = 1.0 - chi_exp2_prod<SEL, SEL>(nAG, E[n], ek);
+        }
+        Pn[n] = P;
+        const double u = om[n] * P;
+        T = fma(fTs, u, T);                       // f Ts (1-e) x attenuation in front
+        P = fma(-f, u, P);                        // P (1 - f + f e)
+      }
+      const double mu = (bg * P + T) - bg + base;  // ON - OFF, physics.py:362-365
+      double mubar;
+      if (G) {
+        mubar = G[sx];
+      } else {
+        const double r = (STAGED ? sg[64] : __ldg(cs + 64)) - mu;
+        mubar = (STAGED ? sg[96] : __ldg(cs + 96)) * r;  // d logp / d mu
+        if (STAGED && s >= s_end) mubar = 0.0;    // padded lanes of a ragged end
+        lp = fma(mubar, r, lp);                   // -0.5 applied once at the end
+      }
+      if (STAGED && s >= s_end) mubar = 0.0;
+      gb0 = fma(mubar, p0, gb0);
+      if (!SB) {
+        if (nb > 1) gb1 = fma(mubar, p1, gb1);
+        for (int i = CHI_BASE_REG; i < nb; ++i)
+          s_gb[i - CHI_BASE_REG][threadIdx.x] =
+              fma(mubar, a.basis[(int64_t)i * S + s], s_gb[i - CHI_BASE_REG][threadIdx.x]);
+      }
+
+      // ---- reverse, farthest cloud first; Q = brightness arriving behind cloud n ----
+      double Q = bg;
+  #pragma unroll
+      for (int n = N - 1; n >= 0; --n) {
+        double c0, nk, f, Ts;
+        lds2(&sc[n][0], c0, nk);
+        lds2(&sc[n][4], f, Ts);
+        const double Sn = Ts - Q;                 // Ts_n - Q_n
+        const double x = om[n] * Pn[n];
+        const double mx = mubar * x;
+        acc[n][3] += mx;                          // -> d/dTs (times f)
+        acc[n][4] = fma(mx, Sn, acc[n][4]);       // -> d/df
+        const double g = (mubar * Sn) * (Pn[n] - x);  // taubar / f = mubar e P (Ts - Q)
+        const double d = v - c0;
+        const double t = g * E[n];
+        const double td = t * d;
+        acc[n][0] += t;
+        acc[n][1] += td;
+        acc[n][2] = fma(td, d, acc[n][2]);
+        if (PV) {
+          const double u = g * q[n];
+          const double u2 = u * q[n];
+          acc[n][5] += u;
+          acc[n][6] += u2;
+          acc[n][7] = fma(u2, d, acc[n][7]);
+        }
+        Q = fma(om[n], f * Sn, Q);                // (1 - f om) Q + f Ts om
+      }
     }
 
-    // ---- reverse, farthest cloud first; Q = brightness arriving behind cloud n ----
-    double Q = bg;
-#pragma unroll
-    for (int n = N - 1; n >= 0; --n) {
-      double c0, nk, f, Ts;
-      lds2(&sc[n][0], c0, nk);
-      lds2(&sc[n][4], f, Ts);
-      const double Sn = Ts - Q;                 // Ts_n - Q_n
-      const double x = om[n] * Pn[n];
-      const double mx = mubar * x;
-      acc[n][3] += mx;                          // -> d/dTs (times f)
-      acc[n][4] = fma(mx, Sn, acc[n][4]);       // -> d/df
-      const double g = (mubar * Sn) * (Pn[n] - x);  // taubar / f = mubar e P (Ts - Q)
-      const double d = v - c0;
-      const double t = g * E[n];
-      const double td = t * d;
-      acc[n][0] += t;
-      acc[n][1] += td;
-      acc[n][2] = fma(td, d, acc[n][2]);
-      if (PV) {
-        const double u = g * q[n];
-        const double u2 = u * q[n];
-        acc[n][5] += u;
-        acc[n][6] += u2;
-        acc[n][7] = fma(u2, d, acc[n][7]);
+    double* out = a.mom + item * a.mom_stride;
+    if (!SB)
+      for (int i = CHI_BASE_REG; i < nb; ++i) {
+        double g = warp_sum(s_gb[i - CHI_BASE_REG][threadIdx.x]);
+        if (lane == 0) out[1 + i] = g;
       }
-      Q = fma(om[n], f * Sn, Q);                // (1 - f om) Q + f Ts om
+    // logp, the two register-held baseline gradients and the N * NE moments: one folded reduction
+    typedef WarpFold<3 + N * NE> Fold;
+    double v[3 + N * NE];
+    v[0] = lp; v[1] = gb0; v[2] = gb1;
+  #pragma unroll
+    for (int n = 0; n < N; ++n)
+  #pragma unroll
+      for (int j = 0; j < NE; ++j) v[3 + n * NE + j] = acc[n][j];
+    Fold::run(v, lane);
+  #pragma unroll
+    for (int i = 0; i < Fold::OUT; ++i) {
+      const int idx = Fold::index(i, lane);
+      if (idx >= 3) out[1 + nb + (idx - 3)] = v[i];
+      else if (idx == 0) out[0] = -0.5 * v[i];
+      else if (idx > 0 && idx <= nb) out[idx] = v[i];
     }
-  }
-
-  double* out = a.mom + item * a.mom_stride;
-  if (!SB)
-    for (int i = CHI_BASE_REG; i < nb; ++i) {
-      double g = warp_sum(s_gb[i - CHI_BASE_REG][threadIdx.x]);
-      if (lane == 0) out[1 + i] = g;
+  };
+  if (MODE != EA_FIXUP) {
+    const int64_t item = (int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp;
+    if (item < a.B * a.n_chunks) one_item(item);
+  } else {
+    // 32 draws per warp and pass: one ballot of their marks, then the marked ones chunk by chunk
+    const int64_t n_warps = (int64_t)gridDim.x * CHI_WARPS_PER_BLOCK;
+    for (int64_t b0 = ((int64_t)blockIdx.x * CHI_WARPS_PER_BLOCK + warp) * 32; b0 < a.B; b0 += n_warps * 32) {
+      bool m = false;
+      if (b0 + lane < a.B)
+        for (int n = 0; n < a.n_real; ++n)
+          m |= __ldg(a.cc + ((b0 + lane) * a.n_real + n) * CHI_CC_STRIDE + CC_CAREFUL) != 0.0;
+      for (unsigned todo = __ballot_sync(0xffffffffu, m); todo; todo &= todo - 1) {
+        const int64_t bb = b0 + (__ffs(todo) - 1);
+        for (int chunk = 0; chunk < a.n_chunks; ++chunk) {
+          one_item(bb * a.n_chunks + chunk);
+          __syncwarp();  // the warp's shared constants are rewritten by the next item
+        }
+      }
     }
-  // logp, the two register-held baseline gradients and the N * NE moments: one folded reduction
-  typedef WarpFold<3 + N * NE> Fold;
-  double v[3 + N * NE];
-  v[0] = lp; v[1] = gb0; v[2] = gb1;
-#pragma unroll
-  for (int n = 0; n < N; ++n)
-#pragma unroll
-    for (int j = 0; j < NE; ++j) v[3 + n * NE + j] = acc[n][j];
-  Fold::run(v, lane);
-#pragma unroll
-  for (int i = 0; i < Fold::OUT; ++i) {
-    const int idx = Fold::index(i, lane);
-    if (idx >= 3) out[1 + nb + (idx - 3)] = v[i];
-    else if (idx == 0) out[0] = -0.5 * v[i];
-    else if (idx > 0 && idx <= nb) out[idx] = v[i];
   }
 }
 

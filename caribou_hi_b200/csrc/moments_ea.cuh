@@ -71,7 +71,7 @@ __device__ __forceinline__ void ldg2(const double* p, double& x, double& y) {
 // draws with it (normally none: the scan takes microseconds next to the other launch; a batch of nothing
 // but marked draws runs at the speed of EA_ALL).  EA_ALL is the single launch with the branch, for small
 // batches.
-enum { EA_ALL = 0, EA_TAME = 1, EA_FIXUP = 2 };
+// (enum { EA_ALL, EA_TAME, EA_FIXUP }: moments.cuh)
 
 template <int N, bool PV, bool SB, bool STAGED = false, bool VJP = true, int MODE = EA_ALL>
 __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(FusedArgs a) {

@@ -587,20 +587,23 @@ def test_nan_inputs_propagate(cuda_device, shared, lorentzian):
     eng.close()
 
 
+@pytest.mark.parametrize("two_axes", [False, True])
 @pytest.mark.parametrize("sightlines", [1, 3])
-def test_negative_depths_in_a_large_batch(cuda_device, sightlines):
+def test_negative_depths_in_a_large_batch(cuda_device, sightlines, two_axes):
     """Large Gaussian batches on a shared axis run the fused channel kernel as two launches (moments_ea.cuh,
     MODE): every draw without the +inf branch of 2^y, and the draws the cloud map marked -- a negative or NaN
     optical depth, which the seven physics-level inputs allow -- on a small scanning grid with it.  Marked
     draws of every flavour (mildly negative, overflowing, NaN, negative absorption weight only) in a batch
     large enough for that form must give what the one-launch form gives, bit for bit, and what the oracle
-    gives: values where it is finite, the same NaN / -inf elsewhere."""
+    gives: values where it is finite, the same NaN / -inf elsewhere.  two_axes: the spectra on different axes,
+    i.e. the emission kernel's two-launch form next to the one-launch absorption kernel."""
     import torch
     from caribou_hi_b200 import Engine
 
     rng = np.random.default_rng(41)
     B, N, S = 8000, 4, 96  # past the small-batch forms (batch_is_small in csrc/chi.cu)
     v = np.linspace(-40, 40, S)
+    va = np.linspace(-30, 30, S) if two_axes else v
     inp = {
         "velocity": rng.normal(0, 8, (B, N)),
         "fwhm2": rng.uniform(5, 200, (B, N)),
@@ -627,11 +630,11 @@ def test_negative_depths_in_a_large_batch(cuda_device, sightlines):
     eng = Engine("physics", N, lorentzian=False, bg_temp=3.77)
     if sightlines == 1:
         eng.set_spectra(emission=dict(spectral=v, brightness=ye[0], noise=0.3, offset=0.0),
-                        absorption=dict(spectral=v, brightness=ya[0], noise=0.02, offset=0.0))
+                        absorption=dict(spectral=va, brightness=ya[0], noise=0.02, offset=0.0))
         sl_arg = None
     else:
         eng.set_spectra(emission=dict(spectral=v, brightness=ye, noise=0.3, offset=0.0),
-                        absorption=dict(spectral=v, brightness=ya, noise=0.02, offset=0.0), n_sightlines=sightlines)
+                        absorption=dict(spectral=va, brightness=ya, noise=0.02, offset=0.0), n_sightlines=sightlines)
         sl_arg = sl
     theta = eng.pack(inp)
     n0 = eng.launch_count()
@@ -651,7 +654,7 @@ def test_negative_depths_in_a_large_batch(cuda_device, sightlines):
     ref_g = {k: np.zeros((B, N)) for k in inp}
     for s in range(sightlines):
         m = sl == s if sightlines > 1 else np.ones(B, bool)
-        data = {"emission": mr.OracleData(v, ye[s], 0.3), "absorption": mr.OracleData(v, ya[s], 0.02)}
+        data = {"emission": mr.OracleData(v, ye[s], 0.3), "absorption": mr.OracleData(va, ya[s], 0.02)}
         for d in data.values():
             d._brightness_offset = 0.0
         it = {k: torch.tensor(x[m], requires_grad=True) for k, x in inp.items()}
@@ -673,7 +676,7 @@ def test_negative_depths_in_a_large_batch(cuda_device, sightlines):
         assert_close(got[name][fin], ref_g[name][fin], what=f"d/d{name} of a batch with marked draws")
     if sightlines == 1:
         # the spectra kernels choose between their two loops per block (= per draw) from the same marks
-        data = {"emission": mr.OracleData(v, ye[0], 0.3), "absorption": mr.OracleData(v, ya[0], 0.02)}
+        data = {"emission": mr.OracleData(v, ye[0], 0.3), "absorption": mr.OracleData(va, ya[0], 0.02)}
         for d in data.values():
             d._brightness_offset = 0.0
         with np.errstate(all="ignore"):
