@@ -403,7 +403,8 @@ int small_args(chi_handle* h, Lane& L, int64_t B, const double* theta, const dou
 // becomes ~ 9 + 1.7 w.
 // CHI_OPT_NUTS_TICK: 0 = by size, 1 = graph with the round-1 tick, 2 = graph with the staged tick, 3 = the chain
 // kernel with 256 threads whenever it can run (bit-identical to 2 + the one-launch evaluation with one block per
-// draw), 4 = the chain kernel with 512 threads where it can (else 256).
+// draw), 4 = the chain kernel with 512 threads where it can (else 256), 5 = the cluster form, 6 = the speculative
+// form (a ninth warp runs the state machine next to the evaluation; same draws as 3).
 #define CHI_CHAIN_TICKS 2048
 // blocks per chain of the chain kernel's CLUSTER form (k_nuts_chain_cl), 0 = not that form: every block of every
 // chain has to be resident (two blocks per SM), and a cluster has at most 8 blocks
@@ -432,9 +433,11 @@ int nuts_chain_threads(const chi_handle* h, int64_t B) {
   const bool wide_ok = N <= 8 && B <= (int64_t)h->n_sm;
   if (mode == 3) return CHI_SM_THREADS;
   if (mode == 4) return wide_ok ? 512 : CHI_SM_THREADS;
+  if (mode == 6) return CHI_SM_THREADS + 32;  // the speculative form (nuts_chain.cuh: k_nuts_chain_spec)
   const int64_t S = std::max(h->has_e ? h->e.S : 0, h->has_a ? h->a.S : 0);
   const int64_t work = (int64_t)N * S * (h->cfg.lorentzian ? 3 : 2) / 2;
   if (B > 8 * (int64_t)h->n_sm) return 0;
+  if (work <= 6500 && B <= (int64_t)h->n_sm) return CHI_SM_THREADS + 32;  // one block per SM: the speculative form
   if (wide_ok && work <= 14000) return 512;
   return work <= 6500 ? CHI_SM_THREADS : 0;
 }
@@ -2415,7 +2418,8 @@ int chi_nuts_sample(chi_handle* h, const chi_nuts_config* cfg, const double* ini
     CK(cudaGetLastError());
   } else if (chain_kernel) {
     rc = small_args(h, h->lanes[0], B, s.eu, nbe ? s.ece : nullptr, nba ? s.eca : nullptr, d_sl, s.elogp, s.egu,
-                    nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, 1, &chain_args, &chain_nl, &chain_dyn, chain_threads);
+                    nbe ? s.egce : nullptr, nba ? s.egca : nullptr, true, 1, &chain_args, &chain_nl, &chain_dyn,
+                    chain_threads == 512 ? 512 : CHI_SM_THREADS);
     if (rc) return rc;
     if (chain_args.n_chunks != 1) return fail(h, CHI_ECUDA, "chi_nuts_sample: the chain kernel needs one block per draw");
     if (launch_eval_small(chain_nl, h->cfg.lorentzian != 0, h->map, chain_args, chain_dyn, st))

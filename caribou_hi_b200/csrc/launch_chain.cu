@@ -11,7 +11,10 @@ namespace {
 template <int NL, bool PV>
 int run_chain(int threads, const MapCfg& cfg, const SmallArgs& a, const NutsState& s, const NutsAsync& A, int max_ticks,
               size_t gb_bytes, cudaStream_t st) {
-  if (threads == 512) {
+  if (threads == CHI_SPEC_THREADS) {  // the state machine on a ninth warp, next to the evaluation
+    if (sm_allow_dyn(k_nuts_chain_spec<NL, PV>, gb_bytes)) return -2;
+    k_nuts_chain_spec<NL, PV><<<(unsigned)a.B, CHI_SPEC_THREADS, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
+  } else if (threads == 512) {
     if (sm_allow_dyn(k_nuts_chain<NL, PV, 512>, gb_bytes)) return -2;
     k_nuts_chain<NL, PV, 512><<<(unsigned)a.B, 512, gb_bytes, st>>>(cfg, a, s, A, max_ticks);
   } else {

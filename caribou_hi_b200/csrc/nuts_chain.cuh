@@ -66,6 +66,207 @@ __global__ void __launch_bounds__(NT, NT == CHI_SM_THREADS ? 2 : 1) k_nuts_chain
   }
 }
 
+// ---- the speculative form: the state machine NEXT TO the evaluation ---------------------------------------------
+// In the common tick (a leaf inside a sub-tree) the next evaluation point depends on the gradient that has just
+// arrived and on nothing else: x' = x + h M^-1 (p + h g); everything else the tick does for the finished leaf --
+// energy, acceptance, multinomial choice, the U-turn checks against the checkpoints -- only decides whether the
+// sub-tree goes on.  So a ninth warp runs the state machine: it computes and publishes the next point FIRST, the
+// eight evaluating warps start on it at once, and the bookkeeping of the finished leaf runs next to the
+// evaluation instead of in front of it (3.8 of a 14 us tick).  When the bookkeeping says the sub-tree has ended
+// (a U-turn, a divergence: a handful of leaves per iteration) the evaluation in flight is of a point nobody
+// wants: its result is dropped, the general path computes the real next point and that is evaluated.  Same
+// arithmetic in the same order for everything that is kept: bit-identical draws.
+#define CHI_SPEC_THREADS (CHI_SM_THREADS + 32)
+#define CHI_FOR_D(d) for (int d = lane; d < s.D; d += 32)
+
+__device__ __forceinline__ void chain_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(CHI_SPEC_THREADS) : "memory"); }
+
+// nw_leaf_staged with the drift moved to the front: `point` receives the next evaluation point and `go()` (called
+// by every lane) releases the evaluating warps, both only if the sub-tree can go on (*released says so).  Returns
+// what nw_leaf_staged returns.
+// `cached`: the previous tick of this chain was such a leaf and the sub-tree went on, so the position of the leaf
+// now finished (= the point just evaluated, still in `point`), its half-step momentum (wph), the inverse mass and
+// the sub-tree's momentum sum are in shared memory from that tick: only the gradient comes from global memory.
+template <class Go>
+__device__ __forceinline__ bool nw_leaf_spec(const NutsState& s, int64_t b, int lane, const NwStage& w, double* point,
+                                             double* wph, const bool cached, bool* released, Go go) {
+  const int leaf = s.leaf[b];
+  const int depth = s.depth[b];
+  const int64_t o = b * s.D;
+  const double h = s.dir[b] * s.eps[b];
+  const double lp = s.elogp[b];
+  const double energy0 = s.energy0[b], lw_sub = s.lw_sub[b];
+  double kin = 0.0;
+  CHI_FOR_D(d) {
+    const double x = cached ? point[d] : nuts_ev(s.eu, s.ece, s.eca, s, b, d);
+    const double im = cached ? w.im[d] : s.inv_mass[o + d];
+    double g = 0.0, p = 0.0;
+    if (s.role[d] == 1) {
+      g = nuts_grad(s, b, d);
+      p = (cached ? wph[d] : s.ph[o + d]) + 0.5 * h * g;
+      kin += 0.5 * im * p * p;
+    }
+    const double rs = (cached ? w.rs[d] : s.rsum_s[o + d]) + p;
+    w.x[d] = x; w.g[d] = g; w.p[d] = p; w.im[d] = im; w.rs[d] = rs;
+    s.qc[o + d] = x;
+    s.gc[o + d] = g;
+    s.pc[o + d] = p;
+    s.rsum_s[o + d] = rs;
+  }
+  *released = leaf + 1 < (1 << depth);
+  if (*released) {
+    // ---- first half of the next leapfrog step, ahead of the bookkeeping (nw_leaf_staged does it last) ----
+    __syncwarp();
+    CHI_FOR_D(d) {
+      double x = w.x[d];
+      if (s.role[d] == 1) {
+        const double ph = w.p[d] + 0.5 * h * w.g[d];
+        s.ph[o + d] = ph;
+        wph[d] = ph;
+        x += h * w.im[d] * ph;
+      }
+      point[d] = x;
+    }
+    __syncwarp();
+    CHI_FOR_D(d) {
+      if (s.role[d] == 2) point[d] = point[d - (d % s.N)];
+    }
+    __syncwarp();
+    CHI_FOR_D(d) nuts_ev(s.eu, s.ece, s.eca, s, b, d) = point[d];
+    go();
+  }
+  kin = nw_sum(kin);
+  double energy = -lp + kin;
+  if (!(energy == energy) || isinf(energy)) energy = INFINITY;
+  const double delta = energy - energy0;
+  const bool diverging = !(delta <= 1000.0);
+  const double lw_leaf = -delta;
+  const double lw_new = nuts_logaddexp(lw_sub, lw_leaf);
+  int take = 0;
+  if (lane == 0) {
+    unsigned long long st = s.rng[b];
+    take = nuts_uniform(st) < exp(lw_leaf - lw_new);
+    s.rng[b] = st;
+  }
+  take = __shfl_sync(0xffffffffu, take, 0);
+  if (lane == 0) {
+    s.leaf[b] = leaf + 1;
+    s.sum_acc[b] += (delta == delta) ? fmin(1.0, exp(-delta)) : 0.0;
+    s.n_leap[b] += 1;
+    s.lw_sub[b] = lw_new;
+    if (take) s.logp_s[b] = lp;
+    if (diverging) s.diverged[b] = 1;
+  }
+  if (take) {
+    CHI_FOR_D(d) {
+      s.qs[o + d] = w.x[d];
+      s.gs[o + d] = w.g[d];
+    }
+  }
+  bool turning = false;
+  const int idx_max = __popc((unsigned)leaf >> 1);
+  double* ckr = s.ck_r + (b * CHI_NUTS_MAX_DEPTH) * s.D;
+  double* ckrs = s.ck_rs + (b * CHI_NUTS_MAX_DEPTH) * s.D;
+  if ((leaf & 1) == 0) {
+    CHI_FOR_D(d) {
+      ckr[idx_max * s.D + d] = w.p[d];
+      ckrs[idx_max * s.D + d] = w.rs[d];
+    }
+  } else {
+    const int n_sub = __ffs(~(unsigned)leaf) - 1;
+    const int idx_min = idx_max - n_sub + 1;
+    for (int i = idx_max; i >= idx_min && !turning; --i) {
+      const double* ca = ckr + i * s.D;
+      const double* cs = ckrs + i * s.D;
+      double da = 0.0, db = 0.0;
+      CHI_FOR_D(d) {
+        if (s.role[d] != 1) continue;
+        const double a = ca[d], bb = w.p[d];
+        const double rsum = (w.rs[d] - cs[d] + a) - 0.5 * (a + bb);
+        da += w.im[d] * a * rsum;
+        db += w.im[d] * bb * rsum;
+      }
+      da = nw_sum(da);
+      db = nw_sum(db);
+      turning = da <= 0.0 || db <= 0.0;
+    }
+  }
+  int stop = 0;
+  if (turning || diverging) stop = turning ? 2 : 3;
+  if (lane == 0 && stop) s.sub_stop[b] = stop;
+  __syncwarp();
+  return !(stop != 0 || leaf + 1 >= (1 << depth));
+}
+#undef CHI_FOR_D
+
+// barriers between the state-machine warp and the evaluating warps (all CHI_SPEC_THREADS threads):
+//   3 "a point is published (s_go = 1) or the kernel ends (s_go = 0)",  4 "its evaluation is complete"
+template <int NL, bool PV>
+__global__ void __launch_bounds__(CHI_SPEC_THREADS, 1) k_nuts_chain_spec(MapCfg cfg, SmallArgs a, NutsState s, NutsAsync A, int max_ticks) {
+  __shared__ SmSmem S;
+  __shared__ double s_stage[6][CHI_NUTS_MAXD];
+  __shared__ double s_point[CHI_NUTS_MAXD];
+  __shared__ int s_go;
+  extern __shared__ double s_gb_dyn[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t b = blockIdx.x;
+  if (A.iter[b] >= A.n_total) return;  // finished in an earlier launch
+  const int nu = CHI_NSLOT * s.N;
+  if (tid < CHI_SM_THREADS) sm_init(S, cfg, a.rm);
+  __syncthreads();
+  if (tid < CHI_SM_THREADS) {
+    // ---- the evaluating warps ----
+    for (;;) {
+      chain_bar(3);
+      if (!s_go) break;
+      sm_eval<NL, PV, SM_CHAIN, CHI_SM_THREADS, true>(S, s_gb_dyn, a, b, 0, s_point, s.nbe ? s_point + nu : nullptr,
+                                                      s.nba ? s_point + nu + s.nbe : nullptr);
+      sm_sync<true, CHI_SM_THREADS>();  // logp and gradient are written
+      chain_bar(4);
+    }
+    return;
+  }
+  // ---- the state-machine warp ----
+  const NwStage w = {s_stage[0], s_stage[1], s_stage[2], s_stage[3], s_stage[4]};
+  auto publish = [&]() {  // the evaluation point as the general path left it in global memory
+    for (int d = lane; d < s.D; d += 32) s_point[d] = nuts_ev(s.eu, s.ece, s.eca, s, b, d);
+    if (lane == 0) s_go = 1;
+    __syncwarp();
+    chain_bar(3);
+  };
+  bool done = false;
+  for (int t = 0; t < max_ticks; ++t) {
+    // here the logp / gradient of the point last published are in global memory
+    const int started = A.started[b];
+    __syncwarp();
+    const bool cached = done;  // the previous tick was a leaf and its sub-tree went on
+    done = false;
+    if (started) {
+      bool released = false;
+      done = nw_leaf_spec(s, b, lane, w, s_point, s_stage[5], cached, &released, [&]() {
+        if (lane == 0) s_go = 1;
+        __syncwarp();
+        chain_bar(3);
+      });
+      if (!done) {
+        nw_tick_rest<CHI_MODEL_PHYSICS>(s, A, S.cfg, S.rm, nullptr, nullptr, b, lane, 1, true);
+        if (released) chain_bar(4);  // the evaluation in flight is of a point nobody wants: let it finish, drop it
+      }
+    } else {
+      nw_tick_rest<CHI_MODEL_PHYSICS>(s, A, S.cfg, S.rm, nullptr, nullptr, b, lane, 0, false);
+    }
+    __syncwarp();
+    if (!done) {
+      if (A.iter[b] >= A.n_total) break;  // the chain has finished
+      publish();
+    }
+    chain_bar(4);  // the evaluation of the published point is complete
+  }
+  if (lane == 0) s_go = 0;
+  __syncwarp();
+  chain_bar(3);
+}
+
 // The same with the n_chunks blocks of a chain as one thread-block CLUSTER (small.cuh, SM_CLUSTER), for models
 // whose channel sums want more than one SM per chain (configs[2]: 8 clouds x 2048+2048 channels): the cluster's
 // first block runs the chain's state machine and publishes the evaluation point in its shared memory; after a

@@ -448,28 +448,15 @@ __device__ __forceinline__ bool nw_leaf_staged(const NutsState& s, int64_t b, in
   return true;
 }
 
-// one tick of chain b's state machine (see NutsAsync in nuts.cuh), by one warp.  `st`: the warp's
-// [5][CHI_NUTS_MAXD] staging area in shared memory (STAGED).  The cloud map of the new evaluation point
-// (k_cloud_map's work: transforms, parameter map, profile constants) is done here by lanes 0..N-1 when cc is
-// given, which takes one kernel out of the dependent chain of a tick; cc == null: the evaluation maps the
-// point itself (k_eval_small, k_nuts_chain).
-template <int MODEL, bool STAGED>
-__device__ __forceinline__ void nw_tick(const NutsState& s, const NutsAsync& A, const MapCfg& cfg, const RowMap& rm,
-                                        double* __restrict__ cc, double* __restrict__ xcon, const int64_t b, const int lane,
-                                        double (*st)[STAGED ? CHI_NUTS_MAXD : 1]) {
+// the rest of a tick once the leaf in flight is accounted for (`finished`: the sub-tree ended with it) or the
+// chain has not started yet: merge the sub-tree, maybe end the iteration (adapt, record, next momentum), start
+// the next sub-tree, and the first half of the next leapfrog step
+template <int MODEL>
+__device__ __forceinline__ void nw_tick_rest(const NutsState& s, const NutsAsync& A, const MapCfg& cfg, const RowMap& rm,
+                                             double* __restrict__ cc, double* __restrict__ xcon, const int64_t b, const int lane,
+                                             const int started, const bool finished) {
   int it = A.iter[b];
-  if (it >= A.n_total) return;  // finished: its evaluation point stays at the last state
-  const int started = A.started[b];
-  __syncwarp();
   if (started) {
-    bool finished;
-    if (STAGED) {
-      const NwStage w = {st[0], st[1], st[2], st[3], st[4]};
-      if (nw_leaf_staged<MODEL>(s, b, lane, w, cfg, rm, cc, xcon)) return;  // the common tick: done
-      finished = true;
-    } else {
-      finished = nw_leap_b(s, b, lane);
-    }
     if (finished) {  // the logp / gradient of the leaf in flight has arrived
       if (!nw_end_subtree(s, b, lane, A.max_depth)) {
         NutsAdapt a;
@@ -499,6 +486,26 @@ __device__ __forceinline__ void nw_tick(const NutsState& s, const NutsAsync& A, 
   }
   nw_leap_a(s, b, lane);
   if (cc && lane < s.N) cloud_map_one<MODEL>(cfg, rm, s.N, s.eu, cc, xcon, b, lane);
+}
+
+// one tick of chain b's state machine (see NutsAsync in nuts.cuh), by one warp.  `st`: the warp's
+// [5][CHI_NUTS_MAXD] staging area in shared memory (STAGED).  The cloud map of the new evaluation point
+// (k_cloud_map's work: transforms, parameter map, profile constants) is done here by lanes 0..N-1 when cc is
+// given, which takes one kernel out of the dependent chain of a tick; cc == null: the evaluation maps the
+// point itself (k_eval_small, k_nuts_chain).
+template <int MODEL, bool STAGED>
+__device__ __forceinline__ void nw_tick(const NutsState& s, const NutsAsync& A, const MapCfg& cfg, const RowMap& rm,
+                                        double* __restrict__ cc, double* __restrict__ xcon, const int64_t b, const int lane,
+                                        double (*st)[STAGED ? CHI_NUTS_MAXD : 1]) {
+  int it = A.iter[b];
+  if (it >= A.n_total) return;  // finished: its evaluation point stays at the last state
+  const int started = A.started[b];
+  __syncwarp();
+  if (started && STAGED) {
+    const NwStage w = {st[0], st[1], st[2], st[3], st[4]};
+    if (nw_leaf_staged<MODEL>(s, b, lane, w, cfg, rm, cc, xcon)) return;  // the common tick: done
+  }
+  nw_tick_rest<MODEL>(s, A, cfg, rm, cc, xcon, b, lane, started, started ? (STAGED ? true : nw_leap_b(s, b, lane)) : false);
 }
 
 // one tick of every chain; 4 chains per block

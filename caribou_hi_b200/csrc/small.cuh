@@ -503,10 +503,19 @@ __device__ __forceinline__ void sm_init(SmSmemT<NT>& S, const MapCfg& cfg, const
 // back through L2 -- which is ~5 us of a 27 us evaluation at configs[2]'s shape.  Same sums in the same order.
 enum { SM_GLOBAL = 0, SM_CHAIN = 1, SM_CLUSTER = 2 };
 
-template <int NL, bool PV, int MODE, int NT = CHI_SM_THREADS>
+// SUB: the NT evaluating threads are the first NT threads of a LARGER block (k_nuts_chain_spec: one more warp runs
+// the chain's state machine next to them), so their block barrier is a named one over NT threads.
+template <bool SUB, int NT>
+__device__ __forceinline__ void sm_sync() {
+  if (SUB) asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
+  else __syncthreads();
+}
+
+template <int NL, bool PV, int MODE, int NT = CHI_SM_THREADS, bool SUB = false>
 __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const SmallArgs& a, const int64_t b, const int chunk,
                                         const double* tb, const double* ce_b, const double* ca_b, double* xbuf = nullptr) {
   constexpr bool CHAIN = MODE == SM_CHAIN, CLUSTER = MODE == SM_CLUSTER;
+  static_assert(!SUB || CHAIN, "a sub-block evaluation is the chain kernel's");
   constexpr int NF = PV ? 10 : 6, NE = PV ? 8 : 5, NA = PV ? 6 : 3;
   double* const s_T = S.T;
   double* const s_cc = S.cc;
@@ -538,7 +547,7 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
   }
   const int n_gb = (nbe > 1 ? nbe - 1 : 0) + (nba > 1 ? nba - 1 : 0);
   for (int i = 0; i < n_gb; ++i) s_gb_dyn[i * NT + tid] = 0.0;
-  __syncthreads();
+  sm_sync<SUB, NT>();
   if (a.prior) {
     // the transforms of the draw's free RVs, one thread each (the channel warps have nothing else to do yet)
     if (tid < N * CHI_NSLOT) {
@@ -546,7 +555,7 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
       const double u = s_rm.row[sl_] >= 0 ? tb[(int64_t)s_rm.row[sl_] * N + n] : 0.0;
       S.tr[tid] = sm_transform(&s_cfg, sl_, u);
     }
-    __syncthreads();
+    sm_sync<SUB, NT>();
   }
 
   // where the draw's records meet: the first block of the cluster, or the workspace in global memory
@@ -652,7 +661,7 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
     }
   }
   if (a.stamps) t_chan = clock64();
-  __syncthreads();
+  sm_sync<SUB, NT>();
   if (a.stamps && b == 0 && chunk == 0 && lane == 0 && (warp == 0 || warp == (NT / 32) - 1)) {
     long long* o = a.stamps + (warp == 0 ? 0 : 8);
     o[0] = t_map - t_0; o[1] = t_jac - t_0; o[2] = t_chan - t_0; o[3] = clock64() - t_0;
@@ -687,13 +696,13 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
       rec[t] = v;
     }
     __threadfence();
-    __syncthreads();
+    sm_sync<SUB, NT>();
     if (tid == 0) {
       const unsigned done = atomicAdd(a.counter + b, 1u);
       s_last = (done == (unsigned)a.n_chunks - 1u);
       if (s_last) a.counter[b] = 0;  // ready for the next launch
     }
-    __syncthreads();
+    sm_sync<SUB, NT>();
     if (a.stamps && b == 0 && chunk == 0 && tid == 0) a.stamps[4] = clock64() - t_0;
     if (!s_last) return;
     __threadfence();
@@ -715,7 +724,7 @@ __device__ __forceinline__ void sm_eval(SmSmemT<NT>& S, double* s_gb_dyn, const 
   }
   // the per-cloud prior terms of the draw (written by the Jacobian warps of its blocks)
   if (a.prior && tid < N) s_red[0][tid] = CLUSTER ? prior_b[tid] : __ldcg(prior_b + tid);
-  __syncthreads();
+  sm_sync<SUB, NT>();
   const bool use_e = a.fused || a.has_e, use_a = a.fused || a.has_a;
   const int nbe_u = use_e ? nbe : 0, nba_u = use_a ? nba : 0;
   if (tid < nbe + nba) {

@@ -810,7 +810,7 @@ class Engine:
         """Tuning / test knobs (``chi_set_option``): ``small_path`` 0 by batch size, 1 never, 2 always
         (the one-launch evaluation of small batches); ``small_nl`` clouds per thread of that kernel;
         ``small_chunks`` its blocks per draw; ``nuts_tick`` 0 by model size, 1 / 2 graph of kernels per tick
-        (global-memory / staged tick), 3 / 4 / 5 the per-chain kernel (256 / 512 threads / a cluster of blocks per chain); ``dev_overlap``, ``ea_one_pass``, ``small_cluster``: ``include/chi.h``."""
+        (global-memory / staged tick), 3 / 4 / 5 / 6 the per-chain kernel (256 / 512 threads / a cluster of blocks per chain / speculative); ``dev_overlap``, ``ea_one_pass``, ``small_cluster``: ``include/chi.h``."""
         opts = {"small_path": _lib.OPT_SMALL_PATH, "small_nl": _lib.OPT_SMALL_NL, "small_chunks": _lib.OPT_SMALL_CHUNKS,
                 "small_stamps": _lib.OPT_SMALL_STAMPS, "nuts_tick": _lib.OPT_NUTS_TICK,
                 "dev_overlap": _lib.OPT_DEV_OVERLAP, "ea_one_pass": _lib.OPT_EA_ONE_PASS, "small_cluster": _lib.OPT_SMALL_CLUSTER}

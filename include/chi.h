@@ -472,7 +472,11 @@ int64_t chi_launch_count(const chi_handle* h);
                                       (<= 16 clouds); same draws as 2 with CHI_OPT_SMALL_PATH 2, CHI_OPT_SMALL_CHUNKS 1;
                                   4 = that kernel with 512 threads per chain where it can (<= 8 clouds, chains <= SMs);
                                   5 = that kernel with the 2..8 blocks of a chain as a thread-block cluster (for models
-                                      whose channel sums want more than one SM per chain; needs chains <= SMs) */
+                                      whose channel sums want more than one SM per chain; needs chains <= SMs);
+                                  6 = that kernel with the chain's state machine on a ninth warp: the next point is
+                                      published first and the bookkeeping of the finished leaf runs next to its
+                                      evaluation (same draws as 3 bit for bit; the default for small models when
+                                      chains <= SMs) */
 #define CHI_OPT_DEV_OVERLAP 5  /* 1 = consecutive chi_logp_grad[_rows]_dev calls of large batches alternate between
                                   two internal lanes and may overlap (map / epilogue of one call next to the channel
                                   kernel of the other); each call still starts after everything enqueued on the

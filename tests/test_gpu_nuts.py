@@ -173,22 +173,27 @@ def test_chain_kernel_matches_the_graph_of_kernels(cuda_device, kind_n_shared):
     graph = _sample_with(kind, N, {"nuts_tick": 2, "small_path": 2, "small_chunks": 1}, shared=shared)
     _same_run(chain, graph)
     assert chain[2] < 60 and graph[2] > 20 * chain[2], (chain[2], graph[2])
+    # the speculative form (the state machine on a ninth warp, next to the evaluation): the same draws again
+    spec = _sample_with(kind, N, {"nuts_tick": 6}, shared=shared)
+    _same_run(spec, chain)
+    assert spec[2] < 60
     # the cluster form: the blocks of a chain (8 asked for; what the channel count allows) as one thread-block
     # cluster, against the same graph with that many blocks per draw
     cluster = _sample_with(kind, N, {"nuts_tick": 5}, shared=shared)
     graph_cl = _sample_with(kind, N, {"nuts_tick": 2, "small_path": 2, "small_chunks": 8}, shared=shared)
     _same_run(cluster, graph_cl)
     assert cluster[2] < 60
-    # a model this small takes the chain kernel by itself, in its wide form (512 threads per chain: the channels
-    # are spread over twice the warps, so the sums agree with the 256-thread form to rounding and the chains part
-    # ways after a while; the first draws of the warm-up still agree closely)
+    # a model this small takes the speculative chain kernel by itself
     auto = _sample_with(kind, N, {}, shared=shared)
+    _same_run(auto, spec)
+    assert auto[2] == spec[2]
+    # the wide form (512 threads per chain: the channels are spread over twice the warps, so the sums agree with
+    # the 256-thread form to rounding and the chains part ways after a while)
     wide = _sample_with(kind, N, {"nuts_tick": 4}, shared=shared)
-    _same_run(auto, wide)
-    assert auto[2] < 60
+    assert wide[2] < 60
     for k in ("accept", "depth"):
-        assert np.all(np.isfinite(auto[1][k]))
-    assert abs(auto[1]["accept"].mean() - chain[1]["accept"].mean()) < 0.25, (auto[1]["accept"].mean(), chain[1]["accept"].mean())
+        assert np.all(np.isfinite(wide[1][k]))
+    assert abs(wide[1]["accept"].mean() - chain[1]["accept"].mean()) < 0.25, (wide[1]["accept"].mean(), chain[1]["accept"].mean())
 
 
 def test_chain_kernels_with_one_sightline_per_chain(cuda_device):
