@@ -87,22 +87,44 @@ __device__ __forceinline__ void chain_bar(int id) { asm volatile("bar.sync %0, %
 // `cached`: the previous tick of this chain was such a leaf and the sub-tree went on, so the position of the leaf
 // now finished (= the point just evaluated, still in `point`), its half-step momentum (wph), the inverse mass and
 // the sub-tree's momentum sum are in shared memory from that tick: only the gradient comes from global memory.
+// The leaf's scalars travel in registers from one such tick to the next (LeafRegs); `role` is the block's copy of
+// s.role in shared memory.
+// nuts_grad with the roles from shared memory
+__device__ __forceinline__ double chain_grad(const NutsState& s, const int* role, int64_t b, int d) {
+  double g = nuts_ev(s.egu, s.egce, s.egca, s, b, d);
+  if (d < CHI_NSLOT * s.N && (d % s.N) == 0) {
+    for (int n = 1; n < s.N; ++n)
+      if (role[d + n] == 2) g += nuts_ev(s.egu, s.egce, s.egca, s, b, d + n);
+  }
+  return g;
+}
+struct LeafRegs {
+  int leaf, depth;
+  double h, energy0, lw_sub;
+};
 template <class Go>
 __device__ __forceinline__ bool nw_leaf_spec(const NutsState& s, int64_t b, int lane, const NwStage& w, double* point,
-                                             double* wph, const bool cached, bool* released, Go go) {
-  const int leaf = s.leaf[b];
-  const int depth = s.depth[b];
+                                             double* wph, const int* role, LeafRegs& c, const bool cached, bool* released,
+                                             Go go) {
+  if (!cached) {
+    c.leaf = s.leaf[b];
+    c.depth = s.depth[b];
+    c.h = s.dir[b] * s.eps[b];
+    c.energy0 = s.energy0[b];
+    c.lw_sub = s.lw_sub[b];
+  }
+  const int leaf = c.leaf;
+  const int depth = c.depth;
   const int64_t o = b * s.D;
-  const double h = s.dir[b] * s.eps[b];
-  const double lp = s.elogp[b];
-  const double energy0 = s.energy0[b], lw_sub = s.lw_sub[b];
+  const double h = c.h;
+  const double energy0 = c.energy0, lw_sub = c.lw_sub;
   double kin = 0.0;
   CHI_FOR_D(d) {
     const double x = cached ? point[d] : nuts_ev(s.eu, s.ece, s.eca, s, b, d);
     const double im = cached ? w.im[d] : s.inv_mass[o + d];
     double g = 0.0, p = 0.0;
-    if (s.role[d] == 1) {
-      g = nuts_grad(s, b, d);
+    if (role[d] == 1) {
+      g = chain_grad(s, role, b, d);
       p = (cached ? wph[d] : s.ph[o + d]) + 0.5 * h * g;
       kin += 0.5 * im * p * p;
     }
@@ -119,7 +141,7 @@ __device__ __forceinline__ bool nw_leaf_spec(const NutsState& s, int64_t b, int 
     __syncwarp();
     CHI_FOR_D(d) {
       double x = w.x[d];
-      if (s.role[d] == 1) {
+      if (role[d] == 1) {
         const double ph = w.p[d] + 0.5 * h * w.g[d];
         s.ph[o + d] = ph;
         wph[d] = ph;
@@ -129,12 +151,13 @@ __device__ __forceinline__ bool nw_leaf_spec(const NutsState& s, int64_t b, int 
     }
     __syncwarp();
     CHI_FOR_D(d) {
-      if (s.role[d] == 2) point[d] = point[d - (d % s.N)];
+      if (role[d] == 2) point[d] = point[d - (d % s.N)];
     }
     __syncwarp();
     CHI_FOR_D(d) nuts_ev(s.eu, s.ece, s.eca, s, b, d) = point[d];
     go();
   }
+  const double lp = s.elogp[b];
   kin = nw_sum(kin);
   double energy = -lp + kin;
   if (!(energy == energy) || isinf(energy)) energy = INFINITY;
@@ -180,7 +203,7 @@ __device__ __forceinline__ bool nw_leaf_spec(const NutsState& s, int64_t b, int 
       const double* cs = ckrs + i * s.D;
       double da = 0.0, db = 0.0;
       CHI_FOR_D(d) {
-        if (s.role[d] != 1) continue;
+        if (role[d] != 1) continue;
         const double a = ca[d], bb = w.p[d];
         const double rsum = (w.rs[d] - cs[d] + a) - 0.5 * (a + bb);
         da += w.im[d] * a * rsum;
@@ -195,6 +218,8 @@ __device__ __forceinline__ bool nw_leaf_spec(const NutsState& s, int64_t b, int 
   if (turning || diverging) stop = turning ? 2 : 3;
   if (lane == 0 && stop) s.sub_stop[b] = stop;
   __syncwarp();
+  c.leaf = leaf + 1;
+  c.lw_sub = lw_new;
   return !(stop != 0 || leaf + 1 >= (1 << depth));
 }
 #undef CHI_FOR_D
@@ -207,12 +232,14 @@ __global__ void __launch_bounds__(CHI_SPEC_THREADS, 1) k_nuts_chain_spec(MapCfg 
   __shared__ double s_stage[6][CHI_NUTS_MAXD];
   __shared__ double s_point[CHI_NUTS_MAXD];
   __shared__ int s_go;
+  __shared__ int s_role[CHI_NUTS_MAXD];
   extern __shared__ double s_gb_dyn[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t b = blockIdx.x;
   if (A.iter[b] >= A.n_total) return;  // finished in an earlier launch
   const int nu = CHI_NSLOT * s.N;
   if (tid < CHI_SM_THREADS) sm_init(S, cfg, a.rm);
+  for (int d = tid; d < s.D; d += CHI_SPEC_THREADS) s_role[d] = s.role[d];
   __syncthreads();
   if (tid < CHI_SM_THREADS) {
     // ---- the evaluating warps ----
@@ -235,6 +262,7 @@ __global__ void __launch_bounds__(CHI_SPEC_THREADS, 1) k_nuts_chain_spec(MapCfg 
     chain_bar(3);
   };
   bool done = false;
+  LeafRegs regs = {0, 0, 0.0, 0.0, 0.0};
   for (int t = 0; t < max_ticks; ++t) {
     // here the logp / gradient of the point last published are in global memory
     const int started = A.started[b];
@@ -243,7 +271,7 @@ __global__ void __launch_bounds__(CHI_SPEC_THREADS, 1) k_nuts_chain_spec(MapCfg 
     done = false;
     if (started) {
       bool released = false;
-      done = nw_leaf_spec(s, b, lane, w, s_point, s_stage[5], cached, &released, [&]() {
+      done = nw_leaf_spec(s, b, lane, w, s_point, s_stage[5], s_role, regs, cached, &released, [&]() {
         if (lane == 0) s_go = 1;
         __syncwarp();
         chain_bar(3);
