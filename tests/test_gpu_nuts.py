@@ -234,6 +234,9 @@ def test_chain_kernels_with_one_sightline_per_chain(cuda_device):
     for k in ("u", "accept", "depth", "logp", "step_size", "coeff_e", "coeff_a"):
         assert np.array_equal(chain[k], graph[k], equal_nan=True), k
     assert chain["launches"] < 300 and graph["launches"] > 20 * chain["launches"], (chain["launches"], graph["launches"])
+    spec, _ = run({"nuts_tick": 6})
+    for k in ("u", "accept", "depth", "logp", "step_size"):
+        assert np.array_equal(spec[k], chain[k], equal_nan=True), k
     cluster, _ = run({"nuts_tick": 5})
     graph_cl, _ = run({"nuts_tick": 2, "small_path": 2, "small_chunks": 8})
     for k in ("u", "accept", "depth", "logp"):
