@@ -38,6 +38,17 @@ def test_header_constants_match_binding():
     enum = dict(re.findall(r"(CHI_MODEL_[A-Z_]+) = (\d+)", text))
     for k, v in enum.items():
         assert getattr(_lib, k.replace("CHI_", "")) == int(v)
+    # every chi_set_option knob of the header has its constant in the binding and its name in Engine.set_option
+    import inspect
+    from caribou_hi_b200 import engine
+
+    opts = dict(re.findall(r"#define (CHI_OPT_[A-Z_]+) (\d+)", text))
+    count = int(opts.pop("CHI_OPT_COUNT"))
+    assert len(opts) >= 8 and max(map(int, opts.values())) < count
+    src = inspect.getsource(engine.Engine.set_option)
+    for k, v in opts.items():
+        assert getattr(_lib, k.replace("CHI_", "")) == int(v), k
+        assert f"_lib.{k.replace('CHI_', '')}" in src, f"{k} is not reachable through Engine.set_option"
 
 
 def test_no_cpu_fallback():
