@@ -165,6 +165,13 @@ struct chi_handle {
   int64_t launches = 0;
   int64_t opt[CHI_OPT_COUNT] = {};  // chi_set_option
   int64_t dev_calls = 0;            // CHI_OPT_DEV_OVERLAP: device-resident calls issued (lane rotation)
+  // two-launch forms of the large-batch kernels (moments_ea.cuh, MODE): the EA_FIXUP launch counts the draws it
+  // evaluated; the count is copied to pinned memory behind it and read, without waiting, by later calls -- a
+  // handle whose batches are full of marked draws goes back to the one-launch form (see two_pass_ok)
+  Buf marked_dev;                                 // [CHI_LANES] counters
+  unsigned long long* marked_host = nullptr;      // pinned [CHI_LANES]
+  int64_t marked_B[CHI_LANES] = {};               // draws of the call whose count is (being) copied there
+  int64_t dense_calls = 0;
   cudaEvent_t ev_dev_in = nullptr;
   // multi-GPU (comm.cuh): communicator, its stream, and the workspace of k_shard_sums
   NcclComm comm = nullptr;
@@ -475,6 +482,33 @@ int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const doub
   return CHI_OK;
 }
 
+// The two-launch forms pay off while marked draws are rare: EA_FIXUP's persistent scan evaluates a marked draw
+// ~1.7x slower than the one launch does (measured: every draw marked 2.45 against 1.47 ms, 1 % marked 1.46 against
+// 1.47, none 1.41 against 1.47; tools/marked_batch_bench.py).  A recent COMPLETED call's count of marked draws above
+// 0.5 % of its batch sends the handle back to the one-launch form; every 64th call tries the two launches again.
+bool two_pass_ok(chi_handle* h) {
+  if (h->opt[CHI_OPT_EA_ONE_PASS]) return false;
+  bool dense = false;
+  if (h->marked_host)
+    for (int i = 0; i < CHI_LANES; ++i)
+      if (h->marked_B[i] > 0 && (int64_t)h->marked_host[i] * 200 > h->marked_B[i]) dense = true;
+  if (!dense) return true;
+  return (++h->dense_calls % 64) == 0;
+}
+// the counter of lane L for an EA_FIXUP launch on `st`, zeroed there; null if it cannot be had
+unsigned long long* marked_counter(chi_handle* h, Lane& L, cudaStream_t st) {
+  if (!h->marked_host || !h->marked_dev.p) return nullptr;
+  unsigned long long* c = (unsigned long long*)h->marked_dev.p + (&L - h->lanes);
+  if (cudaMemsetAsync(c, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
+  return c;
+}
+// behind the EA_FIXUP launch: its count to pinned memory (not inside a capture: a replay would not update marked_B)
+void marked_readback(chi_handle* h, Lane& L, unsigned long long* c, int64_t B, cudaStream_t st) {
+  if (!c || h->capturing) return;
+  const int i = (int)(&L - h->lanes);
+  if (cudaMemcpyAsync(h->marked_host + i, c, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) == cudaSuccess) h->marked_B[i] = B;
+}
+
 // moments (+ optional logp) + epilogue; gbar_* != null selects the VJP mode
 // `model` = true: theta holds unconstrained values; priors and Jacobians are added (chi_model_logp_grad)
 enum { PHASE_ALL = 0, PHASE_MAP = 1, PHASE_REST = 2 };
@@ -566,11 +600,13 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     a.basis_a = h->a.basis.d(); a.coeff_a = ca;
     a.vjp = vjp ? 1 : 0; a.gbar_e = vjp ? gbar_e : nullptr; a.gbar_a = vjp ? gbar_a : nullptr;
     a.sl = sl; a.cc = L.cc.d(); a.mom = L.mom_e.d();
-    if (!small && !h->opt[CHI_OPT_EA_ONE_PASS] && moments_ea_two_pass(N, pv, a)) {
-      // the marked draws (a negative or NaN optical depth; normally none) on a few resident blocks next to
-      // the big grid, which then runs without the overflow branch of 2^y (moments_ea.cuh, MODE)
+    if (!small && moments_ea_two_pass(N, pv, a) && two_pass_ok(h)) {
+      // the marked draws (a negative or huge optical depth; normally none) on a wave of resident blocks next to
+      // the big grid, which then runs without the range selects of exp(-tau) (moments_ea.cuh, MODE)
       CK(cudaStreamWaitEvent(L.aux, L.ev_fork, 0));
+      a.n_marked = marked_counter(h, L, L.aux);
       if (launch_moments_ea_fixup(N, a, h->n_sm, L.aux)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+      marked_readback(h, L, a.n_marked, B, L.aux);
       CK(cudaEventRecord(L.ev_join, L.aux));
       if (launch_moments_ea_tame(N, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
       CK(cudaStreamWaitEvent(L.st, L.ev_join, 0));
@@ -598,10 +634,12 @@ int run_backward(chi_handle* h, Lane& L, int64_t B, const double* theta, const d
     CK(L.mom_e.ensure((size_t)B * a.n_chunks * a.mom_stride * sizeof(double)));
     a.chan = h->e.chan.d(); a.basis = h->e.basis.d();
     a.coeff = ce; a.sl = sl; a.gbar = vjp ? gbar_e : nullptr; a.cc = L.cc.d(); a.mom = L.mom_e.d();
-    if (!small && !h->opt[CHI_OPT_EA_ONE_PASS] && moments_em_two_pass(N, a)) {
+    if (!small && moments_em_two_pass(N, a) && two_pass_ok(h)) {
       // as for the fused kernel: the marked draws on a wave of resident blocks next to the big grid
       CK(cudaStreamWaitEvent(L.aux, L.ev_fork, 0));
+      a.n_marked = marked_counter(h, L, L.aux);
       if (launch_moments_em_fixup(N, pv, a, h->n_sm, L.aux)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
+      marked_readback(h, L, a.n_marked, B, L.aux);
       CK(cudaEventRecord(L.ev_join, L.aux));
       if (launch_moments_em_tame(N, pv, a, L.st)) return fail(h, CHI_EINVAL, "unsupported n_clouds");
       CK(cudaStreamWaitEvent(L.st, L.ev_join, 0));
@@ -1000,6 +1038,14 @@ int chi_create(chi_handle** out, int device, const chi_config* cfg) {
   h->cfg = *cfg;
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
+  // (allocated here, not at first use: a first use may be inside a stream capture)
+  if (h->marked_dev.ensure(CHI_LANES * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMallocHost(&h->marked_host, CHI_LANES * sizeof(unsigned long long)) != cudaSuccess) {
+    h->marked_host = nullptr;
+    cudaGetLastError();
+  } else {
+    memset(h->marked_host, 0, CHI_LANES * sizeof(unsigned long long));
+  }
   const int m = cfg->model;
   h->has_e = (m == CHI_MODEL_PHYSICS) ? cfg->has_emission != 0 : kind_has_emission(m);
   h->has_a = (m == CHI_MODEL_PHYSICS) ? cfg->has_absorption != 0 : kind_has_absorption(m);
@@ -1059,8 +1105,10 @@ void chi_destroy(chi_handle* h) {
     cudaEventDestroy(h->ev_comm_out);
   }
   h->sums_partial.release();
+  h->marked_dev.release();
   h->sums_counter.release();
   if (h->sums_stage) cudaFreeHost(h->sums_stage);
+  if (h->marked_host) cudaFreeHost(h->marked_host);
   for (Lane& L : h->lanes) {
     if (L.st) cudaStreamSynchronize(L.st);
     if (L.hi) cudaStreamSynchronize(L.hi);

@@ -364,6 +364,7 @@ struct ChanArgs {
   const double* __restrict__ gbar;    // [B][S] cotangent (vjp mode) or null (logp mode)
   const double* __restrict__ cc;      // [B][N][12]
   double* __restrict__ mom;           // [B][n_chunks][mom_stride]
+  unsigned long long* n_marked;        // EA_FIXUP: += the draws it evaluated (null: not counted)
 };
 
 // record layout: [0]=sum -0.5 w r^2, [1..n_base]=d/dcoeff, then per cloud NE/NA moments
@@ -604,7 +605,9 @@ __global__ void __launch_bounds__(CHI_BLOCK, em_min_blocks(N, PV)) k_moments_em(
       if (b0 + lane < a.B)
         for (int n = 0; n < a.n_real; ++n)
           m |= __ldg(a.cc + ((b0 + lane) * a.n_real + n) * CHI_CC_STRIDE + CC_CAREFUL) != 0.0;
-      for (unsigned todo = __ballot_sync(0xffffffffu, m); todo; todo &= todo - 1) {
+      const unsigned marks = __ballot_sync(0xffffffffu, m);
+      if (marks && lane == 0 && a.n_marked) atomicAdd(a.n_marked, (unsigned long long)__popc(marks));
+      for (unsigned todo = marks; todo; todo &= todo - 1) {
         const int64_t bb = b0 + (__ffs(todo) - 1);
         for (int chunk = 0; chunk < a.n_chunks; ++chunk) {
           one_item(bb * a.n_chunks + chunk);

@@ -42,6 +42,7 @@ struct FusedArgs {
   const int32_t* __restrict__ sl;
   const double* __restrict__ cc;
   double* __restrict__ mom;
+  unsigned long long* n_marked;        // EA_FIXUP: += the draws it evaluated (null: not counted)
 };
 
 template <bool PV> struct FusedLayout { static constexpr int NF = PV ? 10 : 6; };
@@ -68,9 +69,11 @@ __device__ __forceinline__ void ldg2(const double* p, double& x, double& y) {
 // kernel).  The cloud map marks the clouds whose depths are negative (cc[..][CC_CAREFUL]); a large batch
 // then runs as two launches side by side: EA_TAME over every draw without that branch (a marked draw
 // leaves at once), and EA_FIXUP, one wave of resident blocks that scan the marks and evaluate the marked
-// draws with it (normally none: the scan takes microseconds next to the other launch; a batch of nothing
-// but marked draws runs at the speed of EA_ALL).  EA_ALL is the single launch with the branch, for small
-// batches.
+// draws with it (normally none: the scan takes microseconds next to the other launch).  The scanning form
+// evaluates a marked draw ~1.7x slower than EA_ALL does (more spills around the persistent loop), so a batch FULL
+// of marked draws would lose (2.45 against 1.47 ms): EA_FIXUP counts the draws it evaluated and the host side goes
+// back to EA_ALL while recent calls had more than 0.5 % of them (two_pass_ok in chi.cu).  EA_ALL is the single
+// launch with the branch, also for small batches.
 // (enum { EA_ALL, EA_TAME, EA_FIXUP }: moments.cuh)
 
 template <int N, bool PV, bool SB, bool STAGED = false, bool VJP = true, int MODE = EA_ALL>
@@ -320,7 +323,9 @@ __global__ void __launch_bounds__(CHI_BLOCK, ea_min_blocks(N, PV)) k_moments_ea(
       if (b0 + lane < a.B)
         for (int n = 0; n < a.n_real; ++n)
           m |= __ldg(a.cc + ((b0 + lane) * a.n_real + n) * CHI_CC_STRIDE + CC_CAREFUL) != 0.0;
-      for (unsigned todo = __ballot_sync(0xffffffffu, m); todo; todo &= todo - 1) {
+      const unsigned marks = __ballot_sync(0xffffffffu, m);
+      if (marks && lane == 0 && a.n_marked) atomicAdd(a.n_marked, (unsigned long long)__popc(marks));
+      for (unsigned todo = marks; todo; todo &= todo - 1) {
         const int64_t b = b0 + (__ffs(todo) - 1);
         for (int chunk = 0; chunk < a.n_chunks; ++chunk) {
           one_item(b * a.n_chunks + chunk);
