@@ -482,8 +482,8 @@ int run_small(chi_handle* h, Lane& L, int64_t B, const double* theta, const doub
   return CHI_OK;
 }
 
-// The two-launch forms pay off while marked draws are rare: EA_FIXUP's persistent scan evaluates a marked draw
-// ~1.7x slower than the one launch does (measured: every draw marked 2.45 against 1.47 ms, 1 % marked 1.46 against
+// The two-launch forms pay off while marked draws are rare: a marked draw is one warp's work for ~34 us, and
+// EA_FIXUP's static partition balances a batch full of them badly (measured: every draw marked 2.45 against 1.47 ms, 1 % marked 1.46 against
 // 1.47, none 1.41 against 1.47; tools/marked_batch_bench.py).  A recent COMPLETED call's count of marked draws above
 // 0.5 % of its batch sends the handle back to the one-launch form; every 64th call tries the two launches again.
 bool two_pass_ok(chi_handle* h) {

@@ -69,9 +69,10 @@ __device__ __forceinline__ void ldg2(const double* p, double& x, double& y) {
 // kernel).  The cloud map marks the clouds whose depths are negative (cc[..][CC_CAREFUL]); a large batch
 // then runs as two launches side by side: EA_TAME over every draw without that branch (a marked draw
 // leaves at once), and EA_FIXUP, one wave of resident blocks that scan the marks and evaluate the marked
-// draws with it (normally none: the scan takes microseconds next to the other launch).  The scanning form
-// evaluates a marked draw ~1.7x slower than EA_ALL does (more spills around the persistent loop), so a batch FULL
-// of marked draws would lose (2.45 against 1.47 ms): EA_FIXUP counts the draws it evaluated and the host side goes
+// draws with it (normally none: the scan takes microseconds next to the other launch).  The scan is
+// built for FEW marks: a marked draw is one warp's work for ~34 us whatever the rest of the machine does, and the
+// static partition (32 draws per warp and pass) balances a batch FULL of marked draws badly -- 64 draws on some
+// warps, 32 on others: 2.45 against 1.47 ms.  So EA_FIXUP counts the draws it evaluated and the host side goes
 // back to EA_ALL while recent calls had more than 0.5 % of them (two_pass_ok in chi.cu).  EA_ALL is the single
 // launch with the branch, also for small batches.
 // (enum { EA_ALL, EA_TAME, EA_FIXUP }: moments.cuh)
